@@ -1,0 +1,21 @@
+"""adaptigraph_b200 — B200-native engine for AdaptiGraph's particle-graph dynamics hot path.
+
+Importing the compute API loads libadaptigraph_b200.so and fails loudly if it is missing.
+`adaptigraph_b200.synthetic` (workload generators) is importable without it.
+"""
+__all__ = ["DynamicsPredictor", "EdgeList", "build_edges", "construct_edges_from_states",
+           "construct_edges_from_states_batch", "edges_from_onehots", "pad_torch", "truncate_graph"]
+
+
+def __getattr__(name):
+    if name == "DynamicsPredictor":
+        from .model import DynamicsPredictor
+        return DynamicsPredictor
+    if name in ("EdgeList", "build_edges", "construct_edges_from_states", "construct_edges_from_states_batch",
+                "edges_from_onehots"):
+        from . import graph
+        return getattr(graph, name)
+    if name in ("pad_torch", "truncate_graph"):
+        from . import utils
+        return getattr(utils, name)
+    raise AttributeError(name)

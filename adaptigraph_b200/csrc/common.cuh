@@ -1,0 +1,85 @@
+// Shared host/device helpers for the adaptigraph_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/adaptigraph_b200.h"
+
+namespace agx {
+
+constexpr int FP = AGX_FP;          // padded feature stride (floats)
+constexpr int NFEAT = AGX_NFEAT;    // per-node relation-input record (floats)
+constexpr int H_FIX = 4;            // history frames the kernels are specialised for
+constexpr int D_NODE_IN = 8;        // node encoder input (6) padded to a multiple of 8
+constexpr int D_REL_IN = 24;        // relation encoder input (17) padded to a multiple of 8
+
+// ---- error plumbing (thread-local, no exceptions across the ABI)
+char* err_buf();
+int set_err(int code, const char* fmt, ...);
+int64_t& launch_counter();
+
+#define AGX_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return agx::set_err(AGX_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define AGX_LAUNCH_CHECK()                                                                  \
+  do {                                                                                      \
+    agx::launch_counter()++;                                                                \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess)                                                                  \
+      return agx::set_err(AGX_ERR_CUDA, "%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define AGX_REQUIRE(cond, code, ...)                                                        \
+  do {                                                                                      \
+    if (!(cond)) return agx::set_err(code, __VA_ARGS__);                                    \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Carves 256-byte aligned sub-buffers out of the caller's workspace.
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+int num_sms();
+
+// ---- optional per-kernel timing (agx_profile_*): CUDA events recorded on the launch stream
+// around every kernel, summed per kernel kind when read.  Off by default.
+struct ProfScope {
+  int kind;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr;
+  ProfScope(int kind, cudaStream_t st);
+  ~ProfScope();
+};
+
+// ---- packed weight blob (built by agx_pack_weights) -------------------------------------
+// Every matrix is stored k-major ("transposed"): Wt[k*FP + n] = W[n][col0 + k], zero padded to
+// [Kpad][FP]; biases are padded to FP floats.  Offsets are in floats.
+struct PackedLayout {
+  size_t penc0_w, penc0_b, penc2_w, penc2_b, penc4_w, penc4_b;
+  size_t renc0_w, renc0_b, renc2_w, renc2_b, renc4_w, renc4_b;
+  size_t rp_rel_w, rp_b, rp_recv_w, rp_send_w;   // relation_propagator split by operand
+  size_t pp_enc_w, pp_b, pp_agg_w;               // particle_propagator split by operand
+  size_t pred0_w, pred0_b, pred1_w, pred1_b;
+  size_t pred2_w, pred2_b;                       // pred2_w is row-major [3][FP]; pred2_b 4 floats
+  size_t total;
+};
+PackedLayout packed_layout();
+
+}  // namespace agx

@@ -1,0 +1,443 @@
+// Radius AND top-k directed relation builder emitting CSR-by-receiver edge lists.
+//
+// Replaces construct_edges_from_states_batch (reference dynamics/dataset/graph.py:91-156)
+// and construct_edges_from_states (:38-89).  The reference materialises B x N x N x 3
+// difference tensors, a B x N x N distance matrix, a top-k index tensor and two dense
+// B x n_rel x N one-hots; here nothing quadratic ever reaches HBM:
+//
+//   G0 tool_list     (only with connect_tools_all) ascending list of tool particles per graph
+//   G1 knn_rows      one warp per receiver: stream all senders of the graph from shared memory,
+//                    keep the k nearest in-radius ones in a warp-resident sorted list (one entry
+//                    per lane), bitonic-sort them by sender id, store <= k candidates per row
+//   G2 degrees_scan  per-row relation count after the tool rules (:134-144 / :77-80) + block scan
+//   G2b scan_blocks  scan of the block sums -> row offsets, total
+//   G3 fill_rows     merge candidates and tool senders in ascending sender order into send/recv
+//
+// Arithmetic follows the reference exactly: dis = (dx*dx + dy*dy) + dz*dz in fp32 without FMA
+// contraction (:109-110), radius test (dis - thr^2) < 0 (:125), pairs with an invalid endpoint or
+// tool-tool pairs excluded (:111-118).  Distance ties are broken towards the lower sender id
+// (torch.topk leaves the order of ties unspecified).
+#include "common.cuh"
+
+namespace agx {
+
+constexpr int G1_THREADS = 256;
+constexpr int G1_ROWS_PER_CTA = 64;
+constexpr int SCAN_BLOCK = 1024;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct GraphWs {
+  int32_t* cand;       // [B*N][topk]
+  int32_t* cnt;        // [B*N]   cnt | (non-tool cnt << 8)
+  int32_t* deg;        // [B*N]
+  int32_t* lpre;       // [B*N]   block-local exclusive prefix
+  int32_t* blk;        // [nblk]  block sums -> exclusive block offsets
+  int32_t* total;      // [1]
+  int32_t* flags;      // [B]     probe: some tool receiver kept a non-tool sender (graph.py:135)
+  int32_t* n_tools;    // [B]
+  int32_t* tools;      // [B*N]
+};
+
+static size_t graph_ws_carve(void* base, int B, int N, int topk, GraphWs* ws) {
+  Carver c(base);
+  size_t rows = (size_t)B * N;
+  size_t nblk = (rows + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  GraphWs w;
+  w.cand = c.take<int32_t>(rows * topk);
+  w.cnt = c.take<int32_t>(rows);
+  w.deg = c.take<int32_t>(rows);
+  w.lpre = c.take<int32_t>(rows);
+  w.blk = c.take<int32_t>(nblk + 1);
+  w.total = c.take<int32_t>(1);
+  w.flags = c.take<int32_t>(B);
+  w.n_tools = c.take<int32_t>(B);
+  w.tools = c.take<int32_t>(rows);
+  if (ws) *ws = w;
+  return align_up(c.off, 256);
+}
+
+// ------------------------------------------------------------------------------------ G0
+__global__ void __launch_bounds__(256) tool_list_kernel(const uint8_t* __restrict__ tool_mask, int N,
+                                                         int32_t* __restrict__ tools, int32_t* __restrict__ n_tools,
+                                                         int32_t* __restrict__ flags) {
+  __shared__ int warp_tot[8];
+  __shared__ int base_s;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { base_s = 0; flags[b] = 0; }
+  __syncthreads();
+  for (int j0 = 0; j0 < N; j0 += 256) {
+    int j = j0 + tid;
+    bool f = (j < N) && tool_mask[(size_t)b * N + j];
+    unsigned m = __ballot_sync(FULL, f);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int off = base_s;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (f) tools[(size_t)b * N + off + __popc(m & ((1u << lane) - 1))] = j;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += warp_tot[w];
+      base_s += t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) n_tools[b] = base_s;
+}
+
+// ------------------------------------------------------------------------------------ G1
+__global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
+    const float* __restrict__ pos, int64_t pos_stride_b, const uint8_t* __restrict__ mask,
+    const uint8_t* __restrict__ tool_mask, const float* __restrict__ thr2, int N, int topk, int probe_tools,
+    int32_t* __restrict__ cand, int32_t* __restrict__ cnt_out, int32_t* __restrict__ flags) {
+  extern __shared__ float smem[];
+  float* px = smem;
+  float* py = px + N;
+  float* pz = py + N;
+  uint8_t* fl = reinterpret_cast<uint8_t*>(pz + N);  // bit0 valid, bit1 tool
+
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* p = pos + (size_t)b * pos_stride_b;
+  for (int j = tid; j < N; j += G1_THREADS) {
+    px[j] = p[3 * j + 0];
+    py[j] = p[3 * j + 1];
+    pz[j] = p[3 * j + 2];
+    fl[j] = (mask[(size_t)b * N + j] ? 1 : 0) | (tool_mask[(size_t)b * N + j] ? 2 : 0);
+  }
+  __syncthreads();
+
+  const float t2 = thr2[b];
+  const int row_end = min(N, (int)(blockIdx.x + 1) * G1_ROWS_PER_CTA);
+  for (int i = blockIdx.x * G1_ROWS_PER_CTA + warp; i < row_end; i += G1_THREADS / 32) {
+    const int fi = fl[i];
+    float ld = __int_as_float(0x7f800000);  // +inf
+    int lj = 0x7fffffff;
+    int total = 0;
+    if (fi & 1) {
+      const float xi = px[i], yi = py[i], zi = pz[i];
+      const bool tool_i = fi & 2;
+      for (int j0 = 0; j0 < N; j0 += 32) {
+        const int j = j0 + lane;
+        bool ok = false;
+        float d = 0.f;
+        if (j < N) {
+          const int fj = fl[j];
+          const float dx = __fsub_rn(xi, px[j]), dy = __fsub_rn(yi, py[j]), dz = __fsub_rn(zi, pz[j]);
+          d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          ok = (fj & 1) && !(tool_i && (fj & 2)) && (__fsub_rn(d, t2) < 0.f);
+        }
+        unsigned m = __ballot_sync(FULL, ok);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const float dc = __shfl_sync(FULL, d, src);
+          const int jc = j0 + src;
+          const bool less = (ld < dc) || (ld == dc && lj < jc);
+          const int at = __popc(__ballot_sync(FULL, less));  // list is sorted: `less` lanes form a prefix
+          if (at < topk) {
+            const float ud = __shfl_up_sync(FULL, ld, 1);
+            const int uj = __shfl_up_sync(FULL, lj, 1);
+            if (lane == at) { ld = dc; lj = jc; }
+            else if (lane > at) { ld = ud; lj = uj; }
+          }
+          ++total;
+        }
+      }
+    }
+    const int cnt = min(total, topk);
+    int key = (lane < cnt) ? lj : 0x7fffffff;
+    // bitonic sort of the 32 lane keys, ascending sender id
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const int other = __shfl_xor_sync(FULL, key, stride);
+        const bool up = (lane & size) == 0;
+        const bool lower = (lane & stride) == 0;
+        key = (lower == up) ? min(key, other) : max(key, other);
+      }
+    }
+    const bool nontool = (lane < cnt) && !(fl[key < N ? key : 0] & 2);
+    const int nt = __popc(__ballot_sync(FULL, nontool));
+    const size_t row = (size_t)b * N + i;
+    if (lane < topk) cand[row * topk + lane] = key;
+    if (lane == 0) {
+      cnt_out[row] = cnt | (nt << 8);
+      if (probe_tools && (fi & 2) && cnt > 0) atomicOr(&flags[b], 1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ G2
+__device__ __forceinline__ int row_degree(int packed, bool valid, bool tool_i, int cta, int sem, int flag, int ntools,
+                                          bool* keep_base, bool* add_tools) {
+  const int cnt = packed & 0xff, nt = packed >> 8;
+  if (!cta) { *keep_base = true; *add_tools = false; return cnt; }
+  // graph.py:134-144 (batched) / :77-80 (single), see the derivation in DESIGN.md
+  *keep_base = !tool_i;
+  *add_tools = valid && (sem == AGX_SEM_BATCH ? (flag != 0) : !tool_i);
+  return (tool_i ? 0 : nt) + (*add_tools ? ntools : 0);
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) degrees_scan_kernel(
+    const int32_t* __restrict__ cnt, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ tool_mask,
+    const int32_t* __restrict__ flags, const int32_t* __restrict__ n_tools, int rows, int N, int cta, int sem,
+    int32_t* __restrict__ deg, int32_t* __restrict__ lpre, int32_t* __restrict__ blk) {
+  __shared__ int warp_sum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = blockIdx.x * SCAN_BLOCK + tid;
+  int d = 0;
+  if (r < rows) {
+    const int b = r / N;
+    bool kb, at;
+    d = row_degree(cnt[r], mask[r] != 0, tool_mask[r] != 0, cta, sem, cta ? flags[b] : 0, cta ? n_tools[b] : 0, &kb, &at);
+    deg[r] = d;
+  }
+  int incl = d;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, w, o);
+      if (lane >= o) w += v;
+    }
+    warp_sum[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  const int warp_off = warp ? warp_sum[warp - 1] : 0;
+  if (r < rows) lpre[r] = warp_off + incl - d;
+  if (tid == SCAN_BLOCK - 1) blk[blockIdx.x] = warp_off + incl;
+}
+
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(int32_t* __restrict__ blk, int nblk, int32_t* __restrict__ total,
+                                                            int32_t* __restrict__ row_ptr_end) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < nblk; i0 += 1024) {
+    const int i = i0 + tid;
+    const int v = i < nblk ? blk[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(FULL, w, o);
+        if (lane >= o) w += u;
+      }
+      warp_sum[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int excl = carry + (warp ? warp_sum[warp - 1] : 0) + incl - v;
+    if (i < nblk) blk[i] = excl;
+    __syncthreads();
+    if (tid == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) { *total = carry_s; *row_ptr_end = carry_s; }
+}
+
+// ------------------------------------------------------------------------------------ G3
+__global__ void __launch_bounds__(256) fill_rows_kernel(
+    const int32_t* __restrict__ cand, const int32_t* __restrict__ cnt, const int32_t* __restrict__ lpre,
+    const int32_t* __restrict__ blk, const int32_t* __restrict__ total, const uint8_t* __restrict__ mask,
+    const uint8_t* __restrict__ tool_mask, const int32_t* __restrict__ flags, const int32_t* __restrict__ n_tools,
+    const int32_t* __restrict__ tools, int rows, int N, int topk, int cta, int sem, int32_t* __restrict__ row_ptr,
+    int32_t* __restrict__ send, int32_t* __restrict__ recv, int64_t cap, int32_t* __restrict__ n_edges,
+    int32_t* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int b = r / N, n = r - b * N;
+  const int start = lpre[r] + blk[r / SCAN_BLOCK];
+  if (lane == 0) {
+    row_ptr[r] = start;
+    if (n == 0) {
+      const int r2 = r + N;
+      const int end = (r2 < rows) ? lpre[r2] + blk[r2 / SCAN_BLOCK] : *total;
+      n_edges[b] = end - start;
+    }
+  }
+  const int packed = cnt[r];
+  const int c = packed & 0xff;
+  const bool valid = mask[r] != 0, tool_i = tool_mask[r] != 0;
+  const int ntl = cta ? n_tools[b] : 0;
+  bool keep_base, add_tools;
+  const int deg = row_degree(packed, valid, tool_i, cta, sem, cta ? flags[b] : 0, ntl, &keep_base, &add_tools);
+  if (deg == 0) return;
+  bool overflow = false;
+  const int key = (lane < c) ? cand[(size_t)r * topk + lane] : 0x7fffffff;
+  if (!cta) {
+    if (lane < c) {
+      const int64_t o = (int64_t)start + lane;
+      if (o < cap) { send[o] = key; recv[o] = r; } else overflow = true;
+    }
+  } else {
+    const int32_t* tl = tools + (size_t)b * N;
+    const bool keep = (lane < c) && keep_base && !tool_mask[(size_t)b * N + key];
+    const unsigned km = __ballot_sync(FULL, keep);
+    if (keep) {
+      int o = __popc(km & ((1u << lane) - 1));
+      if (add_tools)
+        for (int t = 0; t < ntl; ++t) o += (tl[t] < key);
+      const int64_t oo = (int64_t)start + o;
+      if (oo < cap) { send[oo] = key; recv[oo] = r; } else overflow = true;
+    }
+    if (add_tools) {
+      for (int t0 = 0; t0 < ntl; t0 += 32) {
+        const int t = t0 + lane;
+        const int tj = (t < ntl) ? tl[t] : 0x7fffffff;
+        int below = 0;
+        for (int mth = 0; mth < 32; ++mth) {
+          const int am = __shfl_sync(FULL, key, mth);
+          below += (((km >> mth) & 1u) && am < tj);
+        }
+        if (t < ntl) {
+          const int64_t oo = (int64_t)start + t + below;
+          if (oo < cap) { send[oo] = tj; recv[oo] = r; } else overflow = true;
+        }
+      }
+    }
+  }
+  if (overflow) atomicOr(status, 1);
+}
+
+// ------------------------------------------------------------------------------------ dense one-hot <-> ids
+__global__ void __launch_bounds__(256) onehot_to_ids_kernel(const float* __restrict__ R, int64_t rows, int N,
+                                                             int32_t* __restrict__ ids) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* p = R + row * N;
+  int first = 0x7fffffff;
+  for (int j = lane; j < N; j += 32)
+    if (p[j] != 0.f) first = min(first, j);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(FULL, first, o));
+  if (lane == 0) ids[row] = (first == 0x7fffffff) ? -1 : first;
+}
+
+__global__ void __launch_bounds__(256) edges_to_onehot_kernel(const int32_t* __restrict__ row_ptr,
+                                                               const int32_t* __restrict__ send, int rows, int N,
+                                                               int n_rel, float* __restrict__ Rr, float* __restrict__ Rs) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= rows) return;
+  const int b = r / N, n = r - b * N;
+  const int base = row_ptr[(size_t)b * N];
+  for (int e = row_ptr[r]; e < row_ptr[r + 1]; ++e) {
+    const int el = e - base;
+    if (el < n_rel) {
+      Rr[((size_t)b * n_rel + el) * N + n] = 1.f;
+      Rs[((size_t)b * n_rel + el) * N + send[e]] = 1.f;
+    }
+  }
+}
+
+// Internal entry shared with the rollout driver (pos may be a strided view of the state history).
+int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask, const uint8_t* tool_mask,
+                     const float* thr2, int B, int N, int topk, int cta, int sem, int32_t* row_ptr, int32_t* send,
+                     int32_t* recv, int64_t cap, int32_t* n_edges, int32_t* status, void* workspace,
+                     size_t workspace_bytes, cudaStream_t st) {
+  AGX_REQUIRE(B > 0 && N > 0, AGX_ERR_ARG, "graph_build: B=%d N=%d must be positive", B, N);
+  AGX_REQUIRE(topk >= 1, AGX_ERR_ARG, "graph_build: topk=%d must be >= 1", topk);
+  topk = topk < N ? topk : N;  // graph.py:128
+  AGX_REQUIRE(topk <= AGX_MAX_TOPK, AGX_ERR_ARG, "graph_build: min(topk, N)=%d exceeds AGX_MAX_TOPK=%d", topk, AGX_MAX_TOPK);
+  AGX_REQUIRE((int64_t)B * N < (1ll << 31) - 1, AGX_ERR_ARG, "graph_build: B*N overflows int32");
+  AGX_REQUIRE(sem == AGX_SEM_BATCH || sem == AGX_SEM_SINGLE, AGX_ERR_ARG, "graph_build: bad semantics %d", sem);
+  GraphWs ws;
+  const size_t need = graph_ws_carve(workspace, B, N, topk, &ws);
+  AGX_REQUIRE(workspace && workspace_bytes >= need, AGX_ERR_CAPACITY, "graph_build: workspace %zu < %zu bytes",
+              workspace_bytes, need);
+  const size_t smem = (size_t)N * 13 + 16;
+  AGX_REQUIRE(smem <= 227 * 1024, AGX_ERR_ARG, "graph_build: N=%d exceeds the shared-memory staging limit", N);
+  static thread_local size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    AGX_CUDA_OK(cudaFuncSetAttribute(knn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int rows = B * N;
+  const int nblk = (rows + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  if (cta) {
+    { ProfScope ps(AGX_KIND_GRAPH_TOOLS, st);
+      tool_list_kernel<<<B, 256, 0, st>>>(tool_mask, N, ws.tools, ws.n_tools, ws.flags); }
+    AGX_LAUNCH_CHECK();
+  }
+  dim3 g1((N + G1_ROWS_PER_CTA - 1) / G1_ROWS_PER_CTA, B);
+  { ProfScope ps(AGX_KIND_GRAPH_KNN, st);
+    knn_rows_kernel<<<g1, G1_THREADS, smem, st>>>(pos, pos_stride_b, mask, tool_mask, thr2, N, topk,
+                                                   cta && sem == AGX_SEM_BATCH, ws.cand, ws.cnt, ws.flags); }
+  AGX_LAUNCH_CHECK();
+  { ProfScope ps(AGX_KIND_GRAPH_SCAN, st);
+    degrees_scan_kernel<<<nblk, SCAN_BLOCK, 0, st>>>(ws.cnt, mask, tool_mask, ws.flags, ws.n_tools, rows, N, cta, sem,
+                                                      ws.deg, ws.lpre, ws.blk); }
+  AGX_LAUNCH_CHECK();
+  { ProfScope ps(AGX_KIND_GRAPH_SCAN, st);
+    scan_blocks_kernel<<<1, 1024, 0, st>>>(ws.blk, nblk, ws.total, row_ptr + rows); }
+  AGX_LAUNCH_CHECK();
+  { ProfScope ps(AGX_KIND_GRAPH_FILL, st);
+    fill_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ws.cand, ws.cnt, ws.lpre, ws.blk, ws.total, mask, tool_mask, ws.flags,
+                                                      ws.n_tools, ws.tools, rows, N, topk, cta, sem, row_ptr, send, recv,
+                                                      cap, n_edges, status); }
+  AGX_LAUNCH_CHECK();
+  return AGX_OK;
+}
+
+}  // namespace agx
+
+extern "C" {
+
+size_t agx_graph_workspace_bytes(int32_t B, int32_t N, int32_t topk) {
+  if (B <= 0 || N <= 0 || topk <= 0) return 0;
+  topk = topk < N ? topk : N;
+  return agx::graph_ws_carve(nullptr, B, N, topk, nullptr);
+}
+
+int agx_graph_build(const float* pos, const uint8_t* mask, const uint8_t* tool_mask, const float* thr2, int32_t B,
+                    int32_t N, int32_t topk, int32_t connect_tools_all, int32_t semantics, int32_t* row_ptr,
+                    int32_t* send, int32_t* recv, int64_t cap, int32_t* n_edges, int32_t* status, void* workspace,
+                    size_t workspace_bytes, agx_stream_t stream) {
+  AGX_REQUIRE(pos && mask && tool_mask && thr2 && row_ptr && send && recv && n_edges && status, AGX_ERR_ARG,
+              "graph_build: null pointer argument");
+  return agx::graph_build_impl(pos, (int64_t)N * 3, mask, tool_mask, thr2, B, N, topk, connect_tools_all != 0, semantics,
+                               row_ptr, send, recv, cap, n_edges, status, workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int agx_onehot_to_ids(const float* R, int32_t B, int32_t n_rel, int32_t N, int32_t* ids, agx_stream_t stream) {
+  AGX_REQUIRE(R && ids && B > 0 && n_rel >= 0 && N > 0, AGX_ERR_ARG, "onehot_to_ids: bad arguments");
+  const int64_t rows = (int64_t)B * n_rel;
+  if (rows == 0) return AGX_OK;
+  { agx::ProfScope ps(AGX_KIND_OTHER, static_cast<cudaStream_t>(stream));
+    agx::onehot_to_ids_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(R, rows, N, ids); }
+  AGX_LAUNCH_CHECK();
+  return AGX_OK;
+}
+
+int agx_edges_to_onehot(const int32_t* row_ptr, const int32_t* send, int32_t B, int32_t N, int32_t n_rel, float* Rr,
+                        float* Rs, agx_stream_t stream) {
+  AGX_REQUIRE(row_ptr && send && Rr && Rs && B > 0 && N > 0 && n_rel >= 0, AGX_ERR_ARG, "edges_to_onehot: bad arguments");
+  const int rows = B * N;
+  agx::edges_to_onehot_kernel<<<(rows + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(row_ptr, send, rows, N,
+                                                                                                 n_rel, Rr, Rs);
+  AGX_LAUNCH_CHECK();
+  return AGX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,219 @@
+"""PyTorch custom ops over the C ABI (include/adaptigraph_b200.h).
+
+Each op validates shapes/dtypes/devices on the Python side, allocates outputs
+and the workspace from torch's caching allocator, and calls the library on the
+current CUDA stream through ctypes.  Nothing here computes: a CPU tensor is an
+error, not a fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+lib = L.lib
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Tensor) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts: Tensor) -> None:
+    for t in ts:
+        if not t.is_cuda:
+            raise RuntimeError("adaptigraph_b200 runs on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor of shape {tuple(t.shape)}")
+
+
+def _f32(t: Tensor) -> Tensor:
+    return t.to(torch.float32).contiguous()
+
+
+def _u8(t: Tensor) -> Tensor:
+    return t.to(torch.uint8).contiguous()
+
+
+def make_dims(F: int, n_his: int, d_attr: int, d_phys: int, d_act: int, pstep: int) -> L.AgxModelDims:
+    return L.AgxModelDims(F, n_his, d_attr, d_phys, d_act, pstep)
+
+
+def launch_count() -> int:
+    return int(lib.agx_launch_count())
+
+
+# --------------------------------------------------------------------------- weights
+@torch.library.custom_op("agx::pack_weights", mutates_args=())
+def pack_weights(weights: List[Tensor], biases: List[Tensor], n_his: int, d_attr: int, d_phys: int, d_act: int) -> Tensor:
+    """Pads, transposes and splits the 11 reference-layout Linear layers into the packed blob the kernels read."""
+    _need_cuda(*weights, *biases)
+    assert len(weights) == L.AGX_NUM_LAYERS and len(biases) == L.AGX_NUM_LAYERS
+    F = weights[1].shape[0]
+    dims = make_dims(F, n_his, d_attr, d_phys, d_act, 1)
+    ws = [_f32(w) for w in weights]
+    bs = [_f32(b) for b in biases]
+    raw = L.AgxWeights()
+    for i in range(L.AGX_NUM_LAYERS):
+        raw.weight[i] = ws[i].data_ptr()
+        raw.bias[i] = bs[i].data_ptr()
+    n = lib.agx_packed_weights_bytes(C.byref(dims))
+    out = torch.empty(n // 4, dtype=torch.float32, device=ws[0].device)
+    L.check(lib.agx_pack_weights(C.byref(dims), C.byref(raw), _ptr(out), _stream()), "agx_pack_weights")
+    return out
+
+
+@pack_weights.register_fake
+def _(weights, biases, n_his, d_attr, d_phys, d_act):
+    return weights[0].new_empty(1)
+
+
+# --------------------------------------------------------------------------- graph construction
+@torch.library.custom_op("agx::graph_build", mutates_args=())
+def graph_build(pos: Tensor, mask: Tensor, tool_mask: Tensor, thr2: Tensor, topk: int, connect_tools_all: bool,
+                semantics: int, cap: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """(B,N,3) positions -> CSR relations: row_ptr (B*N+1), send (cap), recv (cap), n_edges (B), status (1)."""
+    _need_cuda(pos, mask, tool_mask, thr2)
+    B, N, _ = pos.shape
+    pos, thr2 = _f32(pos), _f32(thr2)
+    mask, tool_mask = _u8(mask), _u8(tool_mask)
+    dev = pos.device
+    row_ptr = torch.empty(B * N + 1, dtype=torch.int32, device=dev)
+    send = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    recv = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    n_edges = torch.empty(B, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    nws = lib.agx_graph_workspace_bytes(B, N, topk)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    L.check(lib.agx_graph_build(_ptr(pos), _ptr(mask), _ptr(tool_mask), _ptr(thr2), B, N, topk, int(connect_tools_all),
+                                semantics, _ptr(row_ptr), _ptr(send), _ptr(recv), cap, _ptr(n_edges), _ptr(status),
+                                _ptr(ws), nws, _stream()), "agx_graph_build")
+    return row_ptr, send, recv, n_edges, status
+
+
+@graph_build.register_fake
+def _(pos, mask, tool_mask, thr2, topk, connect_tools_all, semantics, cap):
+    B, N, _ = pos.shape
+    i32 = dict(dtype=torch.int32, device=pos.device)
+    return (torch.empty(B * N + 1, **i32), torch.empty(max(cap, 1), **i32), torch.empty(max(cap, 1), **i32),
+            torch.empty(B, **i32), torch.empty(1, **i32))
+
+
+@torch.library.custom_op("agx::onehot_to_ids", mutates_args=())
+def onehot_to_ids(R: Tensor) -> Tensor:
+    """Dense one-hot relation rows (B, n_rel, N) -> int32 (B, n_rel) particle id per row, -1 for all-zero rows."""
+    _need_cuda(R)
+    R = _f32(R)
+    B, n_rel, N = R.shape
+    ids = torch.empty(B, n_rel, dtype=torch.int32, device=R.device)
+    if n_rel:
+        L.check(lib.agx_onehot_to_ids(_ptr(R), B, n_rel, N, _ptr(ids), _stream()), "agx_onehot_to_ids")
+    return ids
+
+
+@onehot_to_ids.register_fake
+def _(R):
+    return R.new_empty(R.shape[:2], dtype=torch.int32)
+
+
+@torch.library.custom_op("agx::edges_to_onehot", mutates_args=())
+def edges_to_onehot(row_ptr: Tensor, send: Tensor, B: int, N: int, n_rel: int) -> Tuple[Tensor, Tensor]:
+    """CSR relations -> the reference's dense (B, n_rel, N) Rr, Rs (graph.py:152-155)."""
+    _need_cuda(row_ptr, send)
+    Rr = torch.zeros(B, n_rel, N, dtype=torch.float32, device=row_ptr.device)
+    Rs = torch.zeros(B, n_rel, N, dtype=torch.float32, device=row_ptr.device)
+    if n_rel:
+        L.check(lib.agx_edges_to_onehot(_ptr(row_ptr), _ptr(send), B, N, n_rel, _ptr(Rr), _ptr(Rs), _stream()),
+                "agx_edges_to_onehot")
+    return Rr, Rs
+
+
+@edges_to_onehot.register_fake
+def _(row_ptr, send, B, N, n_rel):
+    return (row_ptr.new_empty((B, n_rel, N), dtype=torch.float32), row_ptr.new_empty((B, n_rel, N), dtype=torch.float32))
+
+
+# --------------------------------------------------------------------------- forward / rollout
+@torch.library.custom_op("agx::forward", mutates_args=())
+def forward(packed: Tensor, state: Tensor, attrs: Tensor, action: Tensor, p_instance: Tensor, physics: Tensor,
+            row_ptr: Tensor, send: Tensor, recv: Tensor, F: int, pstep: int, precision: int) -> Tuple[Tensor, Tensor]:
+    """DynamicsPredictor.forward on CSR relations -> (pred_pos, pred_motion), each (B, n_p, 3)."""
+    _need_cuda(packed, state, attrs, action, p_instance, physics, row_ptr, send, recv)
+    B, H, N, _ = state.shape
+    n_p = p_instance.shape[1]
+    state, attrs, action, physics = _f32(state), _f32(attrs), _f32(action), _f32(physics)
+    p_inst = _f32(p_instance.reshape(B, n_p, -1)[:, :, 0])
+    dims = make_dims(F, H, attrs.shape[2], physics.shape[1], action.shape[2], pstep)
+    E_cap = int(send.numel())
+    g = L.AgxGraphIn(B, N, n_p, state.data_ptr(), attrs.data_ptr(), action.data_ptr(), p_inst.data_ptr(),
+                     physics.data_ptr(), row_ptr.data_ptr(), send.data_ptr(), recv.data_ptr(), E_cap)
+    dev = state.device
+    pred_pos = torch.empty(B, n_p, 3, dtype=torch.float32, device=dev)
+    pred_motion = torch.empty(B, n_p, 3, dtype=torch.float32, device=dev)
+    nws = lib.agx_forward_workspace_bytes(C.byref(dims), B, N, E_cap)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    L.check(lib.agx_forward(C.byref(dims), _ptr(packed), C.byref(g), _ptr(pred_pos), n_p * 3, _ptr(pred_motion),
+                            precision, _ptr(ws), nws, _stream()), "agx_forward")
+    return pred_pos, pred_motion
+
+
+@forward.register_fake
+def _(packed, state, attrs, action, p_instance, physics, row_ptr, send, recv, F, pstep, precision):
+    B, n_p = p_instance.shape[0], p_instance.shape[1]
+    return state.new_empty((B, n_p, 3)), state.new_empty((B, n_p, 3))
+
+
+@torch.library.custom_op("agx::rollout", mutates_args=("state",))
+def rollout(packed: Tensor, state: Tensor, attrs: Tensor, action: Tensor, p_instance: Tensor, physics: Tensor,
+            mask: Tensor, tool_mask: Tensor, thr2: Tensor, F: int, pstep: int, topk: int, connect_tools_all: bool,
+            n_steps: int, y_mode: int, gripper_raise: float, E_cap: int, precision: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """T autoregressive steps on device; `state` (B,H,N,3) is advanced in place.
+    Returns pred_seq (B,T,n_p,3), n_edges (T,B) int32, status (1) int32."""
+    _need_cuda(packed, state, attrs, action, p_instance, physics, mask, tool_mask, thr2)
+    if state.dtype != torch.float32 or not state.is_contiguous():
+        raise ValueError("rollout: state must be a contiguous float32 tensor (it is updated in place)")
+    B, H, N, _ = state.shape
+    n_p = p_instance.shape[1]
+    attrs, action, physics, thr2 = _f32(attrs), _f32(action), _f32(physics), _f32(thr2)
+    p_inst = _f32(p_instance.reshape(B, n_p, -1)[:, :, 0])
+    mask, tool_mask = _u8(mask), _u8(tool_mask)
+    dims = make_dims(F, H, attrs.shape[2], physics.shape[1], action.shape[2], pstep)
+    r = L.AgxRolloutIn(B, N, n_p, state.data_ptr(), attrs.data_ptr(), action.data_ptr(), p_inst.data_ptr(),
+                       physics.data_ptr(), mask.data_ptr(), tool_mask.data_ptr(), thr2.data_ptr(), topk,
+                       int(connect_tools_all), n_steps, y_mode, gripper_raise, E_cap)
+    dev = state.device
+    pred_seq = torch.empty(B, n_steps, n_p, 3, dtype=torch.float32, device=dev)
+    n_edges = torch.empty(n_steps, B, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    nws = lib.agx_rollout_workspace_bytes(C.byref(dims), B, N, E_cap, topk)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    L.check(lib.agx_rollout(C.byref(dims), _ptr(packed), C.byref(r), _ptr(pred_seq), _ptr(n_edges), _ptr(status),
+                            precision, _ptr(ws), nws, _stream()), "agx_rollout")
+    return pred_seq, n_edges, status
+
+
+@rollout.register_fake
+def _(packed, state, attrs, action, p_instance, physics, mask, tool_mask, thr2, F, pstep, topk, connect_tools_all,
+      n_steps, y_mode, gripper_raise, E_cap, precision):
+    B, n_p = p_instance.shape[0], p_instance.shape[1]
+    return (state.new_empty((B, n_steps, n_p, 3)), state.new_empty((n_steps, B), dtype=torch.int32),
+            state.new_empty((1,), dtype=torch.int32))
+
+
+# --------------------------------------------------------------------------- per-kernel timing (bench.py)
+def profile_enable(on: bool) -> None:
+    L.check(lib.agx_profile_enable(int(on)), "agx_profile_enable")
+
+
+def profile_read() -> dict:
+    """{kernel kind: (total ms, launches)} accumulated since the last read (synchronises on the recorded events)."""
+    ms = (C.c_double * L.AGX_NUM_KINDS)()
+    cnt = (C.c_int64 * L.AGX_NUM_KINDS)()
+    L.check(lib.agx_profile_read(ms, cnt), "agx_profile_read")
+    return {lib.agx_kind_name(i).decode(): (ms[i], cnt[i]) for i in range(L.AGX_NUM_KINDS) if cnt[i]}

@@ -96,6 +96,14 @@ class Workload:
                 setattr(out, k, v.to(device))
         return out
 
+    def take(self, sl) -> "Workload":
+        """Sub-batch (slice or index tensor over graphs)."""
+        out = copy.copy(self)
+        for k, v in vars(self).items():
+            if torch.is_tensor(v):
+                setattr(out, k, v[sl])
+        return out
+
     def graph_dict(self, Rr=None, Rs=None) -> Dict[str, torch.Tensor]:
         d = {
             "state": self.state, "action": self.action, "attrs": self.attrs,

@@ -1,0 +1,188 @@
+/*
+ * adaptigraph_b200 — C ABI of the B200-native particle-graph dynamics engine.
+ *
+ * Drop-in boundary for ONE hot path of Boey-li/AdaptiGraph (reference paths are
+ * relative to the reference's src/):
+ *
+ *   graph construction   dynamics/dataset/graph.py:38-89 (single), :91-156 (batched)
+ *   model forward        dynamics/gnn/model.py:129-313
+ *   rollout step         planning/forward_dynamics.py:156-197 (and :351-393)
+ *   pad / truncate       dynamics/utils.py:37-46, :127-137
+ *
+ * The reference exposes no FFI on this path (its boundary is three Python call
+ * signatures); these entry points are what a ctypes binding on the
+ * reference side attaches to.  Conventions:
+ *
+ *   - extern "C", plain pointers and sizes only.  Every pointer is a DEVICE pointer
+ *     unless its name ends in _host.  The caller owns every buffer, including the
+ *     workspace; the library holds no persistent device allocations.
+ *   - All calls are asynchronous and ordered on `stream` (a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream).  No call synchronises the device.
+ *   - Return 0 on success; AGX_ERR_* (<0) otherwise, with a thread-local message from
+ *     agx_last_error().  Edge-capacity overflow inside a kernel cannot be returned
+ *     synchronously: it is reported through the `status` device word (see
+ *     agx_graph_build) which the caller reads when it next synchronises.
+ *   - Feature rows are fp32 with an internal padded stride AGX_FP (=160 floats,
+ *     640 B = five 128-B lines); the padding never leaves the library.
+ *   - Relations are CSR by receiver over the flattened node index r = b*N + n:
+ *     row_ptr int32 [B*N+1], send int32 [E] (sender id LOCAL to its graph), and the
+ *     expanded receiver list recv int32 [E] (flattened id).  Rows appear in the
+ *     reference's order: (graph, receiver, sender) ascending (graph.py:151-155).
+ */
+#ifndef ADAPTIGRAPH_B200_H
+#define ADAPTIGRAPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGX_VERSION 100          /* 0.1.0 */
+#define AGX_FP 160               /* padded feature stride (floats) */
+#define AGX_MAX_TOPK 32          /* graph builder keeps one candidate per warp lane */
+#define AGX_NFEAT 16             /* per-node relation-input record: hist(12) attr(2) group(1) pad(1) */
+
+#define AGX_OK 0
+#define AGX_ERR_ARG (-1)         /* bad argument / unsupported shape */
+#define AGX_ERR_CAPACITY (-2)    /* workspace or edge capacity too small (pad_torch's failure, utils.py:37-46) */
+#define AGX_ERR_CUDA (-3)        /* CUDA runtime error, see agx_last_error() */
+
+/* graph-builder semantics */
+#define AGX_SEM_BATCH 0          /* construct_edges_from_states_batch, graph.py:91-156 */
+#define AGX_SEM_SINGLE 1         /* construct_edges_from_states,       graph.py:38-89  */
+
+/* rollout tool-height rule */
+#define AGX_Y_MIN 0              /* y = min_n pred[n].y           forward_dynamics.py:163 */
+#define AGX_Y_MASKED_MEAN 1      /* y = masked mean of pred[n].y  forward_dynamics.py:359 */
+
+/* arithmetic of the dense 150x150 layers */
+#define AGX_PREC_FP32 0          /* exact fp32 FFMA tiles */
+#define AGX_PREC_3XTF32 1        /* tcgen05 kind::tf32, hi/lo operand split, fp32 accumulate in TMEM */
+
+#if defined(__GNUC__)
+#define AGX_API __attribute__((visibility("default")))
+#else
+#define AGX_API
+#endif
+
+typedef void* agx_stream_t;
+
+/* Model dimensions (DynamicsPredictor.__init__, model.py:77-122). */
+typedef struct AgxModelDims {
+  int32_t F;        /* nf_particle = nf_relation = nf_effect (<= 160; 150 in every shipped config) */
+  int32_t n_his;    /* history frames H (4) */
+  int32_t d_attr;   /* attr_dim (2) */
+  int32_t d_phys;   /* number of physics params in use (1) */
+  int32_t d_act;    /* action_dim (3) */
+  int32_t pstep;    /* propagation steps K */
+} AgxModelDims;
+
+/* Reference-layout parameters, row-major [out][in] fp32 exactly as in the state_dict
+ * (model.py:103-122).  Index order: */
+enum {
+  AGX_W_PENC0 = 0, AGX_W_PENC2, AGX_W_PENC4,   /* particle_encoder.model.{0,2,4} */
+  AGX_W_RENC0, AGX_W_RENC2, AGX_W_RENC4,       /* relation_encoder.model.{0,2,4} */
+  AGX_W_PPROP,                                 /* particle_propagator.linear (F x 2F) */
+  AGX_W_RPROP,                                 /* relation_propagator.linear (F x 3F) */
+  AGX_W_PRED0, AGX_W_PRED1, AGX_W_PRED2,       /* non_rigid_predictor.linear_{0,1,2} */
+  AGX_NUM_LAYERS
+};
+typedef struct AgxWeights {
+  const float* weight[AGX_NUM_LAYERS];
+  const float* bias[AGX_NUM_LAYERS];
+} AgxWeights;
+
+/* One batch of graphs (the reference's graph dict, forward_dynamics.py:130-147). */
+typedef struct AgxGraphIn {
+  int32_t B, N, n_p;       /* graphs, particles per graph (object + tool), object particles */
+  const float* state;      /* (B, H, N, 3) */
+  const float* attrs;      /* (B, N, d_attr) */
+  const float* action;     /* (B, N, 3) */
+  const float* p_instance; /* (B, n_p) — single instance column (max_n = 1 in every shipped config) */
+  const float* physics;    /* (B, d_phys) */
+  const int32_t* row_ptr;  /* (B*N + 1) */
+  const int32_t* send;     /* (E) */
+  const int32_t* recv;     /* (E) */
+  int64_t E_cap;           /* upper bound on E used to size the workspace (E itself is row_ptr[B*N], read on device) */
+} AgxGraphIn;
+
+AGX_API int agx_version(void);
+AGX_API const char* agx_last_error(void);
+
+/* ---- weights: pad / transpose / split the propagator matrices once per parameter update */
+AGX_API size_t agx_packed_weights_bytes(const AgxModelDims* dims);
+AGX_API int agx_pack_weights(const AgxModelDims* dims, const AgxWeights* raw, void* packed, agx_stream_t stream);
+
+/* ---- graph construction (replaces graph.py:38-156) */
+AGX_API size_t agx_graph_workspace_bytes(int32_t B, int32_t N, int32_t topk);
+/* pos (B,N,3); mask, tool_mask (B,N) uint8; thr2 (B) = squared radius per graph.
+ * Writes row_ptr (B*N+1), send/recv (up to cap entries), n_edges (B) per-graph counts.
+ * status: one int32 device word, OR-ed with 1 if the total edge count exceeded cap
+ * (entries beyond cap are dropped, row_ptr still holds the true counts). */
+AGX_API int agx_graph_build(const float* pos, const uint8_t* mask, const uint8_t* tool_mask, const float* thr2,
+                    int32_t B, int32_t N, int32_t topk, int32_t connect_tools_all, int32_t semantics,
+                    int32_t* row_ptr, int32_t* send, int32_t* recv, int64_t cap, int32_t* n_edges,
+                    int32_t* status, void* workspace, size_t workspace_bytes, agx_stream_t stream);
+
+/* Dense one-hot relations (B, n_rel, N) -> per-row receiver / sender ids (-1 on all-zero rows),
+ * the conversion the drop-in forward() applies when it is handed Rr / Rs (model.py:129). */
+AGX_API int agx_onehot_to_ids(const float* R, int32_t B, int32_t n_rel, int32_t N, int32_t* ids, agx_stream_t stream);
+/* CSR -> dense one-hot rows (graph.py:152-155): Rr, Rs (B, n_rel, N) must be zero-filled by the caller. */
+AGX_API int agx_edges_to_onehot(const int32_t* row_ptr, const int32_t* send, int32_t B, int32_t N, int32_t n_rel,
+                        float* Rr, float* Rs, agx_stream_t stream);
+
+/* ---- model forward (replaces model.py:129-313) */
+AGX_API size_t agx_forward_workspace_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap);
+/* pred_pos, pred_motion: (B, n_p, 3).  pos_stride_b: floats between consecutive graphs in
+ * pred_pos (n_p*3 for a dense (B,n_p,3) tensor; T*n_p*3 when writing step t of a (B,T,n_p,3) rollout). */
+AGX_API int agx_forward(const AgxModelDims* dims, const void* packed_weights, const AgxGraphIn* g,
+                float* pred_pos, int64_t pos_stride_b, float* pred_motion,
+                int32_t precision, void* workspace, size_t workspace_bytes, agx_stream_t stream);
+
+/* ---- autoregressive rollout (replaces the loop of forward_dynamics.py:156-197) */
+typedef struct AgxRolloutIn {
+  int32_t B, N, n_p;
+  float* state;              /* (B, H, N, 3): in = initial history, out = history after the last step */
+  const float* attrs;        /* (B, N, d_attr) */
+  const float* action;       /* (B, N, 3) — constant over the rollout (forward_dynamics.py:180) */
+  const float* p_instance;   /* (B, n_p) */
+  const float* physics;      /* (B, d_phys) */
+  const uint8_t* mask;       /* (B, N) state_mask */
+  const uint8_t* tool_mask;  /* (B, N) eef_mask */
+  const float* thr2;         /* (B) */
+  int32_t topk, connect_tools_all;
+  int32_t n_steps;           /* T */
+  int32_t y_mode;            /* AGX_Y_MIN / AGX_Y_MASKED_MEAN */
+  float gripper_raise;       /* 0.01*sim_real_ratio when gripper_enable (forward_dynamics.py:167-168), else 0 */
+  int64_t E_cap;             /* max relations per batch the workspace is sized for (B * max_nR) */
+} AgxRolloutIn;
+AGX_API size_t agx_rollout_workspace_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap, int32_t topk);
+/* pred_seq (B, T, n_p, 3); n_edges_seq (T, B) int32 per-step per-graph relation counts (nullable);
+ * status as in agx_graph_build. */
+AGX_API int agx_rollout(const AgxModelDims* dims, const void* packed_weights, const AgxRolloutIn* r,
+                float* pred_seq, int32_t* n_edges_seq, int32_t* status,
+                int32_t precision, void* workspace, size_t workspace_bytes, agx_stream_t stream);
+
+/* ---- per-kernel timing for bench.py's roofline block.  When enabled, every kernel launched by the
+ * calling thread is bracketed by CUDA events on its launch stream; agx_profile_read synchronises on
+ * those events and ADDS elapsed milliseconds / launch counts per kernel kind into ms[] / count[]
+ * (arrays of AGX_NUM_KINDS), then forgets the recorded events. */
+enum {
+  AGX_KIND_GRAPH_TOOLS = 0, AGX_KIND_GRAPH_KNN, AGX_KIND_GRAPH_SCAN, AGX_KIND_GRAPH_FILL,
+  AGX_KIND_NODE_ENCODER, AGX_KIND_EDGE_ENCODER, AGX_KIND_EDGE_AGGREGATE, AGX_KIND_NODE_UPDATE,
+  AGX_KIND_NODE_HEAD, AGX_KIND_ROLLOUT_ADVANCE, AGX_KIND_OTHER, AGX_NUM_KINDS
+};
+AGX_API int agx_profile_enable(int32_t on);
+AGX_API int agx_profile_read(double* ms, int64_t* count);
+AGX_API const char* agx_kind_name(int32_t kind);
+
+/* Cumulative number of kernel launches issued through this library by the calling thread
+ * (bench.py differences it around the timed region for gpu_launches). */
+AGX_API int64_t agx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADAPTIGRAPH_B200_H */

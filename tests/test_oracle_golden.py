@@ -123,3 +123,23 @@ def test_init_matches_reference_constructor_order():
     names = list(orc.PARAM_SHAPES(6, 17, 150).keys())
     for lyr, nm in zip(layers, names):
         assert torch.equal(lyr.weight.detach(), gw[nm + ".weight"]), nm
+
+
+@pytest.mark.parametrize("name", H.graph_case_names(CASES))
+def test_c_graph_oracle_matches_reference(name):
+    from oracle import build_oracle
+    c = {k.split("/", 1)[1]: v for k, v in CASES.items() if k.startswith(name + "/")}
+    thr = np.float32(c["adj_thresh"])
+    B, N = c["mask"].shape
+    recv, send, n_edges = build_oracle.edges(c["pos"], c["mask"], c["tool_mask"], thr * thr, int(c["topk"]), bool(c["cta"]), 0)
+    off = 0
+    for b in range(B):
+        n = int(n_edges[b])
+        assert n == int((c["batch_recv"][b] >= 0).sum())
+        assert np.array_equal(recv[off:off + n], c["batch_recv"][b, :n]) and np.array_equal(send[off:off + n], c["batch_send"][b, :n])
+        off += n
+    if f"single_recv_0" in c:
+        t2 = np.float32(float(c["adj_thresh"]) * float(c["adj_thresh"]))
+        for b in range(B):
+            r1, s1, _ = build_oracle.edges(c["pos"][b:b + 1], c["mask"][b:b + 1], c["tool_mask"][b:b + 1], t2, int(c["topk"]), bool(c["cta"]), 1)
+            assert np.array_equal(r1, c[f"single_recv_{b}"]) and np.array_equal(s1, c[f"single_send_{b}"])

@@ -1,0 +1,205 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the golden vectors produced by
+the reference and against the CPU oracle on seeded inputs.  Run with `-m gpu` on the B200 box."""
+import numpy as np
+import pytest
+import torch
+
+import agx_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+CASES = H.load_npz("graph_cases.npz")
+FWD = ["forward_rope100_k1.npz", "forward_cloth64_pad_k3.npz", "forward_granular120_k3.npz", "forward_rope300_k4.npz"]
+FWD_TOL = 1e-5      # max-abs on pred_pos / pred_motion, fp32 FFMA path
+ROLL_RMSE = 1e-4    # north_star: RMSE of predicted positions over a 10-step rollout
+
+
+@pytest.fixture(scope="module")
+def agx():
+    import adaptigraph_b200 as pkg
+    import adaptigraph_b200.ops  # noqa: F401  (loads the .so; raises if missing)
+    assert torch.cuda.is_available()
+    return pkg
+
+
+def _model(agx, material, pstep):
+    from adaptigraph_b200 import synthetic as syn
+    m = agx.DynamicsPredictor(*syn.configs(material, pstep), "cuda")
+    m.load_state_dict(H.golden_weights())
+    return m.cuda().eval()
+
+
+def _case(name):
+    return {k.split("/", 1)[1]: v for k, v in CASES.items() if k.startswith(name + "/")}
+
+
+def _edge_lists(el, n_rel_pad):
+    """EdgeList -> (B, n_rel_pad) receiver / sender ids, -1 padded, as the golden files store them."""
+    B, N = el.B, el.N
+    rp = el.row_ptr.cpu().long()
+    send = el.send.cpu().long()
+    recv = el.recv.cpu().long()
+    r = np.full((B, n_rel_pad), -1, np.int32)
+    s = np.full((B, n_rel_pad), -1, np.int32)
+    for b in range(B):
+        lo, hi = int(rp[b * N]), int(rp[(b + 1) * N])
+        assert hi - lo == int(el.n_edges[b])
+        r[b, :hi - lo] = (recv[lo:hi] - b * N).numpy()
+        s[b, :hi - lo] = send[lo:hi].numpy()
+    return r, s
+
+
+@pytest.mark.parametrize("name", H.graph_case_names(CASES))
+def test_graph_build_batch_exact(agx, name):
+    c = _case(name)
+    pos = torch.from_numpy(c["pos"]).cuda()
+    mask, tool = torch.from_numpy(c["mask"]).cuda(), torch.from_numpy(c["tool_mask"]).cuda()
+    thr = torch.from_numpy(c["adj_thresh"]).cuda() if bool(c["thr_is_tensor"]) else float(c["adj_thresh"])
+    el = agx.build_edges(pos, thr, mask, tool, int(c["topk"]), bool(c["cta"])).check()
+    r, s = _edge_lists(el, c["batch_recv"].shape[1])
+    assert np.array_equal(r, c["batch_recv"]) and np.array_equal(s, c["batch_send"])
+    # drop-in dense return equals the reference's one-hots
+    Rr, Rs = agx.construct_edges_from_states_batch(pos, thr, mask, tool, topk=int(c["topk"]), connect_tools_all=bool(c["cta"]))
+    Rr_ref, Rs_ref = H.onehots_from_lists(c["batch_recv"], c["batch_send"], pos.shape[1])
+    assert torch.equal(Rr.cpu(), Rr_ref) and torch.equal(Rs.cpu(), Rs_ref)
+    # and converts back to the same edge list
+    el2 = agx.edges_from_onehots(Rr, Rs)
+    n = int(el.row_ptr[-1])
+    assert torch.equal(el2.row_ptr, el.row_ptr) and torch.equal(el2.send[:n], el.send[:n]) and torch.equal(el2.recv[:n], el.recv[:n])
+
+
+@pytest.mark.parametrize("name", [n for n in H.graph_case_names(CASES) if f"{n}/single_recv_0" in CASES])
+def test_graph_build_single_exact(agx, name):
+    c = _case(name)
+    pos = torch.from_numpy(c["pos"]).cuda()
+    mask, tool = torch.from_numpy(c["mask"]).cuda(), torch.from_numpy(c["tool_mask"]).cuda()
+    for b in range(pos.shape[0]):
+        Rr, Rs = agx.construct_edges_from_states(pos[b], float(c["adj_thresh"]), mask[b], tool[b], topk=int(c["topk"]),
+                                                 connect_tools_all=bool(c["cta"]))
+        r, s = H.lists_from_onehots(Rr[None].cpu(), Rs[None].cpu())
+        assert np.array_equal(r[0].numpy(), c[f"single_recv_{b}"]) and np.array_equal(s[0].numpy(), c[f"single_send_{b}"])
+
+
+def test_graph_build_capacity_overflow_is_reported(agx):
+    c = _case("granular150")
+    pos = torch.from_numpy(c["pos"]).cuda()
+    mask, tool = torch.from_numpy(c["mask"]).cuda(), torch.from_numpy(c["tool_mask"]).cuda()
+    el = agx.build_edges(pos, float(c["adj_thresh"]), mask, tool, int(c["topk"]), False, max_nR=100)
+    with pytest.raises(RuntimeError, match="capacity"):
+        el.check()
+    assert int(el.n_edges.max()) == c["batch_recv"].shape[1]   # true counts are still reported
+
+
+@pytest.mark.parametrize("fname", FWD)
+@pytest.mark.parametrize("path", ["dense", "edges"])
+def test_forward_matches_reference(agx, fname, path):
+    g = H.load_npz(fname)
+    m = _model(agx, str(g["material"]), int(g["pstep"]))
+    t = lambda k: torch.from_numpy(g[k]).cuda()  # noqa: E731
+    N = g["attrs"].shape[1]
+    kw = {f"{g['material']}_physics_param": t("physics_param"), "p_rigid": torch.zeros(1).cuda()}
+    with torch.no_grad():
+        if path == "dense":
+            Rr, Rs = H.onehots_from_lists(g["recv"], g["send"], N)
+            pos, motion = m(t("state"), t("attrs"), Rr.cuda(), Rs.cuda(), t("p_instance"), action=t("action"), **kw)
+        else:
+            from adaptigraph_b200 import synthetic as syn
+            thr, topk, cta, _ = syn.MATERIALS[str(g["material"])]
+            el = agx.build_edges(t("state")[:, -1], thr, t("mask"), t("tool_mask"), topk, cta).check()
+            pos, motion = m(t("state"), t("attrs"), None, None, t("p_instance"), action=t("action"), edges=el, **kw)
+    assert np.abs(pos.cpu().numpy() - g["pred_pos"]).max() <= FWD_TOL
+    assert np.abs(motion.cpu().numpy() - g["pred_motion"]).max() <= FWD_TOL
+
+
+@pytest.mark.parametrize("fname", ["rollout_rope60_T10.npz", "rollout_cloth49_T10.npz", "rollout_granular80_T5.npz"])
+def test_rollout_matches_reference(agx, fname):
+    from adaptigraph_b200 import synthetic as syn
+    g = H.load_npz(fname)
+    mat = str(g["material"])
+    thr, topk, cta, _ = syn.MATERIALS[mat]
+    m = _model(agx, mat, int(g["pstep"]))
+    t = lambda k: torch.from_numpy(g[k]).cuda()  # noqa: E731
+    T = g["preds"].shape[1]
+    state0 = t("state")
+    out = m.rollout(state0, t("attrs"), t("action"), t("p_instance"), t("physics_param"), t("mask"), t("tool_mask"),
+                    thr, topk, cta, T, max_nR=g["recv"].shape[2])
+    assert torch.equal(state0.cpu(), torch.from_numpy(g["state"]))          # caller's history untouched
+    n_ref = (g["recv"] >= 0).sum(-1).T                                      # (T, B)
+    assert np.array_equal(out["n_edges"].cpu().numpy(), n_ref)              # same relation count at every step
+    err = out["state_seqs"].cpu().numpy() - g["preds"]
+    assert np.sqrt((err ** 2).mean()) <= ROLL_RMSE
+    assert np.abs(err).max() <= 1e-4
+    # the final history holds the last H predictions for object particles
+    n_p = g["preds"].shape[2]
+    assert np.abs(out["state"][:, -1, :n_p].cpu().numpy() - g["preds"][:, -1]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("material,n_p,B,pstep", [("cloth", 400, 5, 3), ("granular", 333, 3, 2), ("rope", 513, 2, 1)])
+def test_forward_matches_oracle_on_seeded_inputs(agx, material, n_p, B, pstep):
+    """Sizes the dense CPU oracle finishes in seconds; tiles straddle graphs and are ragged."""
+    from adaptigraph_b200 import synthetic as syn
+    from oracle import dynamics_oracle as orc
+    w = syn.make_workload(material, n_p, B, seed=77, n_pad=3)
+    p = H.golden_weights()
+    Rr, Rs = orc.edges_dense_batch(w.state[:, -1], w.adj_thresh, w.state_mask, w.eef_mask, w.topk, w.connect_tools_all)
+    ref_pos, ref_motion = orc.forward_dense(p, pstep, w.state, w.attrs, Rr, Rs, w.p_instance, w.action, w.physics_param)
+    m = _model(agx, material, pstep)
+    wd = w.to("cuda")
+    el = agx.build_edges(wd.state[:, -1], w.adj_thresh, wd.state_mask, wd.eef_mask, w.topk, w.connect_tools_all).check()
+    r_ref, s_ref = H.lists_from_onehots(Rr, Rs)
+    r, s = _edge_lists(el, Rr.shape[1])
+    assert np.array_equal(r, r_ref.numpy()) and np.array_equal(s, s_ref.numpy())
+    with torch.no_grad():
+        pos, motion = m(**wd.graph_dict(), edges=el)
+    assert (pos.cpu() - ref_pos).abs().max() <= FWD_TOL
+    assert (motion.cpu() - ref_motion).abs().max() <= FWD_TOL
+
+
+def test_graph_without_relations_and_single_particle_tiles(agx):
+    """Empty relation set (radius below every pair distance except self excluded by topk... here: all
+    particles invalid but one) and B*N smaller than one tile."""
+    from adaptigraph_b200 import synthetic as syn
+    from oracle import dynamics_oracle as orc
+    w = syn.make_workload("rope", 9, 2, seed=5)
+    w.state_mask[:] = False          # no valid particle -> no relation at all (graph.py:111-114)
+    p = H.golden_weights()
+    Rr, Rs = orc.edges_dense_batch(w.state[:, -1], w.adj_thresh, w.state_mask, w.eef_mask, w.topk, False)
+    assert Rr.shape[1] == 0
+    ref_pos, _ = orc.forward_dense(p, 2, w.state, w.attrs, Rr, Rs, w.p_instance, w.action, w.physics_param)
+    m = _model(agx, "rope", 2)
+    wd = w.to("cuda")
+    el = agx.build_edges(wd.state[:, -1], w.adj_thresh, wd.state_mask, wd.eef_mask, w.topk, False).check()
+    assert int(el.row_ptr[-1]) == 0
+    with torch.no_grad():
+        pos, _ = m(**wd.graph_dict(), edges=el)
+    assert (pos.cpu() - ref_pos).abs().max() <= FWD_TOL
+
+
+def test_full_size_properties_cloth_2k(agx):
+    """BASELINE cfg4 shape (cloth, 2000 particles) at a batch the box handles quickly: properties that
+    need no oracle — determinism, batch independence (shard == whole), permutation equivariance over
+    graphs, relation counts consistent with the CSR."""
+    from adaptigraph_b200 import synthetic as syn
+    w = syn.make_workload("cloth", 2000, 16, seed=1238).to("cuda")
+    m = _model(agx, "cloth", 3)
+    args = (w.attrs, w.action, w.p_instance, w.physics_param, w.state_mask, w.eef_mask, w.adj_thresh, w.topk,
+            w.connect_tools_all)
+    a = m.rollout(w.state, *args, n_steps=3, max_nR=16000)
+    b = m.rollout(w.state, *args, n_steps=3, max_nR=16000)
+    assert torch.equal(a["state_seqs"], b["state_seqs"])                    # bitwise deterministic
+    assert torch.isfinite(a["state_seqs"]).all()
+    lo = m.rollout(w.state[:8], *[x[:8] if torch.is_tensor(x) else x for x in args], n_steps=3, max_nR=16000)
+    assert torch.equal(a["state_seqs"][:8], lo["state_seqs"])               # shard == whole (what multi-GPU relies on)
+    perm = torch.randperm(16, device="cuda")
+    pa = m.rollout(w.state[perm], *[x[perm] if torch.is_tensor(x) else x for x in args], n_steps=3, max_nR=16000)
+    assert torch.equal(a["state_seqs"][perm], pa["state_seqs"])
+    assert int(a["n_edges"].min()) > 2000 * 5 and int(a["n_edges"].max()) <= 2000 * 7 + 2 * 2 + 2002
+
+
+def test_missing_backward_fails_loudly(agx):
+    g = H.load_npz("forward_rope100_k1.npz")
+    m = _model(agx, "rope", 1).train()
+    t = lambda k: torch.from_numpy(g[k]).cuda()  # noqa: E731
+    Rr, Rs = H.onehots_from_lists(g["recv"], g["send"], g["attrs"].shape[1])
+    with pytest.raises(NotImplementedError):
+        m(t("state"), t("attrs"), Rr.cuda(), Rs.cuda(), t("p_instance"), action=t("action"), rope_physics_param=t("physics_param"))
