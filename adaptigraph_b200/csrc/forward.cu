@@ -29,6 +29,17 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
 
 constexpr float MOTION_CLAMP = 100.f;  // model.py:85
 
+// tensor-core path (tc_forward.cu)
+struct TcFwdBuffers {
+  float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
+};
+size_t tc_blob_bytes(size_t base_bytes);
+int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_t base_bytes, cudaStream_t st);
+int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, cudaStream_t st);
+int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, cudaStream_t st);
+int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool last,
+                   float* pred_pos, int64_t pos_stride_b, float* pred_motion, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------ weight packing
 __global__ void pack_mat_kernel(const float* __restrict__ W, int ld, int col0, int K, int F, int Kpad, float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -395,7 +406,7 @@ __global__ void __launch_bounds__(256) rollout_advance_kernel(float* __restrict_
 
 // ------------------------------------------------------------------------------------ host drivers
 struct FwdWs {
-  float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C;
+  float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
 };
 static size_t fwd_ws_carve(void* base, int64_t rows, int64_t E_cap, FwdWs* out) {
   Carver c(base);
@@ -407,6 +418,8 @@ static size_t fwd_ws_carve(void* base, int64_t rows, int64_t E_cap, FwdWs* out) 
   w.Qs = c.take<float>((size_t)rows * FP);
   w.agg = c.take<float>((size_t)rows * FP);
   w.C = c.take<float>((size_t)(E_cap > 0 ? E_cap : 1) * FP);
+  w.rowmaxP = c.take<float>((size_t)rows);
+  w.rowmaxA = c.take<float>((size_t)rows);
   if (out) *out = w;
   return align_up(c.off, 256);
 }
@@ -435,13 +448,30 @@ static int ensure_smem_attrs() {
 static int forward_impl(const AgxModelDims* dims, const float* wts, const AgxGraphIn* g, float* pred_pos,
                         int64_t pos_stride_b, float* pred_motion, int precision, void* workspace, size_t workspace_bytes,
                         cudaStream_t st) {
-  AGX_REQUIRE(precision == AGX_PREC_FP32, AGX_ERR_ARG, "precision %d not available in this build", precision);
+  AGX_REQUIRE(precision == AGX_PREC_FP32 || precision == AGX_PREC_TC_F16X3, AGX_ERR_ARG, "unknown precision %d", precision);
   const int64_t rows = (int64_t)g->B * g->N;
   FwdWs ws;
   const size_t need = fwd_ws_carve(workspace, rows, g->E_cap, &ws);
   AGX_REQUIRE(workspace && workspace_bytes >= need, AGX_ERR_CAPACITY, "forward: workspace %zu < %zu bytes", workspace_bytes, need);
   if (int rc = ensure_smem_attrs()) return rc;
   const PackedLayout L = packed_layout();
+  if (precision == AGX_PREC_TC_F16X3) {
+    // same stages, dense layers on the tcgen05 tensor cores (tc_forward.cu)
+    const size_t base = L.total * sizeof(float);
+    const TcFwdBuffers tb{ws.nfeat, ws.P, ws.A, ws.Qr, ws.Qs, ws.agg, ws.C, ws.rowmaxP, ws.rowmaxA};
+    if (int rc = tc_node_encoder(g, wts, L, base, tb, st)) return rc;
+    if (g->E_cap > 0)
+      if (int rc = tc_edge_encoder(g, wts, L, base, tb, st)) return rc;
+    for (int k = 0; k < dims->pstep; ++k) {
+      { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
+        edge_aggregate_kernel<<<(unsigned)((rows + AGG_NODES - 1) / AGG_NODES), AGG_THREADS, 0, st>>>(
+            g->row_ptr, g->send, rows, g->N, g->E_cap, reinterpret_cast<const float4*>(ws.C),
+            reinterpret_cast<const float4*>(ws.Qr), reinterpret_cast<const float4*>(ws.Qs), reinterpret_cast<float4*>(ws.agg)); }
+      AGX_LAUNCH_CHECK();
+      if (int rc = tc_node_update(g, wts, L, base, tb, k + 1 == dims->pstep, pred_pos, pos_stride_b, pred_motion, st)) return rc;
+    }
+    return AGX_OK;
+  }
   const int grid_cap = 2 * num_sms();
   const int node_tiles = (int)((rows + TM - 1) / TM);
   const int node_grid = node_tiles < grid_cap ? node_tiles : grid_cap;
@@ -507,7 +537,7 @@ extern "C" {
 
 size_t agx_packed_weights_bytes(const AgxModelDims* dims) {
   (void)dims;
-  return agx::packed_layout().total * sizeof(float);
+  return agx::tc_blob_bytes(agx::packed_layout().total * sizeof(float));
 }
 
 int agx_pack_weights(const AgxModelDims* dims, const AgxWeights* raw, void* packed, agx_stream_t stream) {
@@ -550,7 +580,8 @@ int agx_pack_weights(const AgxModelDims* dims, const AgxWeights* raw, void* pack
   if (rc) return AGX_ERR_CUDA;
   pack_rows_kernel<<<(3 * FP + 255) / 256, 256, 0, st>>>(raw->weight[AGX_W_PRED2], 3, F, out + L.pred2_w);
   AGX_LAUNCH_CHECK();
-  return vec(AGX_W_PRED2, 3, 4, L.pred2_b);
+  if (int rc2 = vec(AGX_W_PRED2, 3, 4, L.pred2_b)) return rc2;
+  return tc_pack(dims, raw, packed, L.total * sizeof(float), st);   // scaled fp16 hi/lo images for the tensor-core path
 }
 
 size_t agx_forward_workspace_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap) {

@@ -1,0 +1,537 @@
+// Tensor-core (tcgen05) kernels of the forward pass: same stages and buffers as forward.cu's fp32
+// kernels (node_encoder, edge_encoder, node_update, node_update_head), with the dense 160x160 layers
+// evaluated as split-fp16 MMAs (tc_chain.cuh).  Reference arithmetic: dynamics/gnn/model.py:129-313.
+#include "common.cuh"
+#include "tc_chain.cuh"
+
+namespace agx {
+namespace tc {
+
+constexpr float MOTION_CLAMP = 100.f;  // model.py:85
+
+// ------------------------------------------------------------------------------------ weight images
+struct PackSpec {
+  const float* W; const float* bias; int ld, col0, K, F;   // source: W[n*ld + col0 + k], n < F, k < K
+};
+struct PackArgs {
+  PackSpec spec[T_NUM];
+  uint8_t* blob;
+  TcLayout L;
+};
+
+__global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
+  __shared__ float red_w[8], red_s[8], red_b[8];
+  __shared__ float sw_s;
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const PackSpec s = a.spec[t];
+  const int kpad = tc_kpad(t);
+  float wmax = 0.f, smax = 0.f, bmax = 0.f;
+  for (int n = tid; n < s.F; n += 256) {
+    float rs = 0.f;
+    for (int k = 0; k < s.K; ++k) {
+      const float w = fabsf(s.W[(size_t)n * s.ld + s.col0 + k]);
+      wmax = fmaxf(wmax, w);
+      rs += w;
+    }
+    smax = fmaxf(smax, rs);
+    if (s.bias) bmax = fmaxf(bmax, fabsf(s.bias[n]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+  }
+  if (lane == 0) { red_w[warp] = wmax; red_s[warp] = smax; red_b[warp] = bmax; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) { red_w[0] = fmaxf(red_w[0], red_w[w]); red_s[0] = fmaxf(red_s[0], red_s[w]); red_b[0] = fmaxf(red_b[0], red_b[w]); }
+    const int sw = scale_exp(red_w[0]);
+    sw_s = exp2i(sw);
+    float4* meta = reinterpret_cast<float4*>(a.blob + a.L.meta);
+    meta[t] = make_float4(exp2i(-sw), red_s[0] * 1.0001f, red_b[0], 0.f);   // inf-norm padded for fp32 summation slack
+  }
+  __syncthreads();
+  const float sc = sw_s;
+  uint8_t* hi_img = a.blob + a.L.img[t];
+  uint8_t* lo_img = hi_img + (size_t)FP * kpad * 2;
+  for (int i = tid; i < FP * kpad; i += 256) {
+    const int n = i / kpad, k = i - n * kpad;
+    const float v = (n < s.F && k < s.K) ? s.W[(size_t)n * s.ld + s.col0 + k] * sc : 0.f;
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const uint32_t off = img_offset(n, k, kpad);
+    *reinterpret_cast<__half*>(hi_img + off) = h;
+    *reinterpret_cast<__half*>(lo_img + off) = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------ common kernel prologue / epilogue
+template <int NL>
+__device__ __forceinline__ uint32_t chain_setup(Shared& sh, uint8_t* smem_raw, const LayerStep (&prog)[NL], const uint8_t* blob,
+                                                const TcLayout& L, const float* const (&bias_src)[MAX_BIAS], float4 (&meta)[NL]) {
+  sh = carve_shared(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(sh.bar_wsmall, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh.bar_wfull[i], 1); mbar_init(&sh.bar_wempty[i], 1); mbar_init(&sh.bar_accfull[i], 1); mbar_init(&sh.bar_accempty[i], EPI_WARPS); }
+    for (int i = 0; i < NCHUNK; ++i) mbar_init(&sh.bar_a[i], EPI_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(sh.tmem_ptr, TMEM_COLS);
+  for (int b = 0; b < MAX_BIAS; ++b)
+    for (int i = tid; i < FP; i += THREADS) sh.bias[b * FP + i] = bias_src[b] ? bias_src[b][i] : 0.f;
+  const float4* m = reinterpret_cast<const float4*>(blob + L.meta);
+#pragma unroll
+  for (int l = 0; l < NL; ++l) meta[l] = m[prog[l].layer];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *sh.tmem_ptr;
+}
+
+__device__ __forceinline__ void chain_teardown(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+__device__ __forceinline__ EpiCtx make_ctx(uint32_t tmem_base) {
+  EpiCtx cx;
+  cx.lane = threadIdx.x & 31;
+  cx.warp = threadIdx.x >> 5;
+  cx.row = (cx.warp & 3) * 32 + cx.lane;
+  cx.half = cx.warp >> 2;
+  cx.tmem_lane_base = tmem_base + ((uint32_t)((cx.warp & 3) * 32) << 16);
+  cx.accfull_parity = 0;
+  cx.e_in = 0;
+  cx.rowmax_in = 0.f;
+  return cx;
+}
+
+__device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void load16(const float* src, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = reinterpret_cast<const float4*>(src)[i];
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ float max16(const float (&v)[16], float m) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m = fmaxf(m, fabsf(v[i]));
+  return m;
+}
+
+// relu(bias + acc) -> next A (split fp16), tracking the row maximum for the next layer's scale
+__device__ __forceinline__ void epi_relu_to_a(const Shared& sh, EpiCtx& cx, int l, const float4 meta_l, const float* bias_s) {
+  const int e_next = scale_exp(cx.rowmax_in * meta_l.y + meta_l.z);
+  const float sc = exp2i(e_next), unscale = exp2i(-cx.e_in) * meta_l.x;
+  float mx = 0.f;
+  epi_layer<true>(sh, cx, l & 1, unscale, bias_s, [](int, int, float (&)[16]) {},
+                  [&](int c, int, float (&v)[16]) {
+                    mx = max16(v, mx);
+                    epi_store_a(cx, c, v, sc);
+                    epi_signal_chunk(sh, cx, c);
+                  });
+  cx.rowmax_in = epi_exchange<true>(sh, cx, mx);
+  cx.e_in = e_next;
+}
+
+// bias + acc -> fp32 rows in HBM (A in tensor memory is left untouched)
+__device__ __forceinline__ float epi_store_rows(const Shared& sh, EpiCtx& cx, int l, const float4 meta_l, const float* bias_s, float* out,
+                                                int64_t grow, bool valid) {
+  const float unscale = exp2i(-cx.e_in) * meta_l.x;
+  float mx = 0.f;
+  epi_layer<false>(sh, cx, l & 1, unscale, bias_s, [](int, int, float (&)[16]) {},
+                   [&](int, int col0, float (&v)[16]) {
+                     mx = max16(v, mx);
+                     if (valid) store16(out + grow * FP + col0, v);
+                   });
+  return mx;
+}
+
+// ------------------------------------------------------------------------------------ edge encoder
+struct EdgeArgs {
+  const int32_t* row_ptr; const int32_t* send; const int32_t* recv;
+  int64_t rows; int N; int64_t E_cap;
+  const float* nfeat;
+  const uint8_t* blob; TcLayout L;
+  const float* bias[MAX_BIAS];
+  float* C;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr LayerStep prog[4] = {{T_RENC0, 2, 1}, {T_RENC2, 10, 1}, {T_RENC4, 10, 1}, {T_RP_REL, 10, 1}};
+  Shared sh;
+  float4 meta[4];
+  const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, a.bias, meta);
+  const int64_t E = min((int64_t)a.row_ptr[a.rows], a.E_cap);
+  const int n_tiles = (int)((E + TILE - 1) / TILE);
+  const int warp = threadIdx.x >> 5;
+  if (warp == LOAD_WARP) {
+    loader_role(sh, prog, a.blob, a.L, n_tiles);
+  } else if (warp == MMA_WARP) {
+    mma_role(sh, prog, tmem_base, n_tiles);
+  } else {
+    EpiCtx cx = make_ctx(tmem_base);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t e = (int64_t)tile * TILE + cx.row;
+      const bool valid = e < E;
+      // ---- producer: 17 relation inputs (model.py:224-253), split over the two column halves
+      float in[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) in[i] = 0.f;
+      if (valid) {
+        const int r = a.recv[e];
+        const int s = (r / a.N) * a.N + a.send[e];
+        const float4* fr = reinterpret_cast<const float4*>(a.nfeat + (size_t)r * NFEAT);
+        const float4* fs = reinterpret_cast<const float4*>(a.nfeat + (size_t)s * NFEAT);
+        const float4 r0 = fr[0], r1 = fr[1], r2 = fr[2], r3 = fr[3];
+        const float4 s0 = fs[0], s1 = fs[1], s2 = fs[2], s3 = fs[3];
+        in[0] = r3.x; in[1] = r3.y; in[2] = s3.x; in[3] = s3.y;
+        in[4] = fabsf(r3.z - s3.z);
+        in[5] = r0.x - s0.x; in[6] = r0.y - s0.y; in[7] = r0.z - s0.z; in[8] = r0.w - s0.w;
+        in[9] = r1.x - s1.x; in[10] = r1.y - s1.y; in[11] = r1.z - s1.z; in[12] = r1.w - s1.w;
+        in[13] = r2.x - s2.x; in[14] = r2.y - s2.y; in[15] = r2.z - s2.z; in[16] = r2.w - s2.w;
+      }
+      float mx = 0.f;
+#pragma unroll
+      for (int i = 0; i < 17; ++i) mx = fmaxf(mx, fabsf(in[i]));
+      cx.e_in = scale_exp(mx);
+      cx.rowmax_in = mx;
+      {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = cx.half ? in[16 + i] : in[i];
+        epi_store_a(cx, 0, v, exp2i(cx.e_in));
+        epi_signal_chunk(sh, cx, 0);
+      }
+      epi_relu_to_a(sh, cx, 0, meta[0], sh.bias + 0 * FP);
+      epi_relu_to_a(sh, cx, 1, meta[1], sh.bias + 1 * FP);
+      epi_relu_to_a(sh, cx, 2, meta[2], sh.bias + 2 * FP);
+      epi_store_rows(sh, cx, 3, meta[3], sh.bias + 3 * FP, a.C, e, valid);
+    }
+  }
+  chain_teardown(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------ node encoder
+struct NodeArgs {
+  const float* state; const float* attrs; const float* action; const float* p_instance; const float* physics;
+  int B, N, n_p;
+  const uint8_t* blob; TcLayout L;
+  const float* bias[MAX_BIAS];
+  float* nfeat; float* P; float* A; float* Qr; float* Qs; float* rowmaxP; float* rowmaxA;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr LayerStep prog[6] = {{T_PENC0, 1, 1}, {T_PENC2, 10, 1}, {T_PENC4, 10, 1}, {T_PP_ENC, 10, 1}, {T_RP_RECV, 10, 0}, {T_RP_SEND, 10, 0}};
+  Shared sh;
+  float4 meta[6];
+  const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, a.bias, meta);
+  const int64_t rows = (int64_t)a.B * a.N;
+  const int n_tiles = (int)((rows + TILE - 1) / TILE);
+  const int warp = threadIdx.x >> 5;
+  if (warp == LOAD_WARP) {
+    loader_role(sh, prog, a.blob, a.L, n_tiles);
+  } else if (warp == MMA_WARP) {
+    mma_role(sh, prog, tmem_base, n_tiles);
+  } else {
+    EpiCtx cx = make_ctx(tmem_base);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t r = (int64_t)tile * TILE + cx.row;
+      const bool valid = r < rows;
+      float in[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) in[i] = 0.f;
+      if (valid) {
+        const int b = (int)(r / a.N), n = (int)(r - (int64_t)b * a.N);
+        float s[H_FIX][3];
+#pragma unroll
+        for (int h = 0; h < H_FIX; ++h) {
+          const float* p = a.state + (((size_t)b * H_FIX + h) * a.N + n) * 3;
+          s[h][0] = p[0]; s[h][1] = p[1]; s[h][2] = p[2];
+        }
+        const float a0 = a.attrs[r * 2 + 0], a1 = a.attrs[r * 2 + 1];
+        if (cx.half == 0) {
+          const float grp = n < a.n_p ? a.p_instance[(size_t)b * a.n_p + n] : 0.f;
+          float4* nf = reinterpret_cast<float4*>(a.nfeat + r * NFEAT);      // model.py:155-165 history record
+          nf[0] = make_float4(s[1][0] - s[0][0], s[1][1] - s[0][1], s[1][2] - s[0][2], s[2][0] - s[1][0]);
+          nf[1] = make_float4(s[2][1] - s[1][1], s[2][2] - s[1][2], s[3][0] - s[2][0], s[3][1] - s[2][1]);
+          nf[2] = make_float4(s[3][2] - s[2][2], s[3][0], s[3][1], s[3][2]);
+          nf[3] = make_float4(a0, a1, grp, 0.f);
+        }
+        in[0] = a0; in[1] = a1;
+        in[2] = n < a.n_p ? a.physics[b] : 0.f;                               // model.py:186-189
+        in[3] = a.action[r * 3 + 0]; in[4] = a.action[r * 3 + 1]; in[5] = a.action[r * 3 + 2];
+      }
+      float mx = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) mx = fmaxf(mx, fabsf(in[i]));
+      cx.e_in = scale_exp(mx);
+      cx.rowmax_in = mx;
+      if (cx.half == 0) epi_store_a(cx, 0, in, exp2i(cx.e_in));
+      epi_signal_chunk(sh, cx, 0);
+
+      epi_relu_to_a(sh, cx, 0, meta[0], sh.bias + 0 * FP);
+      epi_relu_to_a(sh, cx, 1, meta[1], sh.bias + 1 * FP);
+      {  // particle_encode = particle_effect_0 (model.py:268-269): next A and P rows
+        const float4 m = meta[2];
+        const int e_next = scale_exp(cx.rowmax_in * m.y + m.z);
+        const float sc = exp2i(e_next), unscale = exp2i(-cx.e_in) * m.x;
+        float pm = 0.f;
+        epi_layer<true>(sh, cx, 0, unscale, sh.bias + 2 * FP, [](int, int, float (&)[16]) {},
+                        [&](int c, int col0, float (&v)[16]) {
+                          pm = max16(v, pm);
+                          epi_store_a(cx, c, v, sc);
+                          epi_signal_chunk(sh, cx, c);
+                          if (valid) store16(a.P + r * FP + col0, v);
+                        });
+        pm = epi_exchange<true>(sh, cx, pm);
+        cx.rowmax_in = pm;
+        cx.e_in = e_next;
+        if (valid && cx.half == 0) a.rowmaxP[r] = pm;
+      }
+      float am = epi_store_rows(sh, cx, 3, meta[3], sh.bias + 3 * FP, a.A, r, valid);   // A_n = W_enc*penc + b
+      am = epi_exchange<true>(sh, cx, am);
+      if (valid && cx.half == 0) a.rowmaxA[r] = am;
+      epi_store_rows(sh, cx, 4, meta[4], nullptr, a.Qr, r, valid);
+      epi_store_rows(sh, cx, 5, meta[5], nullptr, a.Qs, r, valid);
+    }
+  }
+  chain_teardown(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------ node update / head
+struct UpdArgs {
+  int B, N, n_p;
+  const float* agg; const float* A; float* P; float* Qr; float* Qs; float* rowmaxP; const float* rowmaxA;
+  const uint8_t* blob; TcLayout L;
+  const float* bias[MAX_BIAS];
+  const float* head_w;   // fp32 [3][FP] then 4 bias floats (head only)
+  const float* state; float* pred_pos; int64_t pos_stride_b; float* pred_motion;
+};
+
+template <bool LAST>
+__global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr LayerStep prog[3] = {{T_PP_AGG, 10, 1}, {LAST ? T_PRED0 : T_RP_RECV, 10, 1}, {LAST ? T_PRED1 : T_RP_SEND, 10, LAST ? 1 : 0}};
+  Shared sh;
+  float4 meta[3];
+  const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, a.bias, meta);
+  if (LAST) {
+    for (int i = threadIdx.x; i < 3 * FP + 4; i += THREADS) sh.head_w[i] = a.head_w[i];
+    __syncthreads();
+  }
+  const int64_t rows = (int64_t)a.B * a.N;
+  const int n_tiles = (int)((rows + TILE - 1) / TILE);
+  const int warp = threadIdx.x >> 5;
+  if (warp == LOAD_WARP) {
+    loader_role(sh, prog, a.blob, a.L, n_tiles);
+  } else if (warp == MMA_WARP) {
+    mma_role(sh, prog, tmem_base, n_tiles);
+  } else {
+    EpiCtx cx = make_ctx(tmem_base);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t r = (int64_t)tile * TILE + cx.row;
+      const bool valid = r < rows;
+      // ---- producer: the aggregated relation effects of this row become A (K = 160)
+      {
+        float g[NCHUNK][16];
+        float mx = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          if (valid) load16(a.agg + r * FP + 32 * c + 16 * cx.half, g[c]);
+          else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) g[c][i] = 0.f;
+          }
+          mx = max16(g[c], mx);
+        }
+        mx = epi_exchange<true>(sh, cx, mx);
+        cx.e_in = scale_exp(mx);
+        cx.rowmax_in = mx;
+        const float sc = exp2i(cx.e_in);
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          epi_store_a(cx, c, g[c], sc);
+          epi_signal_chunk(sh, cx, c);
+        }
+      }
+      {  // P <- relu((W_agg*agg + A_n) + P)   (model.py:36-40, :299-301)
+        const float4 m = meta[0];
+        const float extra_bound = valid ? a.rowmaxA[r] + a.rowmaxP[r] : 0.f;
+        const int e_next = scale_exp(cx.rowmax_in * m.y + extra_bound);
+        const float sc = exp2i(e_next), unscale = exp2i(-cx.e_in) * m.x;
+        float pm = 0.f;
+        epi_layer<true>(sh, cx, 0, unscale, nullptr,
+                        [&](int, int col0, float (&v)[16]) {
+                          if (valid) {
+                            float an[16], pp[16];
+                            load16(a.A + r * FP + col0, an);
+                            load16(a.P + r * FP + col0, pp);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = (v[i] + an[i]) + pp[i];
+                          }
+                        },
+                        [&](int c, int col0, float (&v)[16]) {
+                          pm = max16(v, pm);
+                          epi_store_a(cx, c, v, sc);
+                          epi_signal_chunk(sh, cx, c);
+                          if (!LAST && valid) store16(a.P + r * FP + col0, v);
+                        });
+        pm = epi_exchange<true>(sh, cx, pm);
+        cx.rowmax_in = pm;
+        cx.e_in = e_next;
+        if (!LAST && valid && cx.half == 0) a.rowmaxP[r] = pm;
+      }
+      if (!LAST) {
+        epi_store_rows(sh, cx, 1, meta[1], nullptr, a.Qr, r, valid);
+        epi_store_rows(sh, cx, 2, meta[2], nullptr, a.Qs, r, valid);
+      } else {
+        epi_relu_to_a(sh, cx, 1, meta[1], sh.bias + 0 * FP);
+        // motion head (model.py:306-309): relu(linear_1) then the 3-row linear_2 as running dot products
+        const float unscale = exp2i(-cx.e_in) * meta[2].x;
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+        epi_layer<true>(sh, cx, 0, unscale, sh.bias + 1 * FP, [](int, int, float (&)[16]) {},
+                        [&](int, int col0, float (&v)[16]) {
+#pragma unroll
+                          for (int i = 0; i < 16; ++i) {
+                            m0 = fmaf(v[i], sh.head_w[col0 + i], m0);
+                            m1 = fmaf(v[i], sh.head_w[FP + col0 + i], m1);
+                            m2 = fmaf(v[i], sh.head_w[2 * FP + col0 + i], m2);
+                          }
+                        });
+        m0 = epi_exchange<false>(sh, cx, m0);
+        m1 = epi_exchange<false>(sh, cx, m1);
+        m2 = epi_exchange<false>(sh, cx, m2);
+        if (valid && cx.half == 0) {
+          const int b = (int)(r / a.N), n = (int)(r - (int64_t)b * a.N);
+          if (n < a.n_p) {
+            m0 += sh.head_w[3 * FP + 0]; m1 += sh.head_w[3 * FP + 1]; m2 += sh.head_w[3 * FP + 2];
+            float* mo = a.pred_motion + ((size_t)b * a.n_p + n) * 3;
+            mo[0] = m0; mo[1] = m1; mo[2] = m2;
+            const float* cur = a.state + (((size_t)b * H_FIX + (H_FIX - 1)) * a.N + n) * 3;
+            float* po = a.pred_pos + (size_t)b * a.pos_stride_b + (size_t)n * 3;
+            po[0] = cur[0] + fminf(fmaxf(m0, -MOTION_CLAMP), MOTION_CLAMP);
+            po[1] = cur[1] + fminf(fmaxf(m1, -MOTION_CLAMP), MOTION_CLAMP);
+            po[2] = cur[2] + fminf(fmaxf(m2, -MOTION_CLAMP), MOTION_CLAMP);
+          }
+        }
+      }
+    }
+  }
+  chain_teardown(tmem_base);
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------ host entry points (used by forward.cu)
+size_t tc_blob_bytes(size_t base_bytes) { return tc::tc_layout(base_bytes).total; }
+
+int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_t base_bytes, cudaStream_t st) {
+  using namespace tc;
+  const int F = dims->F;
+  const int d_node = dims->d_attr + dims->d_phys + dims->d_act, d_rel = 2 * dims->d_attr + 1 + 3 * dims->n_his;
+  AGX_REQUIRE(d_node <= tc_kpad(T_PENC0) && d_rel <= tc_kpad(T_RENC0), AGX_ERR_ARG, "tc_pack: input dims exceed the padded K");
+  PackArgs a;
+  auto set = [&](int t, int layer, int ld, int col0, int K, bool bias) {
+    a.spec[t] = PackSpec{raw->weight[layer], bias ? raw->bias[layer] : nullptr, ld, col0, K, F};
+  };
+  set(T_PENC0, AGX_W_PENC0, d_node, 0, d_node, true);
+  set(T_PENC2, AGX_W_PENC2, F, 0, F, true);
+  set(T_PENC4, AGX_W_PENC4, F, 0, F, true);
+  set(T_RENC0, AGX_W_RENC0, d_rel, 0, d_rel, true);
+  set(T_RENC2, AGX_W_RENC2, F, 0, F, true);
+  set(T_RENC4, AGX_W_RENC4, F, 0, F, true);
+  set(T_RP_REL, AGX_W_RPROP, 3 * F, 0, F, true);
+  set(T_RP_RECV, AGX_W_RPROP, 3 * F, F, F, false);
+  set(T_RP_SEND, AGX_W_RPROP, 3 * F, 2 * F, F, false);
+  set(T_PP_ENC, AGX_W_PPROP, 2 * F, 0, F, true);
+  set(T_PP_AGG, AGX_W_PPROP, 2 * F, F, F, false);
+  set(T_PRED0, AGX_W_PRED0, F, 0, F, true);
+  set(T_PRED1, AGX_W_PRED1, F, 0, F, true);
+  a.blob = static_cast<uint8_t*>(packed);
+  a.L = tc_layout(base_bytes);
+  { ProfScope ps(AGX_KIND_OTHER, st);
+    pack_tc_kernel<<<T_NUM, 256, 0, st>>>(a); }
+  AGX_LAUNCH_CHECK();
+  return AGX_OK;
+}
+
+struct TcFwdBuffers {
+  float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
+};
+
+static int tc_ensure_attrs() {
+  static thread_local bool done = false;
+  if (done) return AGX_OK;
+  using namespace tc;
+  AGX_CUDA_OK(cudaFuncSetAttribute(tc_edge_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  done = true;
+  return AGX_OK;
+}
+
+int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, cudaStream_t st) {
+  using namespace tc;
+  if (int rc = tc_ensure_attrs()) return rc;
+  const int64_t rows = (int64_t)g->B * g->N;
+  const int tiles = (int)((rows + TILE - 1) / TILE);
+  NodeArgs a{g->state, g->attrs, g->action, g->p_instance, g->physics, g->B, g->N, g->n_p,
+             reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
+             {wts + PL.penc0_b, wts + PL.penc2_b, wts + PL.penc4_b, wts + PL.pp_b},
+             w.nfeat, w.P, w.A, w.Qr, w.Qs, w.rowmaxP, w.rowmaxA};
+  { ProfScope ps(AGX_KIND_NODE_ENCODER, st);
+    tc_node_encoder_kernel<<<tiles < num_sms() ? tiles : num_sms(), THREADS, SMEM_BYTES, st>>>(a); }
+  AGX_LAUNCH_CHECK();
+  return AGX_OK;
+}
+
+int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, cudaStream_t st) {
+  using namespace tc;
+  if (int rc = tc_ensure_attrs()) return rc;
+  const int64_t rows = (int64_t)g->B * g->N;
+  const int64_t tiles = (g->E_cap + TILE - 1) / TILE;
+  EdgeArgs a{g->row_ptr, g->send, g->recv, rows, g->N, g->E_cap, w.nfeat, reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
+             {wts + PL.renc0_b, wts + PL.renc2_b, wts + PL.renc4_b, wts + PL.rp_b}, w.C};
+  { ProfScope ps(AGX_KIND_EDGE_ENCODER, st);
+    tc_edge_encoder_kernel<<<(int)(tiles < num_sms() ? tiles : num_sms()), THREADS, SMEM_BYTES, st>>>(a); }
+  AGX_LAUNCH_CHECK();
+  return AGX_OK;
+}
+
+int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool last,
+                   float* pred_pos, int64_t pos_stride_b, float* pred_motion, cudaStream_t st) {
+  using namespace tc;
+  if (int rc = tc_ensure_attrs()) return rc;
+  const int64_t rows = (int64_t)g->B * g->N;
+  const int tiles = (int)((rows + TILE - 1) / TILE);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  UpdArgs a{g->B, g->N, g->n_p, w.agg, w.A, w.P, w.Qr, w.Qs, w.rowmaxP, w.rowmaxA,
+            reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
+            {wts + PL.pred0_b, wts + PL.pred1_b, nullptr, nullptr},
+            wts + PL.pred2_w, g->state, pred_pos, pos_stride_b, pred_motion};
+  if (last) {
+    ProfScope ps(AGX_KIND_NODE_HEAD, st);
+    tc_node_update_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
+  } else {
+    ProfScope ps(AGX_KIND_NODE_UPDATE, st);
+    tc_node_update_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(a);
+  }
+  AGX_LAUNCH_CHECK();
+  return AGX_OK;
+}
+
+}  // namespace agx

@@ -18,9 +18,14 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
+import os
+
 from . import _lib as L
 from . import ops
 from .graph import EdgeList, edges_from_onehots, _thr2_batch
+
+
+_PRECISIONS = {"fp32": L.AGX_PREC_FP32, "tc": L.AGX_PREC_TC_F16X3}
 
 
 class _EncoderParams(nn.Module):
@@ -67,7 +72,8 @@ class DynamicsPredictor(nn.Module):
         self.nf_physics = model_config["nf_physics"]
         self.eps = 1e-6
         self.motion_clamp = 100
-        self.precision = L.AGX_PREC_FP32
+        # arithmetic of the dense layers: "fp32" = exact FFMA tiles, "tc" = tcgen05 split-fp16 tensor-core tiles
+        self.precision = _PRECISIONS[os.environ.get("AGX_PRECISION", "tc")]
 
         self.num_materials = len(material_config["material_index"])
         assert self.num_materials == 1, "Only support single material."
@@ -100,6 +106,11 @@ class DynamicsPredictor(nn.Module):
         if mc["verbose"]:
             print("DynamicsPredictor initialized")
             print("particle input dim: {}, relation input dim: {}".format(input_dim, rel_input_dim))
+
+    def set_precision(self, name: str) -> "DynamicsPredictor":
+        """'fp32' (exact FFMA tiles) or 'tc' (tcgen05 tensor cores on split-fp16 operands, fp32-accurate)."""
+        self.precision = _PRECISIONS[name]
+        return self
 
     # ------------------------------------------------------------------ weights
     def _linear_layers(self):

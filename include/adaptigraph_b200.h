@@ -59,7 +59,8 @@ extern "C" {
 
 /* arithmetic of the dense 150x150 layers */
 #define AGX_PREC_FP32 0          /* exact fp32 FFMA tiles */
-#define AGX_PREC_3XTF32 1        /* tcgen05 kind::tf32, hi/lo operand split, fp32 accumulate in TMEM */
+#define AGX_PREC_TC_F16X3 1      /* tcgen05 kind::f16 on per-row power-of-two scaled fp16 hi/lo splits of both operands
+                                    (3 MMAs per K step, 22 significant bits), fp32 accumulate in tensor memory */
 
 #if defined(__GNUC__)
 #define AGX_API __attribute__((visibility("default")))

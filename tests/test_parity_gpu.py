@@ -22,11 +22,14 @@ def agx():
     return pkg
 
 
-def _model(agx, material, pstep):
+PRECISIONS = ["fp32", "tc"]   # exact FFMA tiles / tcgen05 split-fp16 tensor-core tiles: same tolerances
+
+
+def _model(agx, material, pstep, precision="fp32"):
     from adaptigraph_b200 import synthetic as syn
     m = agx.DynamicsPredictor(*syn.configs(material, pstep), "cuda")
     m.load_state_dict(H.golden_weights())
-    return m.cuda().eval()
+    return m.cuda().eval().set_precision(precision)
 
 
 def _case(name):
@@ -90,11 +93,12 @@ def test_graph_build_capacity_overflow_is_reported(agx):
     assert int(el.n_edges.max()) == c["batch_recv"].shape[1]   # true counts are still reported
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("fname", FWD)
 @pytest.mark.parametrize("path", ["dense", "edges"])
-def test_forward_matches_reference(agx, fname, path):
+def test_forward_matches_reference(agx, fname, path, precision):
     g = H.load_npz(fname)
-    m = _model(agx, str(g["material"]), int(g["pstep"]))
+    m = _model(agx, str(g["material"]), int(g["pstep"]), precision)
     t = lambda k: torch.from_numpy(g[k]).cuda()  # noqa: E731
     N = g["attrs"].shape[1]
     kw = {f"{g['material']}_physics_param": t("physics_param"), "p_rigid": torch.zeros(1).cuda()}
@@ -111,13 +115,14 @@ def test_forward_matches_reference(agx, fname, path):
     assert np.abs(motion.cpu().numpy() - g["pred_motion"]).max() <= FWD_TOL
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("fname", ["rollout_rope60_T10.npz", "rollout_cloth49_T10.npz", "rollout_granular80_T5.npz"])
-def test_rollout_matches_reference(agx, fname):
+def test_rollout_matches_reference(agx, fname, precision):
     from adaptigraph_b200 import synthetic as syn
     g = H.load_npz(fname)
     mat = str(g["material"])
     thr, topk, cta, _ = syn.MATERIALS[mat]
-    m = _model(agx, mat, int(g["pstep"]))
+    m = _model(agx, mat, int(g["pstep"]), precision)
     t = lambda k: torch.from_numpy(g[k]).cuda()  # noqa: E731
     T = g["preds"].shape[1]
     state0 = t("state")
@@ -134,8 +139,9 @@ def test_rollout_matches_reference(agx, fname):
     assert np.abs(out["state"][:, -1, :n_p].cpu().numpy() - g["preds"][:, -1]).max() <= 1e-4
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("material,n_p,B,pstep", [("cloth", 400, 5, 3), ("granular", 333, 3, 2), ("rope", 513, 2, 1)])
-def test_forward_matches_oracle_on_seeded_inputs(agx, material, n_p, B, pstep):
+def test_forward_matches_oracle_on_seeded_inputs(agx, material, n_p, B, pstep, precision):
     """Sizes the dense CPU oracle finishes in seconds; tiles straddle graphs and are ragged."""
     from adaptigraph_b200 import synthetic as syn
     from oracle import dynamics_oracle as orc
@@ -143,7 +149,7 @@ def test_forward_matches_oracle_on_seeded_inputs(agx, material, n_p, B, pstep):
     p = H.golden_weights()
     Rr, Rs = orc.edges_dense_batch(w.state[:, -1], w.adj_thresh, w.state_mask, w.eef_mask, w.topk, w.connect_tools_all)
     ref_pos, ref_motion = orc.forward_dense(p, pstep, w.state, w.attrs, Rr, Rs, w.p_instance, w.action, w.physics_param)
-    m = _model(agx, material, pstep)
+    m = _model(agx, material, pstep, precision)
     wd = w.to("cuda")
     el = agx.build_edges(wd.state[:, -1], w.adj_thresh, wd.state_mask, wd.eef_mask, w.topk, w.connect_tools_all).check()
     r_ref, s_ref = H.lists_from_onehots(Rr, Rs)
@@ -155,7 +161,8 @@ def test_forward_matches_oracle_on_seeded_inputs(agx, material, n_p, B, pstep):
     assert (motion.cpu() - ref_motion).abs().max() <= FWD_TOL
 
 
-def test_graph_without_relations_and_single_particle_tiles(agx):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_graph_without_relations_and_single_particle_tiles(agx, precision):
     """Empty relation set (radius below every pair distance except self excluded by topk... here: all
     particles invalid but one) and B*N smaller than one tile."""
     from adaptigraph_b200 import synthetic as syn
@@ -166,7 +173,7 @@ def test_graph_without_relations_and_single_particle_tiles(agx):
     Rr, Rs = orc.edges_dense_batch(w.state[:, -1], w.adj_thresh, w.state_mask, w.eef_mask, w.topk, False)
     assert Rr.shape[1] == 0
     ref_pos, _ = orc.forward_dense(p, 2, w.state, w.attrs, Rr, Rs, w.p_instance, w.action, w.physics_param)
-    m = _model(agx, "rope", 2)
+    m = _model(agx, "rope", 2, precision)
     wd = w.to("cuda")
     el = agx.build_edges(wd.state[:, -1], w.adj_thresh, wd.state_mask, wd.eef_mask, w.topk, False).check()
     assert int(el.row_ptr[-1]) == 0
@@ -175,13 +182,14 @@ def test_graph_without_relations_and_single_particle_tiles(agx):
     assert (pos.cpu() - ref_pos).abs().max() <= FWD_TOL
 
 
-def test_full_size_properties_cloth_2k(agx):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_full_size_properties_cloth_2k(agx, precision):
     """BASELINE cfg4 shape (cloth, 2000 particles) at a batch the box handles quickly: properties that
     need no oracle — determinism, batch independence (shard == whole), permutation equivariance over
     graphs, relation counts consistent with the CSR."""
     from adaptigraph_b200 import synthetic as syn
     w = syn.make_workload("cloth", 2000, 16, seed=1238).to("cuda")
-    m = _model(agx, "cloth", 3)
+    m = _model(agx, "cloth", 3, precision)
     args = (w.attrs, w.action, w.p_instance, w.physics_param, w.state_mask, w.eef_mask, w.adj_thresh, w.topk,
             w.connect_tools_all)
     a = m.rollout(w.state, *args, n_steps=3, max_nR=16000)
@@ -203,3 +211,15 @@ def test_missing_backward_fails_loudly(agx):
     Rr, Rs = H.onehots_from_lists(g["recv"], g["send"], g["attrs"].shape[1])
     with pytest.raises(NotImplementedError):
         m(t("state"), t("attrs"), Rr.cuda(), Rs.cuda(), t("p_instance"), action=t("action"), rope_physics_param=t("physics_param"))
+
+
+def test_tensor_core_path_agrees_with_fp32_path_at_scale(agx):
+    """Same engine, two arithmetic paths, BASELINE-sized graphs: a forward on 8 cloth-2000 graphs."""
+    from adaptigraph_b200 import synthetic as syn
+    w = syn.make_workload("cloth", 2000, 8, seed=99).to("cuda")
+    el = agx.build_edges(w.state[:, -1], w.adj_thresh, w.state_mask, w.eef_mask, w.topk, w.connect_tools_all).check()
+    with torch.no_grad():
+        a_pos, a_mot = _model(agx, "cloth", 3, "fp32")(**w.graph_dict(), edges=el)
+        b_pos, b_mot = _model(agx, "cloth", 3, "tc")(**w.graph_dict(), edges=el)
+    assert (a_mot - b_mot).abs().max().item() <= FWD_TOL
+    assert (a_pos - b_pos).abs().max().item() <= FWD_TOL

@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import agx_helpers as H  # noqa: E402
 
 
-def main(fname="forward_cloth64_pad_k3.npz"):
+def main(fname="forward_cloth64_pad_k3.npz", precision=0):
     import adaptigraph_b200 as agx
     from adaptigraph_b200 import _lib as L, ops, synthetic as syn
     from oracle import dynamics_oracle as orc
@@ -49,7 +49,7 @@ def main(fname="forward_cloth64_pad_k3.npz"):
     mot = torch.empty(B, n_p, 3, device="cuda")
     packed = m.packed_weights()
     L.check(L.lib.agx_forward(C.byref(dims), C.c_void_p(packed.data_ptr()), C.byref(gin), C.c_void_p(pos.data_ptr()), n_p * 3,
-                              C.c_void_p(mot.data_ptr()), 0, C.c_void_p(ws.data_ptr()), nws, None), "agx_forward")
+                              C.c_void_p(mot.data_ptr()), precision, C.c_void_p(ws.data_ptr()), nws, None), "agx_forward")
     torch.cuda.synchronize()
     wsf = ws.cpu().view(torch.float32)
     rows = B * N
@@ -93,9 +93,11 @@ def main(fname="forward_cloth64_pad_k3.npz"):
         err = (got - ref).abs().max().item() if ref.numel() else 0.0
         flag = "OK " if err <= 1e-4 else "BAD"
         bad += flag == "BAD"
-        print(f"{flag} {name:18s} max-abs {err:.3e}  ref-rms {ref.pow(2).mean().sqrt().item() if ref.numel() else 0:.3e}")
+        print(f"prec={precision} {flag} {name:18s} max-abs {err:.3e}  ref-rms {ref.pow(2).mean().sqrt().item() if ref.numel() else 0:.3e}")
     return bad
 
 
 if __name__ == "__main__":
-    sys.exit(1 if sum(main(f) for f in (sys.argv[1:] or ["forward_rope100_k1.npz", "forward_cloth64_pad_k3.npz"])) else 0)
+    prec = int(os.environ.get("AGX_DEBUG_PREC", "0"))
+    files = [x for x in sys.argv[1:]] or ["forward_rope100_k1.npz", "forward_cloth64_pad_k3.npz"]
+    sys.exit(1 if sum(main(f, prec) for f in files) else 0)
