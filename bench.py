@@ -171,8 +171,10 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--graphs", type=int, default=WORKLOAD["B"], help="graphs per GPU (default: the BASELINE batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rollout-steps", type=int, default=WORKLOAD["T"], help="T (default: the BASELINE 10-step rollout)")
     args = ap.parse_args()
 
+    WORKLOAD["T"] = args.rollout_steps
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
