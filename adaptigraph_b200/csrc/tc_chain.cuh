@@ -1,4 +1,4 @@
-// Tensor-core MLP chains (AGX_PREC_F16X3): tcgen05.mma kind::f16 with fp32-accurate split operands.
+// Tensor-core MLP chains (AGX_PREC_TC_F16X3): tcgen05.mma kind::f16 with fp32-accurate split operands.
 //
 // One CTA owns a tile of 128 rows (relations or particles) and pushes it through a chain of dense
 // layers without the activations ever leaving the SM:
@@ -10,16 +10,17 @@
 //   * the weights are pre-packed (agx_pack_weights) as scaled fp16 hi/lo images in the canonical
 //     K-major core-matrix layout and brought into shared memory by the TMA engine as one bulk copy
 //     per layer, double buffered so the next layer's weights land while the current layer runs;
-//   * a layer is 3 MMAs per 16-wide K step:  D += Ahi*Whi + Alo*Whi + Ahi*Wlo  (the dropped lo*lo
+//   * a layer is 3 MMAs per 16-wide K step:  D += Alo*Whi + Ahi*Wlo + Ahi*Whi  (the dropped lo*lo
 //     term is 2^-22 relative), issued by one thread; fp32 accumulation in tensor memory;
-//   * 8 epilogue warps (thread = row, two warps per 32-lane quarter splitting the columns) read the
-//     accumulator with tcgen05.ld, undo the power-of-two scales exactly, apply bias / residual /
-//     ReLU, and either re-split the result into the next layer's A (tcgen05.st) chunk by chunk —
-//     the MMA warp starts the next layer's K steps as soon as a 32-column chunk is ready — or store
-//     fp32 rows to HBM.
+//   * 16 epilogue warps (thread = row; the four warps of a 32-lane quarter split every 32-column
+//     chunk into 8-column pieces) read the accumulator with tcgen05.ld (whole row piece up front, one
+//     wait, buffer released immediately), undo the power-of-two scales exactly, apply bias /
+//     residual / ReLU, and either re-split the result into the next layer's A (tcgen05.st) chunk by
+//     chunk — the MMA warp starts the next layer's K steps as soon as a chunk is complete — or store
+//     fp32 rows to HBM with 256-bit stores.
 //
-// Warp roles: warps 0-7 epilogue + input producers, warp 8 MMA issuer (+ TMEM allocation),
-// warp 9 weight loader.  All waits are bounded (tc_ptx.cuh: a protocol bug traps, it cannot hang).
+// Warp roles: warps 0-15 epilogue + input producers, warp 16 MMA issuer (+ TMEM allocation),
+// warp 17 weight loader.  All waits are bounded (tc_ptx.cuh: a protocol bug traps, it cannot hang).
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -28,11 +29,13 @@ namespace agx {
 namespace tc {
 
 constexpr int TILE = 128;
-constexpr int EPI_WARPS = 8;
+constexpr int NQ = 4;                                   // column quarters per chunk (warps per lane quarter)
+constexpr int QW = 8;                                   // columns per thread per chunk
+constexpr int EPI_WARPS = 4 * NQ;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int MMA_WARP = 8;
-constexpr int LOAD_WARP = 9;
-constexpr int THREADS = 320;
+constexpr int MMA_WARP = EPI_WARPS;
+constexpr int LOAD_WARP = EPI_WARPS + 1;
+constexpr int THREADS = EPI_THREADS + 64;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_ACC0 = 0, COL_ACC1 = 160, COL_AHI = 320, COL_ALO = 400;
 constexpr int NCHUNK = 5;                               // 32-wide K chunks of a 160-wide layer
@@ -79,10 +82,10 @@ __device__ __forceinline__ int scale_exp(float bound) {
 }
 __device__ __forceinline__ float exp2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
 
-// split 16 scaled fp32 values into packed fp16 hi / lo columns
-__device__ __forceinline__ void split16(const float (&s)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+// split 8 scaled fp32 values into packed fp16 hi / lo columns (hi = round-to-nearest, lo = residual)
+__device__ __forceinline__ void split8(const float (&s)[QW], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const __half2 h = __floats2half2_rn(s[2 * i], s[2 * i + 1]);
     const float2 hf = __half22float2(h);
     const __half2 l = __floats2half2_rn(s[2 * i] - hf.x, s[2 * i + 1] - hf.y);
@@ -95,8 +98,8 @@ __device__ __forceinline__ void split16(const float (&s)[16], uint32_t (&hi)[8],
 struct Shared {
   uint8_t* wbig[2];      // two 2*IMG_BIG weight buffers (hi image then lo image)
   uint8_t* wsmall;       // first-layer weights (K = 16 or 32)
-  float* bias;           // [NBIAS][FP]
-  float* xchg;           // [2][TILE] row exchange between the two column halves
+  float* bias;           // [MAX_BIAS][FP]
+  float* xchg;           // [NQ][TILE] row exchange between the column quarters
   float* head_w;         // [3][FP] + [4] (head program only)
   uint64_t* bar_wsmall;
   uint64_t* bar_wfull;   // [2]
@@ -107,17 +110,18 @@ struct Shared {
   uint32_t* tmem_ptr;
 };
 constexpr int MAX_BIAS = 4;
-constexpr size_t SMEM_BYTES = 2 * (2 * (size_t)IMG_BIG) + 2 * (size_t)FP * 32 * 2 + MAX_BIAS * FP * 4 + 2 * TILE * 4 + (3 * FP + 4) * 4 +
-                              16 * 8 + 16 + 1024 /* alignment slack */;
+constexpr size_t SMEM_BYTES = 2 * (2 * (size_t)IMG_BIG) + 2 * (size_t)FP * 32 * 2 + MAX_BIAS * FP * 4 + NQ * TILE * 4 + (3 * FP + 4) * 4 +
+                              16 * 8 + 16 + 128 /* alignment slack */;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit of a CTA");
 
 __device__ __forceinline__ Shared carve_shared(uint8_t* raw) {
-  uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 127) & ~(uintptr_t)127);
   Shared s;
   s.wbig[0] = p; p += 2 * IMG_BIG;
   s.wbig[1] = p; p += 2 * IMG_BIG;
   s.wsmall = p; p += 2 * FP * 32 * 2;
   s.bias = reinterpret_cast<float*>(p); p += MAX_BIAS * FP * 4;
-  s.xchg = reinterpret_cast<float*>(p); p += 2 * TILE * 4;
+  s.xchg = reinterpret_cast<float*>(p); p += NQ * TILE * 4;
   s.head_w = reinterpret_cast<float*>(p); p += (3 * FP + 4) * 4;
   uint64_t* b = reinterpret_cast<uint64_t*>(p);
   s.bar_wsmall = b; s.bar_wfull = b + 1; s.bar_wempty = b + 3; s.bar_a = b + 5; s.bar_accfull = b + 10; s.bar_accempty = b + 12;
@@ -208,7 +212,7 @@ __device__ __forceinline__ void mma_role(const Shared& sh, const LayerStep (&pro
 // ------------------------------------------------------------------------------------------------ epilogue helpers
 struct EpiCtx {
   int row;          // row of the tile this thread owns (= TMEM lane)
-  int half;         // 0: columns [32c, 32c+16) of every chunk, 1: [32c+16, 32c+32)
+  int q;            // column quarter: this thread handles columns [32c + 8q, 32c + 8q + 8) of every chunk
   int lane, warp;
   uint32_t tmem_lane_base;   // tmem_base + (lane quarter << 16)
   uint32_t accfull_parity;   // bit b: parity to wait for on bar_accfull[b]
@@ -223,65 +227,69 @@ __device__ __forceinline__ void epi_signal_chunk(const Shared& sh, const EpiCtx&
   if (cx.lane == 0) mbar_arrive(&sh.bar_a[c]);
 }
 
-// combine a per-thread partial row value across the two column halves (max or sum)
+// combine a per-thread partial row value across the four column quarters (max or sum)
 template <bool IS_MAX>
 __device__ __forceinline__ float epi_exchange(const Shared& sh, const EpiCtx& cx, float v) {
-  sh.xchg[cx.half * TILE + cx.row] = v;
+  sts32(&sh.xchg[cx.q * TILE + cx.row], v);
   named_bar_sync(1, EPI_THREADS);
-  const float o = sh.xchg[(cx.half ^ 1) * TILE + cx.row];
+  float r = IS_MAX ? v : 0.f;
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    const float o = lds32(&sh.xchg[j * TILE + cx.row]);
+    r = IS_MAX ? fmaxf(r, o) : r + o;      // sums are formed in quarter order by every thread: identical result in all four
+  }
   named_bar_sync(1, EPI_THREADS);
-  return IS_MAX ? fmaxf(v, o) : v + o;
+  return r;
 }
 
-__device__ __forceinline__ void epi_wait_acc(const Shared& sh, EpiCtx& cx, int ab) {
+// Writes this thread's 8 values of chunk c of the next layer's A.
+__device__ __forceinline__ void epi_store_a(const EpiCtx& cx, int c, const float (&v)[QW], float scale) {
+  float s[QW];
+#pragma unroll
+  for (int i = 0; i < QW; ++i) s[i] = v[i] * scale;
+  uint32_t hi[4], lo[4];
+  split8(s, hi, lo);
+  tmem_st4(cx.tmem_lane_base + COL_AHI + 16 * c + 4 * cx.q, hi);
+  tmem_st4(cx.tmem_lane_base + COL_ALO + 16 * c + 4 * cx.q, lo);
+}
+
+// Generic layer epilogue.  The thread's 5 x 8 accumulator values are read up front (one wait) and the
+// accumulator buffer is handed back to the MMA warp immediately; then per chunk:
+//   v = acc * unscale (+ bias) ; extra(c, col0, v) ; [relu] ; consume(c, col0, v).
+template <bool RELU, class Extra, class Consume>
+__device__ __forceinline__ void epi_layer(const Shared& sh, EpiCtx& cx, int ab, float unscale, const float* bias_s, Extra extra, Consume consume) {
   mbar_wait(&sh.bar_accfull[ab], (cx.accfull_parity >> ab) & 1);
   cx.accfull_parity ^= 1u << ab;
   tc_fence_after();
-}
-__device__ __forceinline__ void epi_release_acc(const Shared& sh, const EpiCtx& cx, int ab) {
+  const uint32_t acc = cx.tmem_lane_base + (ab ? COL_ACC1 : COL_ACC0) + QW * cx.q;
+  uint32_t r[NCHUNK][QW];
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) tmem_ld8(acc + 32 * c, r[c]);
+  tmem_wait_ld();
   tc_fence_before();
   __syncwarp();
   if (cx.lane == 0) mbar_arrive(&sh.bar_accempty[ab]);
-}
-
-// Writes one half-chunk (16 values of this row) of the next layer's A.
-__device__ __forceinline__ void epi_store_a(const EpiCtx& cx, int c, const float (&v)[16], float scale) {
-  float s[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) s[i] = v[i] * scale;
-  uint32_t hi[8], lo[8];
-  split16(s, hi, lo);
-  tmem_st8(cx.tmem_lane_base + COL_AHI + 16 * c + 8 * cx.half, hi);
-  tmem_st8(cx.tmem_lane_base + COL_ALO + 16 * c + 8 * cx.half, lo);
-}
-
-// Generic layer epilogue.  For every half-chunk: v = acc * unscale (+ bias) (+ extra(c, i)), then
-// `consume(c, col0, v)` decides what happens with the 16 values.
-template <bool RELU, class Extra, class Consume>
-__device__ __forceinline__ void epi_layer(const Shared& sh, EpiCtx& cx, int ab, float unscale, const float* bias_s, Extra extra, Consume consume) {
-  epi_wait_acc(sh, cx, ab);
-  const uint32_t acc = cx.tmem_lane_base + (ab ? COL_ACC1 : COL_ACC0);
-#pragma unroll 1
   for (int c = 0; c < NCHUNK; ++c) {
-    const int col0 = 32 * c + 16 * cx.half;
-    uint32_t r[16];
-    tmem_ld16(acc + col0, r);
-    tmem_wait_ld();
-    float v[16];
+    const int col0 = 32 * c + QW * cx.q;
+    float v[QW];
+    if (bias_s) {
+      const float4 b0 = lds128(bias_s + col0), b1 = lds128(bias_s + col0 + 4);
+      v[0] = fmaf(__uint_as_float(r[c][0]), unscale, b0.x); v[1] = fmaf(__uint_as_float(r[c][1]), unscale, b0.y);
+      v[2] = fmaf(__uint_as_float(r[c][2]), unscale, b0.z); v[3] = fmaf(__uint_as_float(r[c][3]), unscale, b0.w);
+      v[4] = fmaf(__uint_as_float(r[c][4]), unscale, b1.x); v[5] = fmaf(__uint_as_float(r[c][5]), unscale, b1.y);
+      v[6] = fmaf(__uint_as_float(r[c][6]), unscale, b1.z); v[7] = fmaf(__uint_as_float(r[c][7]), unscale, b1.w);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float x = __uint_as_float(r[i]) * unscale;
-      if (bias_s) x += bias_s[col0 + i];
-      v[i] = x;
+      for (int i = 0; i < QW; ++i) v[i] = __uint_as_float(r[c][i]) * unscale;
     }
     extra(c, col0, v);
     if (RELU) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      for (int i = 0; i < QW; ++i) v[i] = fmaxf(v[i], 0.f);
     }
     consume(c, col0, v);
   }
-  epi_release_acc(sh, cx, ab);
 }
 
 }  // namespace tc

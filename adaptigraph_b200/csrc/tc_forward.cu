@@ -104,7 +104,7 @@ __device__ __forceinline__ EpiCtx make_ctx(uint32_t tmem_base) {
   cx.lane = threadIdx.x & 31;
   cx.warp = threadIdx.x >> 5;
   cx.row = (cx.warp & 3) * 32 + cx.lane;
-  cx.half = cx.warp >> 2;
+  cx.q = cx.warp >> 2;
   cx.tmem_lane_base = tmem_base + ((uint32_t)((cx.warp & 3) * 32) << 16);
   cx.accfull_parity = 0;
   cx.e_in = 0;
@@ -112,20 +112,14 @@ __device__ __forceinline__ EpiCtx make_ctx(uint32_t tmem_base) {
   return cx;
 }
 
-__device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
+__device__ __forceinline__ float max8(const float (&v)[QW], float m) {   // max |v|
 #pragma unroll
-  for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int i = 0; i < QW; ++i) m = fmaxf(m, fabsf(v[i]));
+  return m;
 }
-__device__ __forceinline__ void load16(const float* src, float (&v)[16]) {
+__device__ __forceinline__ float max8_pos(const float (&v)[QW], float m) {   // v >= 0 (after ReLU)
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 t = reinterpret_cast<const float4*>(src)[i];
-    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-  }
-}
-__device__ __forceinline__ float max16(const float (&v)[16], float m) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) m = fmaxf(m, fabsf(v[i]));
+  for (int i = 0; i < QW; ++i) m = fmaxf(m, v[i]);
   return m;
 }
 
@@ -134,9 +128,9 @@ __device__ __forceinline__ void epi_relu_to_a(const Shared& sh, EpiCtx& cx, int 
   const int e_next = scale_exp(cx.rowmax_in * meta_l.y + meta_l.z);
   const float sc = exp2i(e_next), unscale = exp2i(-cx.e_in) * meta_l.x;
   float mx = 0.f;
-  epi_layer<true>(sh, cx, l & 1, unscale, bias_s, [](int, int, float (&)[16]) {},
-                  [&](int c, int, float (&v)[16]) {
-                    mx = max16(v, mx);
+  epi_layer<true>(sh, cx, l & 1, unscale, bias_s, [](int, int, float (&)[QW]) {},
+                  [&](int c, int, float (&v)[QW]) {
+                    mx = max8_pos(v, mx);
                     epi_store_a(cx, c, v, sc);
                     epi_signal_chunk(sh, cx, c);
                   });
@@ -149,10 +143,10 @@ __device__ __forceinline__ float epi_store_rows(const Shared& sh, EpiCtx& cx, in
                                                 int64_t grow, bool valid) {
   const float unscale = exp2i(-cx.e_in) * meta_l.x;
   float mx = 0.f;
-  epi_layer<false>(sh, cx, l & 1, unscale, bias_s, [](int, int, float (&)[16]) {},
-                   [&](int, int col0, float (&v)[16]) {
-                     mx = max16(v, mx);
-                     if (valid) store16(out + grow * FP + col0, v);
+  epi_layer<false>(sh, cx, l & 1, unscale, bias_s, [](int, int, float (&)[QW]) {},
+                   [&](int, int col0, float (&v)[QW]) {
+                     mx = max8(v, mx);
+                     if (valid) stg256(out + grow * FP + col0, v);
                    });
   return mx;
 }
@@ -185,35 +179,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t e = (int64_t)tile * TILE + cx.row;
       const bool valid = e < E;
-      // ---- producer: 17 relation inputs (model.py:224-253), split over the two column halves
-      float in[32];
+      // ---- producer: 17 relation inputs (model.py:224-253); quarter q builds inputs [8q, 8q+8) of the K=32 layer
+      float v[QW];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) in[i] = 0.f;
-      if (valid) {
+      for (int i = 0; i < QW; ++i) v[i] = 0.f;
+      if (valid && cx.q < 3) {
         const int r = a.recv[e];
         const int s = (r / a.N) * a.N + a.send[e];
         const float4* fr = reinterpret_cast<const float4*>(a.nfeat + (size_t)r * NFEAT);
         const float4* fs = reinterpret_cast<const float4*>(a.nfeat + (size_t)s * NFEAT);
-        const float4 r0 = fr[0], r1 = fr[1], r2 = fr[2], r3 = fr[3];
-        const float4 s0 = fs[0], s1 = fs[1], s2 = fs[2], s3 = fs[3];
-        in[0] = r3.x; in[1] = r3.y; in[2] = s3.x; in[3] = s3.y;
-        in[4] = fabsf(r3.z - s3.z);
-        in[5] = r0.x - s0.x; in[6] = r0.y - s0.y; in[7] = r0.z - s0.z; in[8] = r0.w - s0.w;
-        in[9] = r1.x - s1.x; in[10] = r1.y - s1.y; in[11] = r1.z - s1.z; in[12] = r1.w - s1.w;
-        in[13] = r2.x - s2.x; in[14] = r2.y - s2.y; in[15] = r2.z - s2.z; in[16] = r2.w - s2.w;
+        if (cx.q == 0) {          // [attr_r, attr_s, |group_r - group_s|, hist diff 0..2]
+          const float4 r3 = fr[3], s3 = fs[3], r0 = fr[0], s0 = fs[0];
+          v[0] = r3.x; v[1] = r3.y; v[2] = s3.x; v[3] = s3.y; v[4] = fabsf(r3.z - s3.z);
+          v[5] = r0.x - s0.x; v[6] = r0.y - s0.y; v[7] = r0.z - s0.z;
+        } else if (cx.q == 1) {   // hist diff 3..10
+          const float4 r0 = fr[0], s0 = fs[0], r1 = fr[1], s1 = fs[1], r2 = fr[2], s2 = fs[2];
+          v[0] = r0.w - s0.w;
+          v[1] = r1.x - s1.x; v[2] = r1.y - s1.y; v[3] = r1.z - s1.z; v[4] = r1.w - s1.w;
+          v[5] = r2.x - s2.x; v[6] = r2.y - s2.y; v[7] = r2.z - s2.z;
+        } else {                  // hist diff 11
+          v[0] = fr[2].w - fs[2].w;
+        }
       }
-      float mx = 0.f;
-#pragma unroll
-      for (int i = 0; i < 17; ++i) mx = fmaxf(mx, fabsf(in[i]));
+      const float mx = epi_exchange<true>(sh, cx, max8(v, 0.f));
       cx.e_in = scale_exp(mx);
       cx.rowmax_in = mx;
-      {
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = cx.half ? in[16 + i] : in[i];
-        epi_store_a(cx, 0, v, exp2i(cx.e_in));
-        epi_signal_chunk(sh, cx, 0);
-      }
+      epi_store_a(cx, 0, v, exp2i(cx.e_in));
+      epi_signal_chunk(sh, cx, 0);
       epi_relu_to_a(sh, cx, 0, meta[0], sh.bias + 0 * FP);
       epi_relu_to_a(sh, cx, 1, meta[1], sh.bias + 1 * FP);
       epi_relu_to_a(sh, cx, 2, meta[2], sh.bias + 2 * FP);
@@ -250,10 +242,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t r = (int64_t)tile * TILE + cx.row;
       const bool valid = r < rows;
-      float in[16];
+      float in[QW];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) in[i] = 0.f;
-      if (valid) {
+      for (int i = 0; i < QW; ++i) in[i] = 0.f;
+      if (valid && cx.q == 0) {   // the K=16 input layer only needs quarter 0 (6 real inputs)
         const int b = (int)(r / a.N), n = (int)(r - (int64_t)b * a.N);
         float s[H_FIX][3];
 #pragma unroll
@@ -262,24 +254,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
           s[h][0] = p[0]; s[h][1] = p[1]; s[h][2] = p[2];
         }
         const float a0 = a.attrs[r * 2 + 0], a1 = a.attrs[r * 2 + 1];
-        if (cx.half == 0) {
-          const float grp = n < a.n_p ? a.p_instance[(size_t)b * a.n_p + n] : 0.f;
-          float4* nf = reinterpret_cast<float4*>(a.nfeat + r * NFEAT);      // model.py:155-165 history record
-          nf[0] = make_float4(s[1][0] - s[0][0], s[1][1] - s[0][1], s[1][2] - s[0][2], s[2][0] - s[1][0]);
-          nf[1] = make_float4(s[2][1] - s[1][1], s[2][2] - s[1][2], s[3][0] - s[2][0], s[3][1] - s[2][1]);
-          nf[2] = make_float4(s[3][2] - s[2][2], s[3][0], s[3][1], s[3][2]);
-          nf[3] = make_float4(a0, a1, grp, 0.f);
-        }
+        const float grp = n < a.n_p ? a.p_instance[(size_t)b * a.n_p + n] : 0.f;
+        float4* nf = reinterpret_cast<float4*>(a.nfeat + r * NFEAT);      // model.py:155-165 history record
+        nf[0] = make_float4(s[1][0] - s[0][0], s[1][1] - s[0][1], s[1][2] - s[0][2], s[2][0] - s[1][0]);
+        nf[1] = make_float4(s[2][1] - s[1][1], s[2][2] - s[1][2], s[3][0] - s[2][0], s[3][1] - s[2][1]);
+        nf[2] = make_float4(s[3][2] - s[2][2], s[3][0], s[3][1], s[3][2]);
+        nf[3] = make_float4(a0, a1, grp, 0.f);
         in[0] = a0; in[1] = a1;
         in[2] = n < a.n_p ? a.physics[b] : 0.f;                               // model.py:186-189
         in[3] = a.action[r * 3 + 0]; in[4] = a.action[r * 3 + 1]; in[5] = a.action[r * 3 + 2];
       }
-      float mx = 0.f;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) mx = fmaxf(mx, fabsf(in[i]));
+      const float mx = epi_exchange<true>(sh, cx, max8(in, 0.f));
       cx.e_in = scale_exp(mx);
       cx.rowmax_in = mx;
-      if (cx.half == 0) epi_store_a(cx, 0, in, exp2i(cx.e_in));
+      if (cx.q < 2) epi_store_a(cx, 0, in, exp2i(cx.e_in));   // quarters 0 and 1 cover the 16 K columns
       epi_signal_chunk(sh, cx, 0);
 
       epi_relu_to_a(sh, cx, 0, meta[0], sh.bias + 0 * FP);
@@ -289,21 +277,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
         const int e_next = scale_exp(cx.rowmax_in * m.y + m.z);
         const float sc = exp2i(e_next), unscale = exp2i(-cx.e_in) * m.x;
         float pm = 0.f;
-        epi_layer<true>(sh, cx, 0, unscale, sh.bias + 2 * FP, [](int, int, float (&)[16]) {},
-                        [&](int c, int col0, float (&v)[16]) {
-                          pm = max16(v, pm);
+        epi_layer<true>(sh, cx, 0, unscale, sh.bias + 2 * FP, [](int, int, float (&)[QW]) {},
+                        [&](int c, int col0, float (&v)[QW]) {
+                          pm = max8_pos(v, pm);
                           epi_store_a(cx, c, v, sc);
                           epi_signal_chunk(sh, cx, c);
-                          if (valid) store16(a.P + r * FP + col0, v);
+                          if (valid) stg256(a.P + r * FP + col0, v);
                         });
         pm = epi_exchange<true>(sh, cx, pm);
         cx.rowmax_in = pm;
         cx.e_in = e_next;
-        if (valid && cx.half == 0) a.rowmaxP[r] = pm;
+        if (valid && cx.q == 0) a.rowmaxP[r] = pm;
       }
       float am = epi_store_rows(sh, cx, 3, meta[3], sh.bias + 3 * FP, a.A, r, valid);   // A_n = W_enc*penc + b
       am = epi_exchange<true>(sh, cx, am);
-      if (valid && cx.half == 0) a.rowmaxA[r] = am;
+      if (valid && cx.q == 0) a.rowmaxA[r] = am;
       epi_store_rows(sh, cx, 4, meta[4], nullptr, a.Qr, r, valid);
       epi_store_rows(sh, cx, 5, meta[5], nullptr, a.Qs, r, valid);
     }
@@ -346,16 +334,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
       const bool valid = r < rows;
       // ---- producer: the aggregated relation effects of this row become A (K = 160)
       {
-        float g[NCHUNK][16];
+        float g[NCHUNK][QW];
         float mx = 0.f;
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
-          if (valid) load16(a.agg + r * FP + 32 * c + 16 * cx.half, g[c]);
+          if (valid) ldg256(a.agg + r * FP + 32 * c + QW * cx.q, g[c]);
           else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) g[c][i] = 0.f;
+            for (int i = 0; i < QW; ++i) g[c][i] = 0.f;
           }
-          mx = max16(g[c], mx);
+          mx = max8(g[c], mx);
         }
         mx = epi_exchange<true>(sh, cx, mx);
         cx.e_in = scale_exp(mx);
@@ -369,30 +357,30 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
       }
       {  // P <- relu((W_agg*agg + A_n) + P)   (model.py:36-40, :299-301)
         const float4 m = meta[0];
-        const float extra_bound = valid ? a.rowmaxA[r] + a.rowmaxP[r] : 0.f;
+        const float extra_bound = valid ? a.rowmaxA[r] + a.rowmaxP[r] : 0.f;   // bound on |A_n + P| of this row
         const int e_next = scale_exp(cx.rowmax_in * m.y + extra_bound);
         const float sc = exp2i(e_next), unscale = exp2i(-cx.e_in) * m.x;
         float pm = 0.f;
         epi_layer<true>(sh, cx, 0, unscale, nullptr,
-                        [&](int, int col0, float (&v)[16]) {
+                        [&](int, int col0, float (&v)[QW]) {
                           if (valid) {
-                            float an[16], pp[16];
-                            load16(a.A + r * FP + col0, an);
-                            load16(a.P + r * FP + col0, pp);
+                            float an[QW], pp[QW];
+                            ldg256(a.A + r * FP + col0, an);
+                            ldg256(a.P + r * FP + col0, pp);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = (v[i] + an[i]) + pp[i];
+                            for (int i = 0; i < QW; ++i) v[i] = (v[i] + an[i]) + pp[i];
                           }
                         },
-                        [&](int c, int col0, float (&v)[16]) {
-                          pm = max16(v, pm);
+                        [&](int c, int col0, float (&v)[QW]) {
+                          pm = max8_pos(v, pm);
                           epi_store_a(cx, c, v, sc);
                           epi_signal_chunk(sh, cx, c);
-                          if (!LAST && valid) store16(a.P + r * FP + col0, v);
+                          if (!LAST && valid) stg256(a.P + r * FP + col0, v);
                         });
         pm = epi_exchange<true>(sh, cx, pm);
         cx.rowmax_in = pm;
         cx.e_in = e_next;
-        if (!LAST && valid && cx.half == 0) a.rowmaxP[r] = pm;
+        if (!LAST && valid && cx.q == 0) a.rowmaxP[r] = pm;
       }
       if (!LAST) {
         epi_store_rows(sh, cx, 1, meta[1], nullptr, a.Qr, r, valid);
@@ -402,22 +390,24 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
         // motion head (model.py:306-309): relu(linear_1) then the 3-row linear_2 as running dot products
         const float unscale = exp2i(-cx.e_in) * meta[2].x;
         float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-        epi_layer<true>(sh, cx, 0, unscale, sh.bias + 1 * FP, [](int, int, float (&)[16]) {},
-                        [&](int, int col0, float (&v)[16]) {
+        epi_layer<true>(sh, cx, 0, unscale, sh.bias + 1 * FP, [](int, int, float (&)[QW]) {},
+                        [&](int, int col0, float (&v)[QW]) {
 #pragma unroll
-                          for (int i = 0; i < 16; ++i) {
-                            m0 = fmaf(v[i], sh.head_w[col0 + i], m0);
-                            m1 = fmaf(v[i], sh.head_w[FP + col0 + i], m1);
-                            m2 = fmaf(v[i], sh.head_w[2 * FP + col0 + i], m2);
+                          for (int h = 0; h < 2; ++h) {
+                            const float4 w0 = lds128(sh.head_w + col0 + 4 * h), w1 = lds128(sh.head_w + FP + col0 + 4 * h),
+                                         w2 = lds128(sh.head_w + 2 * FP + col0 + 4 * h);
+                            m0 = fmaf(v[4 * h + 3], w0.w, fmaf(v[4 * h + 2], w0.z, fmaf(v[4 * h + 1], w0.y, fmaf(v[4 * h], w0.x, m0))));
+                            m1 = fmaf(v[4 * h + 3], w1.w, fmaf(v[4 * h + 2], w1.z, fmaf(v[4 * h + 1], w1.y, fmaf(v[4 * h], w1.x, m1))));
+                            m2 = fmaf(v[4 * h + 3], w2.w, fmaf(v[4 * h + 2], w2.z, fmaf(v[4 * h + 1], w2.y, fmaf(v[4 * h], w2.x, m2))));
                           }
                         });
         m0 = epi_exchange<false>(sh, cx, m0);
         m1 = epi_exchange<false>(sh, cx, m1);
         m2 = epi_exchange<false>(sh, cx, m2);
-        if (valid && cx.half == 0) {
+        if (valid && cx.q == 0) {
           const int b = (int)(r / a.N), n = (int)(r - (int64_t)b * a.N);
           if (n < a.n_p) {
-            m0 += sh.head_w[3 * FP + 0]; m1 += sh.head_w[3 * FP + 1]; m2 += sh.head_w[3 * FP + 2];
+            m0 += lds32(sh.head_w + 3 * FP + 0); m1 += lds32(sh.head_w + 3 * FP + 1); m2 += lds32(sh.head_w + 3 * FP + 2);
             float* mo = a.pred_motion + ((size_t)b * a.n_p + n) * 3;
             mo[0] = m0; mo[1] = m1; mo[2] = m2;
             const float* cur = a.state + (((size_t)b * H_FIX + (H_FIX - 1)) * a.N + n) * 3;
