@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libadaptigraph_b200.so")
+LIB_PATH = os.environ.get("AGX_LIB", os.path.join(HERE, "libadaptigraph_b200.so"))
 
 AGX_FP = 160
 AGX_MAX_TOPK = 32

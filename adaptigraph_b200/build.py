@@ -29,18 +29,18 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    if not force and not _stale() and out == LIB:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines] + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode:
-        raise RuntimeError("nvcc failed building libadaptigraph_b200.so")
-    return LIB
+        raise RuntimeError("nvcc failed building " + os.path.basename(out))
+    return out
 
 
 if __name__ == "__main__":

@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t chain_setup(Shared& sh, uint8_t* smem_raw, c
   if (tid == 0) {
     mbar_init(sh.bar_wsmall, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&sh.bar_wfull[i], 1); mbar_init(&sh.bar_wempty[i], 1); mbar_init(&sh.bar_accfull[i], 1); mbar_init(&sh.bar_accempty[i], EPI_WARPS); }
-    for (int i = 0; i < NCHUNK; ++i) mbar_init(&sh.bar_a[i], EPI_WARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh.bar_a[i], EPI_WARPS); mbar_init(&sh.bar_in[i], EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == MMA_WARP) tmem_alloc(sh.tmem_ptr, TMEM_COLS);
@@ -106,7 +106,8 @@ __device__ __forceinline__ EpiCtx make_ctx(uint32_t tmem_base) {
   cx.row = (cx.warp & 3) * 32 + cx.lane;
   cx.q = cx.warp >> 2;
   cx.tmem_lane_base = tmem_base + ((uint32_t)((cx.warp & 3) * 32) << 16);
-  cx.accfull_parity = 0;
+  cx.acc_parity = 0;
+  cx.a_cur = 0;
   cx.e_in = 0;
   cx.rowmax_in = 0.f;
   return cx;
@@ -122,33 +123,39 @@ __device__ __forceinline__ float max8_pos(const float (&v)[QW], float m) {   // 
   for (int i = 0; i < QW; ++i) m = fmaxf(m, v[i]);
   return m;
 }
+struct NoExtra { __device__ void operator()(int, int, float (&)[QW]) const {} };
 
-// relu(bias + acc) -> next A (split fp16), tracking the row maximum for the next layer's scale
-__device__ __forceinline__ void epi_relu_to_a(const Shared& sh, EpiCtx& cx, int l, const float4 meta_l, const float* bias_s) {
+// relu(bias + acc) -> next A (split fp16, other buffer), tracking the row maximum for the next layer's scale
+__device__ __forceinline__ void epi_relu_to_a(const Shared& sh, EpiCtx& cx, const float4 meta_l, const float* bias_s) {
   const int e_next = scale_exp(cx.rowmax_in * meta_l.y + meta_l.z);
   const float sc = exp2i(e_next), unscale = exp2i(-cx.e_in) * meta_l.x;
+  const int dst = cx.a_cur ^ 1;
   float mx = 0.f;
-  epi_layer<true>(sh, cx, l & 1, unscale, bias_s, [](int, int, float (&)[QW]) {},
-                  [&](int c, int, float (&v)[QW]) {
-                    mx = max8_pos(v, mx);
-                    epi_store_a(cx, c, v, sc);
-                    epi_signal_chunk(sh, cx, c);
-                  });
+  epi_layer<true>(sh, cx, unscale, bias_s, true, NoExtra{}, [&](int c, int, float (&v)[QW]) {
+    mx = max8_pos(v, mx);
+    epi_store_a(cx, dst, c, v, sc);
+  });
   cx.rowmax_in = epi_exchange<true>(sh, cx, mx);
   cx.e_in = e_next;
+  cx.a_cur = dst;
 }
 
-// bias + acc -> fp32 rows in HBM (A in tensor memory is left untouched)
-__device__ __forceinline__ float epi_store_rows(const Shared& sh, EpiCtx& cx, int l, const float4 meta_l, const float* bias_s, float* out,
+// bias + acc -> fp32 rows in HBM (A in tensor memory is left untouched); returns this thread's partial max |v|
+__device__ __forceinline__ float epi_store_rows(const Shared& sh, EpiCtx& cx, const float4 meta_l, const float* bias_s, float* out,
                                                 int64_t grow, bool valid) {
   const float unscale = exp2i(-cx.e_in) * meta_l.x;
   float mx = 0.f;
-  epi_layer<false>(sh, cx, l & 1, unscale, bias_s, [](int, int, float (&)[QW]) {},
-                   [&](int, int col0, float (&v)[QW]) {
-                     mx = max8(v, mx);
-                     if (valid) stg256(out + grow * FP + col0, v);
-                   });
+  epi_layer<false>(sh, cx, unscale, bias_s, false, NoExtra{}, [&](int, int col0, float (&v)[QW]) {
+    mx = max8(v, mx);
+    if (valid) stg256(out + grow * FP + col0, v);
+  });
   return mx;
+}
+
+// input producer tail: per-row scale from the row maximum, split, write chunk(s), signal
+__device__ __forceinline__ void produce_begin(const Shared& sh, EpiCtx& cx, float partial_max, int& e_out, float& max_out) {
+  max_out = epi_exchange<true>(sh, cx, partial_max);
+  e_out = scale_exp(max_out);
 }
 
 // ------------------------------------------------------------------------------------ edge encoder
@@ -161,9 +168,33 @@ struct EdgeArgs {
   float* C;
 };
 
+// 17 relation inputs (model.py:224-253); quarter q builds inputs [8q, 8q+8) of the K=32 first layer
+__device__ __forceinline__ void edge_inputs(const EdgeArgs& a, int64_t e, int64_t E, int q, float (&v)[QW]) {
+#pragma unroll
+  for (int i = 0; i < QW; ++i) v[i] = 0.f;
+  if (e < E && q < 3) {
+    const int r = a.recv[e];
+    const int s = (r / a.N) * a.N + a.send[e];
+    const float4* fr = reinterpret_cast<const float4*>(a.nfeat + (size_t)r * NFEAT);
+    const float4* fs = reinterpret_cast<const float4*>(a.nfeat + (size_t)s * NFEAT);
+    if (q == 0) {          // [attr_r, attr_s, |group_r - group_s|, hist diff 0..2]
+      const float4 r3 = fr[3], s3 = fs[3], r0 = fr[0], s0 = fs[0];
+      v[0] = r3.x; v[1] = r3.y; v[2] = s3.x; v[3] = s3.y; v[4] = fabsf(r3.z - s3.z);
+      v[5] = r0.x - s0.x; v[6] = r0.y - s0.y; v[7] = r0.z - s0.z;
+    } else if (q == 1) {   // hist diff 3..10
+      const float4 r0 = fr[0], s0 = fs[0], r1 = fr[1], s1 = fs[1], r2 = fr[2], s2 = fs[2];
+      v[0] = r0.w - s0.w;
+      v[1] = r1.x - s1.x; v[2] = r1.y - s1.y; v[3] = r1.z - s1.z; v[4] = r1.w - s1.w;
+      v[5] = r2.x - s2.x; v[6] = r2.y - s2.y; v[7] = r2.z - s2.z;
+    } else {               // hist diff 11
+      v[0] = fr[2].w - fs[2].w;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr LayerStep prog[4] = {{T_RENC0, 2, 1}, {T_RENC2, 10, 1}, {T_RENC4, 10, 1}, {T_RP_REL, 10, 1}};
+  constexpr LayerStep prog[4] = {{T_RENC0, 2, IN_PRODUCER}, {T_RENC2, 10, IN_EPILOGUE}, {T_RENC4, 10, IN_EPILOGUE}, {T_RP_REL, 10, IN_EPILOGUE}};
   Shared sh;
   float4 meta[4];
   const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, a.bias, meta);
@@ -176,40 +207,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
     mma_role(sh, prog, tmem_base, n_tiles);
   } else {
     EpiCtx cx = make_ctx(tmem_base);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t e = (int64_t)tile * TILE + cx.row;
-      const bool valid = e < E;
-      // ---- producer: 17 relation inputs (model.py:224-253); quarter q builds inputs [8q, 8q+8) of the K=32 layer
+    int tile = blockIdx.x;
+    int e_nx = 0;
+    float mx_nx = 0.f;
+    if (tile < n_tiles) {   // first tile's input
       float v[QW];
-#pragma unroll
-      for (int i = 0; i < QW; ++i) v[i] = 0.f;
-      if (valid && cx.q < 3) {
-        const int r = a.recv[e];
-        const int s = (r / a.N) * a.N + a.send[e];
-        const float4* fr = reinterpret_cast<const float4*>(a.nfeat + (size_t)r * NFEAT);
-        const float4* fs = reinterpret_cast<const float4*>(a.nfeat + (size_t)s * NFEAT);
-        if (cx.q == 0) {          // [attr_r, attr_s, |group_r - group_s|, hist diff 0..2]
-          const float4 r3 = fr[3], s3 = fs[3], r0 = fr[0], s0 = fs[0];
-          v[0] = r3.x; v[1] = r3.y; v[2] = s3.x; v[3] = s3.y; v[4] = fabsf(r3.z - s3.z);
-          v[5] = r0.x - s0.x; v[6] = r0.y - s0.y; v[7] = r0.z - s0.z;
-        } else if (cx.q == 1) {   // hist diff 3..10
-          const float4 r0 = fr[0], s0 = fs[0], r1 = fr[1], s1 = fs[1], r2 = fr[2], s2 = fs[2];
-          v[0] = r0.w - s0.w;
-          v[1] = r1.x - s1.x; v[2] = r1.y - s1.y; v[3] = r1.z - s1.z; v[4] = r1.w - s1.w;
-          v[5] = r2.x - s2.x; v[6] = r2.y - s2.y; v[7] = r2.z - s2.z;
-        } else {                  // hist diff 11
-          v[0] = fr[2].w - fs[2].w;
-        }
+      edge_inputs(a, (int64_t)tile * TILE + cx.row, E, cx.q, v);
+      produce_begin(sh, cx, max8(v, 0.f), e_nx, mx_nx);
+      epi_store_a(cx, 0, 0, v, exp2i(e_nx));
+      epi_signal(cx, &sh.bar_in[0]);
+    }
+    for (; tile < n_tiles; tile += gridDim.x) {
+      const int64_t e = (int64_t)tile * TILE + cx.row;
+      cx.e_in = e_nx;
+      cx.rowmax_in = mx_nx;
+      const int next = tile + gridDim.x;
+      float vn[QW];
+      if (next < n_tiles) edge_inputs(a, (int64_t)next * TILE + cx.row, E, cx.q, vn);   // gather in flight during this tile
+      epi_relu_to_a(sh, cx, meta[0], sh.bias + 0 * FP);
+      epi_relu_to_a(sh, cx, meta[1], sh.bias + 1 * FP);
+      epi_relu_to_a(sh, cx, meta[2], sh.bias + 2 * FP);
+      if (next < n_tiles) {   // next tile's A goes into the buffer the last layer is not reading
+        produce_begin(sh, cx, max8(vn, 0.f), e_nx, mx_nx);
+        epi_store_a(cx, cx.a_cur ^ 1, 0, vn, exp2i(e_nx));
+        epi_signal(cx, &sh.bar_in[0]);
       }
-      const float mx = epi_exchange<true>(sh, cx, max8(v, 0.f));
-      cx.e_in = scale_exp(mx);
-      cx.rowmax_in = mx;
-      epi_store_a(cx, 0, v, exp2i(cx.e_in));
-      epi_signal_chunk(sh, cx, 0);
-      epi_relu_to_a(sh, cx, 0, meta[0], sh.bias + 0 * FP);
-      epi_relu_to_a(sh, cx, 1, meta[1], sh.bias + 1 * FP);
-      epi_relu_to_a(sh, cx, 2, meta[2], sh.bias + 2 * FP);
-      epi_store_rows(sh, cx, 3, meta[3], sh.bias + 3 * FP, a.C, e, valid);
+      epi_store_rows(sh, cx, meta[3], sh.bias + 3 * FP, a.C, e, e < E);
+      cx.a_cur ^= 1;
     }
   }
   chain_teardown(tmem_base);
@@ -224,9 +248,35 @@ struct NodeArgs {
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* rowmaxP; float* rowmaxA;
 };
 
+// node inputs (model.py:168-195) + the nfeat record; only quarter 0 carries data (6 real inputs of the K=16 layer)
+__device__ __forceinline__ void node_inputs(const NodeArgs& a, int64_t r, int64_t rows, int q, float (&in)[QW]) {
+#pragma unroll
+  for (int i = 0; i < QW; ++i) in[i] = 0.f;
+  if (r < rows && q == 0) {
+    const int b = (int)(r / a.N), n = (int)(r - (int64_t)b * a.N);
+    float s[H_FIX][3];
+#pragma unroll
+    for (int h = 0; h < H_FIX; ++h) {
+      const float* p = a.state + (((size_t)b * H_FIX + h) * a.N + n) * 3;
+      s[h][0] = p[0]; s[h][1] = p[1]; s[h][2] = p[2];
+    }
+    const float a0 = a.attrs[r * 2 + 0], a1 = a.attrs[r * 2 + 1];
+    const float grp = n < a.n_p ? a.p_instance[(size_t)b * a.n_p + n] : 0.f;
+    float4* nf = reinterpret_cast<float4*>(a.nfeat + r * NFEAT);      // model.py:155-165 history record
+    nf[0] = make_float4(s[1][0] - s[0][0], s[1][1] - s[0][1], s[1][2] - s[0][2], s[2][0] - s[1][0]);
+    nf[1] = make_float4(s[2][1] - s[1][1], s[2][2] - s[1][2], s[3][0] - s[2][0], s[3][1] - s[2][1]);
+    nf[2] = make_float4(s[3][2] - s[2][2], s[3][0], s[3][1], s[3][2]);
+    nf[3] = make_float4(a0, a1, grp, 0.f);
+    in[0] = a0; in[1] = a1;
+    in[2] = n < a.n_p ? a.physics[b] : 0.f;                               // model.py:186-189
+    in[3] = a.action[r * 3 + 0]; in[4] = a.action[r * 3 + 1]; in[5] = a.action[r * 3 + 2];
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr LayerStep prog[6] = {{T_PENC0, 1, 1}, {T_PENC2, 10, 1}, {T_PENC4, 10, 1}, {T_PP_ENC, 10, 1}, {T_RP_RECV, 10, 0}, {T_RP_SEND, 10, 0}};
+  constexpr LayerStep prog[6] = {{T_PENC0, 1, IN_PRODUCER}, {T_PENC2, 10, IN_EPILOGUE}, {T_PENC4, 10, IN_EPILOGUE},
+                                 {T_PP_ENC, 10, IN_EPILOGUE}, {T_RP_RECV, 10, IN_SAME}, {T_RP_SEND, 10, IN_SAME}};
   Shared sh;
   float4 meta[6];
   const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, a.bias, meta);
@@ -239,61 +289,54 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
     mma_role(sh, prog, tmem_base, n_tiles);
   } else {
     EpiCtx cx = make_ctx(tmem_base);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int tile = blockIdx.x;
+    int e_nx = 0;
+    float mx_nx = 0.f;
+    if (tile < n_tiles) {
+      float in[QW];
+      node_inputs(a, (int64_t)tile * TILE + cx.row, rows, cx.q, in);
+      produce_begin(sh, cx, max8(in, 0.f), e_nx, mx_nx);
+      if (cx.q < 2) epi_store_a(cx, 0, 0, in, exp2i(e_nx));   // quarters 0 and 1 cover the 16 K columns
+      epi_signal(cx, &sh.bar_in[0]);
+    }
+    for (; tile < n_tiles; tile += gridDim.x) {
       const int64_t r = (int64_t)tile * TILE + cx.row;
       const bool valid = r < rows;
-      float in[QW];
-#pragma unroll
-      for (int i = 0; i < QW; ++i) in[i] = 0.f;
-      if (valid && cx.q == 0) {   // the K=16 input layer only needs quarter 0 (6 real inputs)
-        const int b = (int)(r / a.N), n = (int)(r - (int64_t)b * a.N);
-        float s[H_FIX][3];
-#pragma unroll
-        for (int h = 0; h < H_FIX; ++h) {
-          const float* p = a.state + (((size_t)b * H_FIX + h) * a.N + n) * 3;
-          s[h][0] = p[0]; s[h][1] = p[1]; s[h][2] = p[2];
-        }
-        const float a0 = a.attrs[r * 2 + 0], a1 = a.attrs[r * 2 + 1];
-        const float grp = n < a.n_p ? a.p_instance[(size_t)b * a.n_p + n] : 0.f;
-        float4* nf = reinterpret_cast<float4*>(a.nfeat + r * NFEAT);      // model.py:155-165 history record
-        nf[0] = make_float4(s[1][0] - s[0][0], s[1][1] - s[0][1], s[1][2] - s[0][2], s[2][0] - s[1][0]);
-        nf[1] = make_float4(s[2][1] - s[1][1], s[2][2] - s[1][2], s[3][0] - s[2][0], s[3][1] - s[2][1]);
-        nf[2] = make_float4(s[3][2] - s[2][2], s[3][0], s[3][1], s[3][2]);
-        nf[3] = make_float4(a0, a1, grp, 0.f);
-        in[0] = a0; in[1] = a1;
-        in[2] = n < a.n_p ? a.physics[b] : 0.f;                               // model.py:186-189
-        in[3] = a.action[r * 3 + 0]; in[4] = a.action[r * 3 + 1]; in[5] = a.action[r * 3 + 2];
-      }
-      const float mx = epi_exchange<true>(sh, cx, max8(in, 0.f));
-      cx.e_in = scale_exp(mx);
-      cx.rowmax_in = mx;
-      if (cx.q < 2) epi_store_a(cx, 0, in, exp2i(cx.e_in));   // quarters 0 and 1 cover the 16 K columns
-      epi_signal_chunk(sh, cx, 0);
-
-      epi_relu_to_a(sh, cx, 0, meta[0], sh.bias + 0 * FP);
-      epi_relu_to_a(sh, cx, 1, meta[1], sh.bias + 1 * FP);
+      cx.e_in = e_nx;
+      cx.rowmax_in = mx_nx;
+      const int next = tile + gridDim.x;
+      float inn[QW];
+      if (next < n_tiles) node_inputs(a, (int64_t)next * TILE + cx.row, rows, cx.q, inn);
+      epi_relu_to_a(sh, cx, meta[0], sh.bias + 0 * FP);
+      epi_relu_to_a(sh, cx, meta[1], sh.bias + 1 * FP);
       {  // particle_encode = particle_effect_0 (model.py:268-269): next A and P rows
         const float4 m = meta[2];
         const int e_next = scale_exp(cx.rowmax_in * m.y + m.z);
         const float sc = exp2i(e_next), unscale = exp2i(-cx.e_in) * m.x;
+        const int dst = cx.a_cur ^ 1;
         float pm = 0.f;
-        epi_layer<true>(sh, cx, 0, unscale, sh.bias + 2 * FP, [](int, int, float (&)[QW]) {},
-                        [&](int c, int col0, float (&v)[QW]) {
-                          pm = max8_pos(v, pm);
-                          epi_store_a(cx, c, v, sc);
-                          epi_signal_chunk(sh, cx, c);
-                          if (valid) stg256(a.P + r * FP + col0, v);
-                        });
+        epi_layer<true>(sh, cx, unscale, sh.bias + 2 * FP, true, NoExtra{}, [&](int c, int col0, float (&v)[QW]) {
+          pm = max8_pos(v, pm);
+          epi_store_a(cx, dst, c, v, sc);
+          if (valid) stg256(a.P + r * FP + col0, v);
+        });
         pm = epi_exchange<true>(sh, cx, pm);
         cx.rowmax_in = pm;
         cx.e_in = e_next;
+        cx.a_cur = dst;
         if (valid && cx.q == 0) a.rowmaxP[r] = pm;
       }
-      float am = epi_store_rows(sh, cx, 3, meta[3], sh.bias + 3 * FP, a.A, r, valid);   // A_n = W_enc*penc + b
+      if (next < n_tiles) {
+        produce_begin(sh, cx, max8(inn, 0.f), e_nx, mx_nx);
+        if (cx.q < 2) epi_store_a(cx, cx.a_cur ^ 1, 0, inn, exp2i(e_nx));
+        epi_signal(cx, &sh.bar_in[0]);
+      }
+      float am = epi_store_rows(sh, cx, meta[3], sh.bias + 3 * FP, a.A, r, valid);   // A_n = W_enc*penc + b
       am = epi_exchange<true>(sh, cx, am);
       if (valid && cx.q == 0) a.rowmaxA[r] = am;
-      epi_store_rows(sh, cx, 4, meta[4], nullptr, a.Qr, r, valid);
-      epi_store_rows(sh, cx, 5, meta[5], nullptr, a.Qs, r, valid);
+      epi_store_rows(sh, cx, meta[4], nullptr, a.Qr, r, valid);
+      epi_store_rows(sh, cx, meta[5], nullptr, a.Qs, r, valid);
+      cx.a_cur ^= 1;
     }
   }
   chain_teardown(tmem_base);
@@ -309,10 +352,37 @@ struct UpdArgs {
   const float* state; float* pred_pos; int64_t pos_stride_b; float* pred_motion;
 };
 
+__device__ __forceinline__ float agg_inputs(const UpdArgs& a, int64_t r, int64_t rows, int q, float (&g)[NCHUNK][QW]) {
+  float mx = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    if (r < rows) ldg256(a.agg + r * FP + 32 * c + QW * q, g[c]);
+    else {
+#pragma unroll
+      for (int i = 0; i < QW; ++i) g[c][i] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) mx = max8(g[c], mx);
+  return mx;
+}
+__device__ __forceinline__ void agg_produce(const Shared& sh, EpiCtx& cx, const float (&g)[NCHUNK][QW], float partial_max, int buf, int& e_out,
+                                            float& max_out) {
+  produce_begin(sh, cx, partial_max, e_out, max_out);
+  const float sc = exp2i(e_out);
+#pragma unroll
+  for (int c = 0; c < NCHUNK_A; ++c) epi_store_a(cx, buf, c, g[c], sc);
+  epi_signal(cx, &sh.bar_in[0]);
+#pragma unroll
+  for (int c = NCHUNK_A; c < NCHUNK; ++c) epi_store_a(cx, buf, c, g[c], sc);
+  epi_signal(cx, &sh.bar_in[1]);
+}
+
 template <bool LAST>
 __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr LayerStep prog[3] = {{T_PP_AGG, 10, 1}, {LAST ? T_PRED0 : T_RP_RECV, 10, 1}, {LAST ? T_PRED1 : T_RP_SEND, 10, LAST ? 1 : 0}};
+  constexpr LayerStep prog[3] = {{T_PP_AGG, 10, IN_PRODUCER}, {LAST ? T_PRED0 : T_RP_RECV, 10, IN_EPILOGUE},
+                                 {LAST ? T_PRED1 : T_RP_SEND, 10, LAST ? IN_EPILOGUE : IN_SAME}};
   Shared sh;
   float4 meta[3];
   const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, a.bias, meta);
@@ -329,78 +399,80 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
     mma_role(sh, prog, tmem_base, n_tiles);
   } else {
     EpiCtx cx = make_ctx(tmem_base);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int tile = blockIdx.x;
+    int e_nx = 0;
+    float mx_nx = 0.f;
+    if (tile < n_tiles) {   // first tile: the aggregated relation effects of this row become A (K = 160)
+      float g[NCHUNK][QW];
+      const float pmx = agg_inputs(a, (int64_t)tile * TILE + cx.row, rows, cx.q, g);
+      agg_produce(sh, cx, g, pmx, 0, e_nx, mx_nx);
+    }
+    for (; tile < n_tiles; tile += gridDim.x) {
       const int64_t r = (int64_t)tile * TILE + cx.row;
       const bool valid = r < rows;
-      // ---- producer: the aggregated relation effects of this row become A (K = 160)
-      {
-        float g[NCHUNK][QW];
-        float mx = 0.f;
-#pragma unroll
-        for (int c = 0; c < NCHUNK; ++c) {
-          if (valid) ldg256(a.agg + r * FP + 32 * c + QW * cx.q, g[c]);
-          else {
-#pragma unroll
-            for (int i = 0; i < QW; ++i) g[c][i] = 0.f;
-          }
-          mx = max8(g[c], mx);
-        }
-        mx = epi_exchange<true>(sh, cx, mx);
-        cx.e_in = scale_exp(mx);
-        cx.rowmax_in = mx;
-        const float sc = exp2i(cx.e_in);
-#pragma unroll
-        for (int c = 0; c < NCHUNK; ++c) {
-          epi_store_a(cx, c, g[c], sc);
-          epi_signal_chunk(sh, cx, c);
-        }
-      }
+      cx.e_in = e_nx;
+      cx.rowmax_in = mx_nx;
+      const int next = tile + gridDim.x;
       {  // P <- relu((W_agg*agg + A_n) + P)   (model.py:36-40, :299-301)
         const float4 m = meta[0];
         const float extra_bound = valid ? a.rowmaxA[r] + a.rowmaxP[r] : 0.f;   // bound on |A_n + P| of this row
         const int e_next = scale_exp(cx.rowmax_in * m.y + extra_bound);
         const float sc = exp2i(e_next), unscale = exp2i(-cx.e_in) * m.x;
+        const int dst = cx.a_cur ^ 1;
         float pm = 0.f;
-        epi_layer<true>(sh, cx, 0, unscale, nullptr,
-                        [&](int, int col0, float (&v)[QW]) {
+        // residual rows A_n and P: software pipeline of depth one (chunk c+1 is requested before chunk c is used)
+        float an[2][QW], pp[2][QW];
+        const float* a_row = a.A + r * FP + QW * cx.q;
+        const float* p_row = a.P + r * FP + QW * cx.q;
+        if (valid) { ldg256(a_row, an[0]); ldg256(p_row, pp[0]); }
+        epi_layer<true, false>(sh, cx, unscale, nullptr, true,
+                        [&](int c, int, float (&v)[QW]) {
                           if (valid) {
-                            float an[QW], pp[QW];
-                            ldg256(a.A + r * FP + col0, an);
-                            ldg256(a.P + r * FP + col0, pp);
+                            if (c + 1 < NCHUNK) { ldg256(a_row + 32 * (c + 1), an[(c + 1) & 1]); ldg256(p_row + 32 * (c + 1), pp[(c + 1) & 1]); }
 #pragma unroll
-                            for (int i = 0; i < QW; ++i) v[i] = (v[i] + an[i]) + pp[i];
+                            for (int i = 0; i < QW; ++i) v[i] = (v[i] + an[c & 1][i]) + pp[c & 1][i];
                           }
                         },
                         [&](int c, int col0, float (&v)[QW]) {
                           pm = max8_pos(v, pm);
-                          epi_store_a(cx, c, v, sc);
-                          epi_signal_chunk(sh, cx, c);
+                          epi_store_a(cx, dst, c, v, sc);
                           if (!LAST && valid) stg256(a.P + r * FP + col0, v);
                         });
         pm = epi_exchange<true>(sh, cx, pm);
         cx.rowmax_in = pm;
         cx.e_in = e_next;
+        cx.a_cur = dst;
         if (!LAST && valid && cx.q == 0) a.rowmaxP[r] = pm;
       }
+      // the next tile's aggregated effects are fetched and written into the free A buffer while the MMA warp is
+      // busy with the remaining layers of this tile (the epilogue threads have slack there)
+      auto produce_next = [&]() {
+        if (next < n_tiles) {
+          float gn[NCHUNK][QW];
+          const float pmx_n = agg_inputs(a, (int64_t)next * TILE + cx.row, rows, cx.q, gn);
+          agg_produce(sh, cx, gn, pmx_n, cx.a_cur ^ 1, e_nx, mx_nx);
+        }
+      };
       if (!LAST) {
-        epi_store_rows(sh, cx, 1, meta[1], nullptr, a.Qr, r, valid);
-        epi_store_rows(sh, cx, 2, meta[2], nullptr, a.Qs, r, valid);
+        epi_store_rows(sh, cx, meta[1], nullptr, a.Qr, r, valid);
+        produce_next();
+        epi_store_rows(sh, cx, meta[2], nullptr, a.Qs, r, valid);
       } else {
-        epi_relu_to_a(sh, cx, 1, meta[1], sh.bias + 0 * FP);
+        epi_relu_to_a(sh, cx, meta[1], sh.bias + 0 * FP);
+        produce_next();
         // motion head (model.py:306-309): relu(linear_1) then the 3-row linear_2 as running dot products
         const float unscale = exp2i(-cx.e_in) * meta[2].x;
         float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-        epi_layer<true>(sh, cx, 0, unscale, sh.bias + 1 * FP, [](int, int, float (&)[QW]) {},
-                        [&](int, int col0, float (&v)[QW]) {
+        epi_layer<true>(sh, cx, unscale, sh.bias + 1 * FP, false, NoExtra{}, [&](int, int col0, float (&v)[QW]) {
 #pragma unroll
-                          for (int h = 0; h < 2; ++h) {
-                            const float4 w0 = lds128(sh.head_w + col0 + 4 * h), w1 = lds128(sh.head_w + FP + col0 + 4 * h),
-                                         w2 = lds128(sh.head_w + 2 * FP + col0 + 4 * h);
-                            m0 = fmaf(v[4 * h + 3], w0.w, fmaf(v[4 * h + 2], w0.z, fmaf(v[4 * h + 1], w0.y, fmaf(v[4 * h], w0.x, m0))));
-                            m1 = fmaf(v[4 * h + 3], w1.w, fmaf(v[4 * h + 2], w1.z, fmaf(v[4 * h + 1], w1.y, fmaf(v[4 * h], w1.x, m1))));
-                            m2 = fmaf(v[4 * h + 3], w2.w, fmaf(v[4 * h + 2], w2.z, fmaf(v[4 * h + 1], w2.y, fmaf(v[4 * h], w2.x, m2))));
-                          }
-                        });
+          for (int h = 0; h < 2; ++h) {
+            const float4 w0 = lds128(sh.head_w + col0 + 4 * h), w1 = lds128(sh.head_w + FP + col0 + 4 * h),
+                         w2 = lds128(sh.head_w + 2 * FP + col0 + 4 * h);
+            m0 = fmaf(v[4 * h + 3], w0.w, fmaf(v[4 * h + 2], w0.z, fmaf(v[4 * h + 1], w0.y, fmaf(v[4 * h], w0.x, m0))));
+            m1 = fmaf(v[4 * h + 3], w1.w, fmaf(v[4 * h + 2], w1.z, fmaf(v[4 * h + 1], w1.y, fmaf(v[4 * h], w1.x, m1))));
+            m2 = fmaf(v[4 * h + 3], w2.w, fmaf(v[4 * h + 2], w2.z, fmaf(v[4 * h + 1], w2.y, fmaf(v[4 * h], w2.x, m2))));
+          }
+        });
         m0 = epi_exchange<false>(sh, cx, m0);
         m1 = epi_exchange<false>(sh, cx, m1);
         m2 = epi_exchange<false>(sh, cx, m2);
@@ -418,6 +490,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
           }
         }
       }
+      cx.a_cur ^= 1;
     }
   }
   chain_teardown(tmem_base);
@@ -525,3 +598,12 @@ int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL
 }
 
 }  // namespace agx
+
+#ifdef AGX_TC_TIMELINE
+// Debug-only entry (tools/tc_timeline.py builds a separate library with -DAGX_TC_TIMELINE): points CTA 0's MMA thread at a
+// device buffer of 4096 int64 stamps (slot << 48 | clock64).
+extern "C" __attribute__((visibility("default"))) int agx_debug_set_timeline(void* dev_ptr) {
+  long long* p = static_cast<long long*>(dev_ptr);
+  return cudaMemcpyToSymbol(agx::tc::g_tc_timeline, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
+}
+#endif
