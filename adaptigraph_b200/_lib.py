@@ -37,7 +37,7 @@ EXPORTS = [
     "agx_rollout_workspace_bytes", "agx_rollout",
     "agx_profile_enable", "agx_profile_read", "agx_kind_name",
 ]
-AGX_NUM_KINDS = 11
+AGX_NUM_KINDS = 12
 
 
 class AgxModelDims(C.Structure):

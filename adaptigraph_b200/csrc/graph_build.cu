@@ -6,12 +6,16 @@
 // B x n_rel x N one-hots; here nothing quadratic ever reaches HBM:
 //
 //   G0 tool_list     (only with connect_tools_all) ascending list of tool particles per graph
-//   G1 knn_rows      one warp per receiver: stream all senders of the graph from shared memory,
-//                    keep the k nearest in-radius ones in a warp-resident sorted list (one entry
-//                    per lane), bitonic-sort them by sender id, store <= k candidates per row
+//   G0b sort_axis    per graph: pick the coordinate axis with the largest extent and sort the particles
+//                    along it (bitonic sort in shared memory); emits the permuted SoA copy of the graph
+//   G1 knn_rows      one warp per receiver: only senders whose sorted coordinate lies within the radius
+//                    of the receiver's can be in range, so the warp binary-searches that window and
+//                    streams it from shared memory (each CTA stages just the slot range its 64
+//                    receivers need); the k nearest in-radius senders live in a warp-resident sorted
+//                    list (one entry per lane), then are bitonic-sorted by sender id -> <= k candidates
 //   G2 degrees_scan  per-row relation count after the tool rules (:134-144 / :77-80) + block scan
 //   G2b scan_blocks  scan of the block sums -> row offsets, total
-//   G3 fill_rows     merge candidates and tool senders in ascending sender order into send/recv
+//   G3 fill_rows     one thread per receiver merges candidates and tool senders in ascending sender order
 //
 // Arithmetic follows the reference exactly: dis = (dx*dx + dy*dy) + dz*dz in fp32 without FMA
 // contraction (:109-110), radius test (dis - thr^2) < 0 (:125), pairs with an invalid endpoint or
@@ -36,6 +40,9 @@ struct GraphWs {
   int32_t* flags;      // [B]     probe: some tool receiver kept a non-tool sender (graph.py:135)
   int32_t* n_tools;    // [B]
   int32_t* tools;      // [B*N]
+  float* sx; float* sy; float* sz; float* skey;   // [B*N] particles permuted into sorted order (SoA)
+  int32_t* sidx;       // [B*N] original particle id of each sorted slot
+  uint8_t* sflag;      // [B*N] bit0 valid, bit1 tool
 };
 
 static size_t graph_ws_carve(void* base, int B, int N, int topk, GraphWs* ws) {
@@ -52,6 +59,9 @@ static size_t graph_ws_carve(void* base, int B, int N, int topk, GraphWs* ws) {
   w.flags = c.take<int32_t>(B);
   w.n_tools = c.take<int32_t>(B);
   w.tools = c.take<int32_t>(rows);
+  w.sx = c.take<float>(rows); w.sy = c.take<float>(rows); w.sz = c.take<float>(rows); w.skey = c.take<float>(rows);
+  w.sidx = c.take<int32_t>(rows);
+  w.sflag = c.take<uint8_t>(rows);
   if (ws) *ws = w;
   return align_up(c.off, 256);
 }
@@ -85,44 +95,145 @@ __global__ void __launch_bounds__(256) tool_list_kernel(const uint8_t* __restric
   if (tid == 0) n_tools[b] = base_s;
 }
 
-// ------------------------------------------------------------------------------------ G1
-__global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
-    const float* __restrict__ pos, int64_t pos_stride_b, const uint8_t* __restrict__ mask,
-    const uint8_t* __restrict__ tool_mask, const float* __restrict__ thr2, int N, int topk, int probe_tools,
-    int32_t* __restrict__ cand, int32_t* __restrict__ cnt_out, int32_t* __restrict__ flags) {
+// ------------------------------------------------------------------------------------ G0b
+// One CTA per graph.  Sort key = coordinate along the axis of largest extent, ties by particle id.
+__global__ void __launch_bounds__(1024) sort_axis_kernel(const float* __restrict__ pos, int64_t pos_stride_b,
+                                                          const uint8_t* __restrict__ mask, const uint8_t* __restrict__ tool_mask,
+                                                          int N, int NP2, float* __restrict__ sx, float* __restrict__ sy,
+                                                          float* __restrict__ sz, float* __restrict__ skey, int32_t* __restrict__ sidx,
+                                                          uint8_t* __restrict__ sflag) {
   extern __shared__ float smem[];
-  float* px = smem;
-  float* py = px + N;
-  float* pz = py + N;
-  uint8_t* fl = reinterpret_cast<uint8_t*>(pz + N);  // bit0 valid, bit1 tool
-
-  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* key = smem;
+  int32_t* val = reinterpret_cast<int32_t*>(smem + NP2);
+  __shared__ float red[6][32];
+  __shared__ int axis_s;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* p = pos + (size_t)b * pos_stride_b;
-  for (int j = tid; j < N; j += G1_THREADS) {
-    px[j] = p[3 * j + 0];
-    py[j] = p[3 * j + 1];
-    pz[j] = p[3 * j + 2];
-    fl[j] = (mask[(size_t)b * N + j] ? 1 : 0) | (tool_mask[(size_t)b * N + j] ? 2 : 0);
+  const float INF = __int_as_float(0x7f800000);
+  float mn[3] = {INF, INF, INF}, mx[3] = {-INF, -INF, -INF};
+  for (int j = tid; j < N; j += 1024) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float v = p[3 * j + a];
+      mn[a] = fminf(mn[a], v);
+      mx[a] = fmaxf(mx[a], v);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o));
+    }
+    if (lane == 0) { red[a][warp] = mn[a]; red[3 + a][warp] = mx[a]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float ext[3];
+    for (int a = 0; a < 3; ++a) {
+      float lo = INF, hi = -INF;
+      for (int w = 0; w < 32; ++w) { lo = fminf(lo, red[a][w]); hi = fmaxf(hi, red[3 + a][w]); }
+      ext[a] = hi - lo;
+    }
+    axis_s = (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[1] >= ext[2] ? 1 : 2);
+  }
+  __syncthreads();
+  const int axis = axis_s;
+  for (int j = tid; j < NP2; j += 1024) {
+    key[j] = j < N ? p[3 * j + axis] : INF;
+    val[j] = j;
+  }
+  __syncthreads();
+  for (int size = 2; size <= NP2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (NP2 >> 1); t += 1024) {
+        const int lo = 2 * t - (t & (stride - 1));   // index with the `stride` bit clear
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const float ka = key[lo], kb = key[hi];
+        const int va = val[lo], vb = val[hi];
+        const bool a_gt_b = (ka > kb) || (ka == kb && va > vb);
+        if (a_gt_b == up) { key[lo] = kb; key[hi] = ka; val[lo] = vb; val[hi] = va; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int s = tid; s < N; s += 1024) {
+    const int j = val[s];
+    const size_t o = (size_t)b * N + s;
+    sx[o] = p[3 * j + 0]; sy[o] = p[3 * j + 1]; sz[o] = p[3 * j + 2];
+    skey[o] = key[s];
+    sidx[o] = j;
+    sflag[o] = (mask[(size_t)b * N + j] ? 1 : 0) | (tool_mask[(size_t)b * N + j] ? 2 : 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------ G1
+// first slot in [lo, hi) whose key is >= x (lower_bound) / > x (upper_bound); `key` may be global or shared
+__device__ __forceinline__ int lower_bound_f(const float* key, int lo, int hi, float x) {
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (key[mid] < x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ int upper_bound_f(const float* key, int lo, int hi, float x) {
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (key[mid] <= x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+// conservative half-width of the window along the sort axis: every sender with (dis - thr^2) < 0 has
+// |x_i - x_j| <= sqrt(thr^2); the slack covers the fp32 rounding of the window bounds themselves
+__device__ __forceinline__ float window_halfwidth(float thr2, float x) { return sqrtf(fmaxf(thr2, 0.f)) * 1.001f + fabsf(x) * 2.4e-7f + 1e-30f; }
+
+__global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
+    const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sz, const float* __restrict__ skey,
+    const int32_t* __restrict__ sidx, const uint8_t* __restrict__ sflag, const float* __restrict__ thr2, int N, int topk,
+    int probe_tools, int smem_cap, int32_t* __restrict__ cand, int32_t* __restrict__ cnt_out, int32_t* __restrict__ flags) {
+  extern __shared__ float smem[];
+  __shared__ int range_s[2];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t gb = (size_t)b * N;
+  const float t2 = thr2[b];
+  const int s_beg = blockIdx.x * G1_ROWS_PER_CTA, s_end = min(N, s_beg + G1_ROWS_PER_CTA);
+  if (tid == 0) {   // slot range this CTA's receivers can reach
+    const float k0 = skey[gb + s_beg], k1 = skey[gb + s_end - 1];
+    range_s[0] = lower_bound_f(skey + gb, 0, s_beg, k0 - window_halfwidth(t2, k0));
+    range_s[1] = upper_bound_f(skey + gb, s_end, N, k1 + window_halfwidth(t2, k1));
+  }
+  __syncthreads();
+  const int r_lo = range_s[0], r_hi = range_s[1], M = r_hi - r_lo;
+  if (M > smem_cap) __trap();   // host sizes shared memory for the whole graph, so this cannot happen
+  float* px = smem;
+  float* py = px + M;
+  float* pz = py + M;
+  float* pk = pz + M;
+  int32_t* pj = reinterpret_cast<int32_t*>(pk + M);
+  uint8_t* fl = reinterpret_cast<uint8_t*>(pj + M);
+  for (int s = tid; s < M; s += G1_THREADS) {
+    const size_t o = gb + r_lo + s;
+    px[s] = sx[o]; py[s] = sy[o]; pz[s] = sz[o]; pk[s] = skey[o]; pj[s] = sidx[o]; fl[s] = sflag[o];
   }
   __syncthreads();
 
-  const float t2 = thr2[b];
-  const int row_end = min(N, (int)(blockIdx.x + 1) * G1_ROWS_PER_CTA);
-  for (int i = blockIdx.x * G1_ROWS_PER_CTA + warp; i < row_end; i += G1_THREADS / 32) {
-    const int fi = fl[i];
+  for (int slot = s_beg + warp; slot < s_end; slot += G1_THREADS / 32) {
+    const int li = slot - r_lo;
+    const int fi = fl[li];
+    const int i = pj[li];
     float ld = __int_as_float(0x7f800000);  // +inf
     int lj = 0x7fffffff;
     int total = 0;
     if (fi & 1) {
-      const float xi = px[i], yi = py[i], zi = pz[i];
+      const float xi = px[li], yi = py[li], zi = pz[li], ki = pk[li];
       const bool tool_i = fi & 2;
-      for (int j0 = 0; j0 < N; j0 += 32) {
-        const int j = j0 + lane;
+      const float w = window_halfwidth(t2, ki);
+      const int w_lo = lower_bound_f(pk, 0, li, ki - w), w_hi = upper_bound_f(pk, li + 1, M, ki + w);
+      for (int j0 = w_lo; j0 < w_hi; j0 += 32) {
+        const int s = j0 + lane;
         bool ok = false;
         float d = 0.f;
-        if (j < N) {
-          const int fj = fl[j];
-          const float dx = __fsub_rn(xi, px[j]), dy = __fsub_rn(yi, py[j]), dz = __fsub_rn(zi, pz[j]);
+        int jc_mine = 0;
+        if (s < w_hi) {
+          const int fj = fl[s];
+          jc_mine = (pj[s] << 1) | ((fj >> 1) & 1);   // sender id, tool bit in the LSB (order by id is preserved)
+          const float dx = __fsub_rn(xi, px[s]), dy = __fsub_rn(yi, py[s]), dz = __fsub_rn(zi, pz[s]);
           d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
           ok = (fj & 1) && !(tool_i && (fj & 2)) && (__fsub_rn(d, t2) < 0.f);
         }
@@ -131,9 +242,9 @@ __global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
           const int src = __ffs(m) - 1;
           m &= m - 1;
           const float dc = __shfl_sync(FULL, d, src);
-          const int jc = j0 + src;
+          const int jc = __shfl_sync(FULL, jc_mine, src);
           const bool less = (ld < dc) || (ld == dc && lj < jc);
-          const int at = __popc(__ballot_sync(FULL, less));  // list is sorted: `less` lanes form a prefix
+          const int at = __popc(__ballot_sync(FULL, less));  // list is sorted by (distance, sender id): `less` lanes form a prefix
           if (at < topk) {
             const float ud = __shfl_up_sync(FULL, ld, 1);
             const int uj = __shfl_up_sync(FULL, lj, 1);
@@ -157,10 +268,9 @@ __global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
         key = (lower == up) ? min(key, other) : max(key, other);
       }
     }
-    const bool nontool = (lane < cnt) && !(fl[key < N ? key : 0] & 2);
-    const int nt = __popc(__ballot_sync(FULL, nontool));
-    const size_t row = (size_t)b * N + i;
-    if (lane < topk) cand[row * topk + lane] = key;
+    const int nt = __popc(__ballot_sync(FULL, (lane < cnt) && !(key & 1)));   // non-tool candidates (needed for the degree)
+    const size_t row = gb + i;
+    if (lane < topk) cand[row * topk + lane] = key >> 1;
     if (lane == 0) {
       cnt_out[row] = cnt | (nt << 8);
       if (probe_tools && (fi & 2) && cnt > 0) atomicOr(&flags[b], 1);
@@ -255,6 +365,7 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(int32_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------ G3
+// One thread per receiver: a row has at most topk + n_tools relations, merged in ascending sender order.
 __global__ void __launch_bounds__(256) fill_rows_kernel(
     const int32_t* __restrict__ cand, const int32_t* __restrict__ cnt, const int32_t* __restrict__ lpre,
     const int32_t* __restrict__ blk, const int32_t* __restrict__ total, const uint8_t* __restrict__ mask,
@@ -262,18 +373,15 @@ __global__ void __launch_bounds__(256) fill_rows_kernel(
     const int32_t* __restrict__ tools, int rows, int N, int topk, int cta, int sem, int32_t* __restrict__ row_ptr,
     int32_t* __restrict__ send, int32_t* __restrict__ recv, int64_t cap, int32_t* __restrict__ n_edges,
     int32_t* __restrict__ status) {
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int r = blockIdx.x * 256 + threadIdx.x;
   if (r >= rows) return;
   const int b = r / N, n = r - b * N;
   const int start = lpre[r] + blk[r / SCAN_BLOCK];
-  if (lane == 0) {
-    row_ptr[r] = start;
-    if (n == 0) {
-      const int r2 = r + N;
-      const int end = (r2 < rows) ? lpre[r2] + blk[r2 / SCAN_BLOCK] : *total;
-      n_edges[b] = end - start;
-    }
+  row_ptr[r] = start;
+  if (n == 0) {
+    const int r2 = r + N;
+    const int end = (r2 < rows) ? lpre[r2] + blk[r2 / SCAN_BLOCK] : *total;
+    n_edges[b] = end - start;
   }
   const int packed = cnt[r];
   const int c = packed & 0xff;
@@ -282,39 +390,27 @@ __global__ void __launch_bounds__(256) fill_rows_kernel(
   bool keep_base, add_tools;
   const int deg = row_degree(packed, valid, tool_i, cta, sem, cta ? flags[b] : 0, ntl, &keep_base, &add_tools);
   if (deg == 0) return;
+  const int32_t* cd = cand + (size_t)r * topk;
+  const int32_t* tl = tools + (size_t)b * N;
+  const uint8_t* tm = tool_mask + (size_t)b * N;
+  int64_t o = start;
   bool overflow = false;
-  const int key = (lane < c) ? cand[(size_t)r * topk + lane] : 0x7fffffff;
-  if (!cta) {
-    if (lane < c) {
-      const int64_t o = (int64_t)start + lane;
-      if (o < cap) { send[o] = key; recv[o] = r; } else overflow = true;
+  int ci = 0, ti = 0;
+  const int nt_add = add_tools ? ntl : 0;
+  // two-way merge of the (sorted) kept candidates and the (sorted) tool list; the sets are disjoint under cta
+  while (true) {
+    int cj = 0x7fffffff;
+    while (ci < c) {   // next kept candidate
+      const int j = cd[ci];
+      if (!cta || (keep_base && !tm[j])) { cj = j; break; }
+      ++ci;
     }
-  } else {
-    const int32_t* tl = tools + (size_t)b * N;
-    const bool keep = (lane < c) && keep_base && !tool_mask[(size_t)b * N + key];
-    const unsigned km = __ballot_sync(FULL, keep);
-    if (keep) {
-      int o = __popc(km & ((1u << lane) - 1));
-      if (add_tools)
-        for (int t = 0; t < ntl; ++t) o += (tl[t] < key);
-      const int64_t oo = (int64_t)start + o;
-      if (oo < cap) { send[oo] = key; recv[oo] = r; } else overflow = true;
-    }
-    if (add_tools) {
-      for (int t0 = 0; t0 < ntl; t0 += 32) {
-        const int t = t0 + lane;
-        const int tj = (t < ntl) ? tl[t] : 0x7fffffff;
-        int below = 0;
-        for (int mth = 0; mth < 32; ++mth) {
-          const int am = __shfl_sync(FULL, key, mth);
-          below += (((km >> mth) & 1u) && am < tj);
-        }
-        if (t < ntl) {
-          const int64_t oo = (int64_t)start + t + below;
-          if (oo < cap) { send[oo] = tj; recv[oo] = r; } else overflow = true;
-        }
-      }
-    }
+    const int tj = ti < nt_add ? tl[ti] : 0x7fffffff;
+    if (cj == 0x7fffffff && tj == 0x7fffffff) break;
+    int j;
+    if (cj < tj) { j = cj; ++ci; } else { j = tj; ++ti; }
+    if (o < cap) { send[o] = j; recv[o] = r; } else overflow = true;
+    ++o;
   }
   if (overflow) atomicOr(status, 1);
 }
@@ -365,12 +461,19 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
   const size_t need = graph_ws_carve(workspace, B, N, topk, &ws);
   AGX_REQUIRE(workspace && workspace_bytes >= need, AGX_ERR_CAPACITY, "graph_build: workspace %zu < %zu bytes",
               workspace_bytes, need);
-  const size_t smem = (size_t)N * 13 + 16;
-  AGX_REQUIRE(smem <= 227 * 1024, AGX_ERR_ARG, "graph_build: N=%d exceeds the shared-memory staging limit", N);
-  static thread_local size_t smem_set = 0;
+  int NP2 = 1;
+  while (NP2 < N) NP2 <<= 1;
+  const size_t sort_smem = (size_t)NP2 * 8;
+  const size_t smem = (size_t)N * 21 + 32;   // worst case: a CTA's window spans the whole graph
+  AGX_REQUIRE(smem <= 227 * 1024 && sort_smem <= 227 * 1024, AGX_ERR_ARG, "graph_build: N=%d exceeds the shared-memory staging limit", N);
+  static thread_local size_t smem_set = 0, sort_smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     AGX_CUDA_OK(cudaFuncSetAttribute(knn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
+  }
+  if (sort_smem > 48 * 1024 && sort_smem > sort_smem_set) {
+    AGX_CUDA_OK(cudaFuncSetAttribute(sort_axis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    sort_smem_set = sort_smem;
   }
   const int rows = B * N;
   const int nblk = (rows + SCAN_BLOCK - 1) / SCAN_BLOCK;
@@ -379,10 +482,13 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
       tool_list_kernel<<<B, 256, 0, st>>>(tool_mask, N, ws.tools, ws.n_tools, ws.flags); }
     AGX_LAUNCH_CHECK();
   }
+  { ProfScope ps(AGX_KIND_GRAPH_SORT, st);
+    sort_axis_kernel<<<B, 1024, sort_smem, st>>>(pos, pos_stride_b, mask, tool_mask, N, NP2, ws.sx, ws.sy, ws.sz, ws.skey, ws.sidx, ws.sflag); }
+  AGX_LAUNCH_CHECK();
   dim3 g1((N + G1_ROWS_PER_CTA - 1) / G1_ROWS_PER_CTA, B);
   { ProfScope ps(AGX_KIND_GRAPH_KNN, st);
-    knn_rows_kernel<<<g1, G1_THREADS, smem, st>>>(pos, pos_stride_b, mask, tool_mask, thr2, N, topk,
-                                                   cta && sem == AGX_SEM_BATCH, ws.cand, ws.cnt, ws.flags); }
+    knn_rows_kernel<<<g1, G1_THREADS, smem, st>>>(ws.sx, ws.sy, ws.sz, ws.skey, ws.sidx, ws.sflag, thr2, N, topk,
+                                                   cta && sem == AGX_SEM_BATCH, N, ws.cand, ws.cnt, ws.flags); }
   AGX_LAUNCH_CHECK();
   { ProfScope ps(AGX_KIND_GRAPH_SCAN, st);
     degrees_scan_kernel<<<nblk, SCAN_BLOCK, 0, st>>>(ws.cnt, mask, tool_mask, ws.flags, ws.n_tools, rows, N, cta, sem,
@@ -392,7 +498,7 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
     scan_blocks_kernel<<<1, 1024, 0, st>>>(ws.blk, nblk, ws.total, row_ptr + rows); }
   AGX_LAUNCH_CHECK();
   { ProfScope ps(AGX_KIND_GRAPH_FILL, st);
-    fill_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ws.cand, ws.cnt, ws.lpre, ws.blk, ws.total, mask, tool_mask, ws.flags,
+    fill_rows_kernel<<<(rows + 255) / 256, 256, 0, st>>>(ws.cand, ws.cnt, ws.lpre, ws.blk, ws.total, mask, tool_mask, ws.flags,
                                                       ws.n_tools, ws.tools, rows, N, topk, cta, sem, row_ptr, send, recv,
                                                       cap, n_edges, status); }
   AGX_LAUNCH_CHECK();

@@ -173,7 +173,7 @@ AGX_API int agx_rollout(const AgxModelDims* dims, const void* packed_weights, co
 enum {
   AGX_KIND_GRAPH_TOOLS = 0, AGX_KIND_GRAPH_KNN, AGX_KIND_GRAPH_SCAN, AGX_KIND_GRAPH_FILL,
   AGX_KIND_NODE_ENCODER, AGX_KIND_EDGE_ENCODER, AGX_KIND_EDGE_AGGREGATE, AGX_KIND_NODE_UPDATE,
-  AGX_KIND_NODE_HEAD, AGX_KIND_ROLLOUT_ADVANCE, AGX_KIND_OTHER, AGX_NUM_KINDS
+  AGX_KIND_NODE_HEAD, AGX_KIND_ROLLOUT_ADVANCE, AGX_KIND_OTHER, AGX_KIND_GRAPH_SORT, AGX_NUM_KINDS
 };
 AGX_API int agx_profile_enable(int32_t on);
 AGX_API int agx_profile_read(double* ms, int64_t* count);

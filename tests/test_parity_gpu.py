@@ -223,3 +223,22 @@ def test_tensor_core_path_agrees_with_fp32_path_at_scale(agx):
         b_pos, b_mot = _model(agx, "cloth", 3, "tc")(**w.graph_dict(), edges=el)
     assert (a_mot - b_mot).abs().max().item() <= FWD_TOL
     assert (a_pos - b_pos).abs().max().item() <= FWD_TOL
+
+
+@pytest.mark.parametrize("material,n_p,B", [("cloth", 2000, 4), ("granular", 1000, 4), ("rope", 300, 8), ("granular", 4099, 1)])
+def test_graph_build_matches_c_oracle_at_baseline_sizes(agx, material, n_p, B):
+    """BASELINE-sized graphs (and one above 4096 particles) against the plain-C restatement of graph.py:91-156:
+    identical relation lists, including after a perturbation that moves the tools away (batch_mask False)."""
+    from adaptigraph_b200 import synthetic as syn
+    from oracle import build_oracle
+    w = syn.make_workload(material, n_p, B, seed=4321, n_pad=3)
+    pos = w.state[:, -1].clone()
+    if B > 1:
+        pos[1, w.n_p:] += 40.0
+    thr2 = np.float32(w.adj_thresh) * np.float32(w.adj_thresh)
+    recv, send, n_edges = build_oracle.edges(pos.numpy(), w.state_mask.numpy(), w.eef_mask.numpy(), thr2, w.topk, w.connect_tools_all, 0)
+    el = agx.build_edges(pos.cuda(), w.adj_thresh, w.state_mask.cuda(), w.eef_mask.cuda(), w.topk, w.connect_tools_all).check()
+    E = int(el.row_ptr[-1])
+    assert E == recv.shape[0] and np.array_equal(el.n_edges.cpu().numpy(), n_edges)
+    assert np.array_equal(el.send[:E].cpu().numpy(), send)
+    assert np.array_equal((el.recv[:E].cpu().numpy() % w.N), recv)
