@@ -32,7 +32,9 @@ constexpr float MOTION_CLAMP = 100.f;  // model.py:85
 // tensor-core path (tc_forward.cu)
 struct TcFwdBuffers {
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
+  int32_t* agg_exp; float* agg_max;
 };
+int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st);
 size_t tc_blob_bytes(size_t base_bytes);
 int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_t base_bytes, cudaStream_t st);
 int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, cudaStream_t st);
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(256) rollout_advance_kernel(float* __restrict_
 // ------------------------------------------------------------------------------------ host drivers
 struct FwdWs {
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
+  int32_t* agg_exp; float* agg_max;
 };
 static size_t fwd_ws_carve(void* base, int64_t rows, int64_t E_cap, FwdWs* out) {
   Carver c(base);
@@ -420,6 +423,8 @@ static size_t fwd_ws_carve(void* base, int64_t rows, int64_t E_cap, FwdWs* out) 
   w.C = c.take<float>((size_t)(E_cap > 0 ? E_cap : 1) * FP);
   w.rowmaxP = c.take<float>((size_t)rows);
   w.rowmaxA = c.take<float>((size_t)rows);
+  w.agg_exp = c.take<int32_t>((size_t)rows);
+  w.agg_max = c.take<float>((size_t)rows);
   if (out) *out = w;
   return align_up(c.off, 256);
 }
@@ -458,16 +463,12 @@ static int forward_impl(const AgxModelDims* dims, const float* wts, const AgxGra
   if (precision == AGX_PREC_TC_F16X3) {
     // same stages, dense layers on the tcgen05 tensor cores (tc_forward.cu)
     const size_t base = L.total * sizeof(float);
-    const TcFwdBuffers tb{ws.nfeat, ws.P, ws.A, ws.Qr, ws.Qs, ws.agg, ws.C, ws.rowmaxP, ws.rowmaxA};
+    const TcFwdBuffers tb{ws.nfeat, ws.P, ws.A, ws.Qr, ws.Qs, ws.agg, ws.C, ws.rowmaxP, ws.rowmaxA, ws.agg_exp, ws.agg_max};
     if (int rc = tc_node_encoder(g, wts, L, base, tb, st)) return rc;
     if (g->E_cap > 0)
       if (int rc = tc_edge_encoder(g, wts, L, base, tb, st)) return rc;
     for (int k = 0; k < dims->pstep; ++k) {
-      { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
-        edge_aggregate_kernel<<<(unsigned)((rows + AGG_NODES - 1) / AGG_NODES), AGG_THREADS, 0, st>>>(
-            g->row_ptr, g->send, rows, g->N, g->E_cap, reinterpret_cast<const float4*>(ws.C),
-            reinterpret_cast<const float4*>(ws.Qr), reinterpret_cast<const float4*>(ws.Qs), reinterpret_cast<float4*>(ws.agg)); }
-      AGX_LAUNCH_CHECK();
+      if (int rc = tc_edge_aggregate(g, tb, st)) return rc;
       if (int rc = tc_node_update(g, wts, L, base, tb, k + 1 == dims->pstep, pred_pos, pos_stride_b, pred_motion, st)) return rc;
     }
     return AGX_OK;

@@ -1,30 +1,27 @@
 // Tensor-core MLP chains (AGX_PREC_TC_F16X3): tcgen05.mma kind::f16 with fp32-accurate split operands.
 //
-// One CTA owns a tile of 128 rows (relations or particles) and pushes it through a chain of dense
-// layers without the activations ever leaving the SM:
+// One CTA keeps TWO tiles of 128 rows (relations or particles) in flight ("slots") and pushes each
+// through a chain of dense layers without the activations ever leaving the SM.  The slots are
+// independent pipelines that share the tensor pipe and the weights in shared memory, so one slot's
+// epilogue (tensor-memory round trip, fp32 math, re-split) is hidden behind the other slot's MMAs.
 //
-//   * the accumulator (160 fp32 columns) and the layer input A live in tensor memory (TS-mode MMA);
-//     every fp32 activation a is scaled by an exact per-row power of two and split into two fp16
-//     values a' = hi + lo (22 significant bits), stored as packed half2 columns (80 hi + 80 lo);
-//     A is double buffered: a layer's epilogue writes the next layer's input into the other buffer;
-//   * the weights are pre-packed (agx_pack_weights) as scaled fp16 hi/lo images in the canonical
-//     K-major core-matrix layout and brought into shared memory by the TMA engine as one bulk copy
-//     per layer, double buffered so the next layer's weights land while the current layer runs;
-//   * a layer is 3 MMAs per 16-wide K step:  D += Alo*Whi + Ahi*Wlo + Ahi*Whi  (the dropped lo*lo
-//     term is 2^-22 relative), issued by one thread; fp32 accumulation in tensor memory.  Each
-//     layer is issued as two column parts (N = 96, then N = 64): the epilogue of part A overlaps the
-//     MMAs of part B, and the next layer's part A starts on the K chunks part A's epilogue produced
-//     while part B's epilogue is still running, so the tensor pipe does not drain between layers;
-//   * 16 epilogue warps (thread = row; the four warps of a 32-lane quarter split every 32-column
-//     chunk into 8-column pieces) read an accumulator part with tcgen05.ld (one wait, part released
-//     to the MMA warp immediately), undo the power-of-two scales exactly, apply bias / residual /
-//     ReLU, and either re-split the result into the next layer's A (tcgen05.st) chunk by chunk or
-//     store fp32 rows to HBM with 256-bit stores;
-//   * the input of the NEXT tile is fetched early and written into the free A buffer before the
-//     current tile's last epilogue, so the first layer of the next tile overlaps that epilogue.
+//   * per slot, tensor memory holds the layer input A (160 K-elements as packed fp16: 80 hi + 80 lo
+//     columns) and a 96-column fp32 accumulator: 256 columns per slot, 512 in total;
+//   * every fp32 activation a is scaled by an exact per-row power of two and split a' = hi + lo
+//     (22 significant bits); the weights are pre-packed (agx_pack_weights) as scaled fp16 hi/lo
+//     images in the canonical K-major core-matrix layout and brought into shared memory by the TMA
+//     engine as one bulk copy per layer, double buffered, shared by both slots;
+//   * a layer is issued as two column parts (N = 96, then N = 64, same accumulator columns), each
+//     3 MMAs per 16-wide K step:  D += Alo*Whi + Ahi*Wlo + Ahi*Whi  (dropped lo*lo term: 2^-22);
+//   * 8 epilogue warps per slot (thread = row = tensor-memory lane; the two warps of a 32-lane
+//     quarter split every 32-column chunk into 16-column halves) read an accumulator part with
+//     tcgen05.ld, undo the power-of-two scales exactly, apply bias / residual / ReLU and either
+//     re-split the result into the slot's next A (written once the layer's last MMA has completed:
+//     part A's results wait in registers as packed fp16) or store fp32 rows to HBM (256-bit stores).
 //
-// Warp roles: warps 0-15 epilogue + input producers, warp 16 MMA issuer (+ TMEM allocation),
-// warp 17 weight loader.  All waits are bounded (tc_ptx.cuh: a protocol bug traps, it cannot hang).
+// Warp roles: warps 0-7 / 8-15 epilogue + input producers of slot 0 / 1, warps 16 / 17 MMA issuers of
+// slot 0 / 1 (warp 16 also owns the TMEM allocation), warp 18 weight loader, warp 19 idle.
+// All waits are bounded (tc_ptx.cuh: a protocol bug traps, it cannot hang).
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -33,25 +30,23 @@ namespace agx {
 namespace tc {
 
 constexpr int TILE = 128;
-constexpr int NQ = 4;                                   // column quarters per chunk (warps per lane quarter)
-constexpr int QW = 8;                                   // columns per thread per chunk
-constexpr int EPI_WARPS = 4 * NQ;
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int MMA_WARP = EPI_WARPS;
-constexpr int LOAD_WARP = EPI_WARPS + 1;
-constexpr int THREADS = EPI_THREADS + 64;
+constexpr int NSLOT = 2;
+constexpr int HW = 16;                                  // columns per thread per 32-column chunk (two halves)
+constexpr int SLOT_WARPS = 8;
+constexpr int SLOT_THREADS = SLOT_WARPS * 32;
+constexpr int EPI_WARPS = NSLOT * SLOT_WARPS;
+constexpr int MMA_WARP0 = EPI_WARPS;                    // warps 16, 17
+constexpr int LOAD_WARP = EPI_WARPS + 2;                // warp 18
+constexpr int THREADS = (EPI_WARPS + 4) * 32;           // 20 warps
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_ACC = 0;
-constexpr uint32_t COL_AHI0 = 160, COL_ALO0 = 240, COL_AHI1 = 320, COL_ALO1 = 400;
+constexpr uint32_t SLOT_COLS = 256;
+constexpr uint32_t COL_ACC = 0, COL_AHI = 96, COL_ALO = 176;   // within a slot
 constexpr int NCHUNK = 5;                               // 32-wide K chunks of a 160-wide layer
 constexpr int NCHUNK_A = 3;                             // accumulator part A = chunks 0..2 (N = 96), part B = chunks 3..4 (N = 64)
 constexpr int N_PART_A = 32 * NCHUNK_A, N_PART_B = FP - N_PART_A;
 constexpr uint32_t IMG_BIG = FP * FP * 2;               // bytes of one fp16 image (hi or lo) of a 160x160 layer
 constexpr uint32_t IDESC_A = make_idesc_f16(TILE, N_PART_A), IDESC_B = make_idesc_f16(TILE, N_PART_B);
 constexpr int TARGET_EXP = 14;                          // scaled operands satisfy |x| <= 2^14 (fp16 max is 65504)
-
-__device__ __forceinline__ uint32_t col_ahi(int buf) { return buf ? COL_AHI1 : COL_AHI0; }
-__device__ __forceinline__ uint32_t col_alo(int buf) { return buf ? COL_ALO1 : COL_ALO0; }
 
 // tensor-core layer ids (order of the fp16 images in the packed blob)
 enum TcLayer {
@@ -92,12 +87,12 @@ __device__ __forceinline__ int scale_exp(float bound) {
 }
 __device__ __forceinline__ float exp2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
 
-// scale 8 fp32 values and split them into packed fp16 hi / lo columns (hi = round-to-nearest, lo = residual);
+// scale 16 fp32 values and split them into packed fp16 hi / lo columns (hi = round-to-nearest, lo = residual);
 // fp32 arithmetic on register pairs (FMUL2 / FADD2)
-__device__ __forceinline__ void split8(const float (&v)[QW], float scale, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+__device__ __forceinline__ void split16(const float (&v)[HW], float scale, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
   const float2 sc2 = make_float2(scale, scale);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     const float2 s = __fmul2_rn(make_float2(v[2 * i], v[2 * i + 1]), sc2);
     const __half2 h = __float22half2_rn(s);
     const float2 hf = __half22float2(h);
@@ -109,23 +104,23 @@ __device__ __forceinline__ void split8(const float (&v)[QW], float scale, uint32
 
 // ------------------------------------------------------------------------------------------------
 struct Shared {
-  uint8_t* wbig[2];      // two 2*IMG_BIG weight buffers (hi image then lo image)
+  uint8_t* wbig[2];      // two 2*IMG_BIG weight buffers (hi image then lo image), shared by both slots
   uint8_t* wsmall;       // first-layer weights (K = 16 or 32)
   float* bias;           // [MAX_BIAS][FP]
-  float* xchg;           // [NQ][TILE] row exchange between the column quarters
+  float* xchg;           // [NSLOT][2][TILE] row exchange between the two column halves of a slot
   float* head_w;         // [3][FP] + [4] (head program only)
   uint64_t* bar_wsmall;
   uint64_t* bar_wfull;   // [2]
-  uint64_t* bar_wempty;  // [2]
-  uint64_t* bar_a;       // [2]  A chunks 0..2 / 3..4 written by a layer epilogue
-  uint64_t* bar_in;      // [2]  A chunks 0..2 / 3..4 written by the tile's input producer
-  uint64_t* bar_accfull; // [2]       accumulator part A / B complete
-  uint64_t* bar_accempty;// [2]       accumulator part A / B read by all epilogue warps
+  uint64_t* bar_wempty;  // [2]      count NSLOT: one arrival per slot per use
+  uint64_t* bar_in;      // [NSLOT]  slot's A written by the tile's input producer
+  uint64_t* bar_a;       // [NSLOT]  slot's A written by a layer epilogue
+  uint64_t* bar_accfull; // [NSLOT]  accumulator part complete (parts alternate on the same barrier)
+  uint64_t* bar_accempty;// [NSLOT]  accumulator part read by all epilogue warps of the slot
   uint32_t* tmem_ptr;
 };
 constexpr int MAX_BIAS = 4;
-constexpr size_t SMEM_BYTES = 2 * (2 * (size_t)IMG_BIG) + 2 * (size_t)FP * 32 * 2 + MAX_BIAS * FP * 4 + NQ * TILE * 4 + (3 * FP + 4) * 4 +
-                              24 * 8 + 16 + 128 /* alignment slack */;
+constexpr size_t SMEM_BYTES = 2 * (2 * (size_t)IMG_BIG) + 2 * (size_t)FP * 32 * 2 + MAX_BIAS * FP * 4 + NSLOT * 2 * TILE * 4 +
+                              (3 * FP + 4) * 4 + 16 * 8 + 16 + 128 /* alignment slack */;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit of a CTA");
 
 __device__ __forceinline__ Shared carve_shared(uint8_t* raw) {
@@ -135,29 +130,43 @@ __device__ __forceinline__ Shared carve_shared(uint8_t* raw) {
   s.wbig[1] = p; p += 2 * IMG_BIG;
   s.wsmall = p; p += 2 * FP * 32 * 2;
   s.bias = reinterpret_cast<float*>(p); p += MAX_BIAS * FP * 4;
-  s.xchg = reinterpret_cast<float*>(p); p += NQ * TILE * 4;
+  s.xchg = reinterpret_cast<float*>(p); p += NSLOT * 2 * TILE * 4;
   s.head_w = reinterpret_cast<float*>(p); p += (3 * FP + 4) * 4;
   uint64_t* b = reinterpret_cast<uint64_t*>(p);
-  s.bar_wsmall = b; s.bar_wfull = b + 1; s.bar_wempty = b + 3; s.bar_a = b + 5; s.bar_in = b + 10; s.bar_accfull = b + 15;
-  s.bar_accempty = b + 17;
-  s.tmem_ptr = reinterpret_cast<uint32_t*>(b + 20);
+  s.bar_wsmall = b; s.bar_wfull = b + 1; s.bar_wempty = b + 3; s.bar_in = b + 5; s.bar_a = b + 7; s.bar_accfull = b + 9;
+  s.bar_accempty = b + 11;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(b + 13);
   return s;
 }
 
 // Program description (compile time).  in_src: where the layer's A comes from —
-//   IN_PRODUCER  written by the tile's input producer      (wait bar_in[c])
-//   IN_EPILOGUE  written by the previous layer's epilogue  (wait bar_a[c], A buffer toggles)
+//   IN_PRODUCER  written by the tile's input producer      (wait bar_in)
+//   IN_EPILOGUE  written by the previous layer's epilogue  (wait bar_a)
 //   IN_SAME      the previous layer's A is reused          (no wait)
 enum { IN_PRODUCER = 0, IN_EPILOGUE = 1, IN_SAME = 2 };
 struct LayerStep { int layer; int ksteps; int in_src; };
 
+// tiles of this CTA: t(k) = blockIdx.x + k * gridDim.x; slot s owns k = s, s + 2, ...; a "round" is one tile per slot
+__device__ __forceinline__ int cta_tile_count(int n_tiles) {
+  return (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+}
+
+// Optional timeline capture (tools/tc_timeline.py builds with -DAGX_TC_TIMELINE): CTA 0's slot-0 MMA thread records stamps.
+#ifdef AGX_TC_TIMELINE
+__device__ long long* g_tc_timeline = nullptr;
+#define AGX_STAMP(slot_id) do { if (g_tc_timeline && blockIdx.x == 0 && slot == 0 && stamp_i < 1024) g_tc_timeline[(NL == 4 ? 0 : NL == 6 ? 1024 : 2048) + stamp_i++] = ((long long)(slot_id) << 48) | (clock64() & 0xffffffffffffll); } while (0)
+#else
+#define AGX_STAMP(slot_id) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------ roles
-// Weight loader: one thread streams the big layers of every tile through the two-buffer ring.
+// Weight loader: one thread streams the big layers of every round through the two-buffer ring.
 template <int NL>
 __device__ __forceinline__ void loader_role(const Shared& sh, const LayerStep (&prog)[NL], const uint8_t* blob, const TcLayout& L,
                                             int n_tiles) {
   if (!elect_one()) return;
-  if ((int)blockIdx.x >= n_tiles) return;
+  const int my_tiles = cta_tile_count(n_tiles);
+  if (my_tiles == 0) return;
   {
     const int t = prog[0].layer;
     if (prog[0].ksteps < 10) {
@@ -167,7 +176,8 @@ __device__ __forceinline__ void loader_role(const Shared& sh, const LayerStep (&
     }
   }
   uint32_t buf = 0, empty_parity = 0x3;   // bit b = parity to wait for on bar_wempty[b] (starts at 1: free)
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int rounds = (my_tiles + NSLOT - 1) / NSLOT;
+  for (int round = 0; round < rounds; ++round) {
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       if (prog[l].ksteps < 10) continue;
@@ -180,29 +190,24 @@ __device__ __forceinline__ void loader_role(const Shared& sh, const LayerStep (&
   }
 }
 
-// MMA issuer: one thread; per layer two column parts, each 3 MMAs per K step.
-// Optional timeline capture (debug builds of the bench tool only): CTA 0's MMA thread records clock64 stamps.
-#ifdef AGX_TC_TIMELINE
-__device__ long long* g_tc_timeline = nullptr;
-#define AGX_STAMP(slot) do { if (g_tc_timeline && blockIdx.x == 0 && stamp_i < 1024) g_tc_timeline[(NL == 4 ? 0 : NL == 6 ? 1024 : 2048) + stamp_i++] = ((long long)(slot) << 48) | (clock64() & 0xffffffffffffll); } while (0)
-#else
-#define AGX_STAMP(slot) do { } while (0)
-#endif
-
+// MMA issuer of one slot: one thread; per layer two column parts, each 3 MMAs per K step.
 template <int NL>
-__device__ __forceinline__ void mma_role(const Shared& sh, const LayerStep (&prog)[NL], uint32_t tmem_base, int n_tiles) {
+__device__ __forceinline__ void mma_role(const Shared& sh, const LayerStep (&prog)[NL], int slot, uint32_t tmem_base, int n_tiles) {
   if (!elect_one()) return;
   int stamp_i = 0; (void)stamp_i;
-  uint32_t buf = 0, full_parity = 0, accempty_parity = 0x3, a_parity = 0, in_parity = 0;
-  int a_cur = 0;   // A buffer the current layer reads
+  const int my_tiles = cta_tile_count(n_tiles);
+  const int rounds = (my_tiles + NSLOT - 1) / NSLOT;
+  const uint32_t tslot = tmem_base + slot * SLOT_COLS;
+  const uint32_t d_tmem = tslot + COL_ACC, a_hi0 = tslot + COL_AHI, a_lo0 = tslot + COL_ALO;
+  uint32_t buf = 0, full_parity = 0, accempty_parity = 1, a_parity = 0, in_parity = 0;
   bool small_ready = false;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int round = 0; round < rounds; ++round) {
+    const bool active = round * NSLOT + slot < my_tiles;
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       const int ksteps = prog[l].ksteps;
       const bool big = ksteps == 10;
       const int kpad = ksteps * 16;
-      if (prog[l].in_src == IN_EPILOGUE) a_cur ^= 1;
       uint32_t w_addr;
       AGX_STAMP(1);
       if (big) {
@@ -214,51 +219,52 @@ __device__ __forceinline__ void mma_role(const Shared& sh, const LayerStep (&pro
         w_addr = smem_u32(sh.wsmall);
       }
       AGX_STAMP(2);
-      const uint32_t img_bytes = (uint32_t)FP * kpad * 2;
-      const uint32_t sbo = (uint32_t)(kpad >> 3) * 128;
-      const uint32_t a_hi0 = tmem_base + col_ahi(a_cur), a_lo0 = tmem_base + col_alo(a_cur);
+      if (active) {
+        const uint32_t img_bytes = (uint32_t)FP * kpad * 2;
+        const uint32_t sbo = (uint32_t)(kpad >> 3) * 128;
 #pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        mbar_wait(&sh.bar_accempty[part], (accempty_parity >> part) & 1);
-        accempty_parity ^= 1u << part;
-        AGX_STAMP(3 + part * 3);
-        const uint32_t d_tmem = tmem_base + COL_ACC + (part ? N_PART_A : 0);
-        const uint32_t row_off = part ? (uint32_t)(N_PART_A / 8) * sbo : 0u;
-        const uint32_t idesc = part ? IDESC_B : IDESC_A;
-        // descriptors advance by 256 B (= 16 in the encoded start address) per K step
-        uint64_t b_hi = make_b_desc(w_addr + row_off, 128, sbo);
-        uint64_t b_lo = make_b_desc(w_addr + img_bytes + row_off, 128, sbo);
-        for (int ks = 0; ks < ksteps; ++ks) {
-          if (part == 0 && (ks == 0 || ks == 2 * NCHUNK_A)) {
-            const int h = ks ? 1 : 0;
-            if (prog[l].in_src == IN_EPILOGUE) { mbar_wait(&sh.bar_a[h], (a_parity >> h) & 1); a_parity ^= 1u << h; }
-            if (prog[l].in_src == IN_PRODUCER) { mbar_wait(&sh.bar_in[h], (in_parity >> h) & 1); in_parity ^= 1u << h; }
-            tc_fence_after();
-            AGX_STAMP(ks == 0 ? 4 : 5);
+        for (int part = 0; part < 2; ++part) {
+          mbar_wait(&sh.bar_accempty[slot], accempty_parity);
+          accempty_parity ^= 1;
+          AGX_STAMP(3 + part * 3);
+          if (part == 0) {
+            if (prog[l].in_src == IN_EPILOGUE) { mbar_wait(&sh.bar_a[slot], a_parity); a_parity ^= 1; }
+            if (prog[l].in_src == IN_PRODUCER) { mbar_wait(&sh.bar_in[slot], in_parity); in_parity ^= 1; }
+            AGX_STAMP(4);
           }
-          mma_f16_ts(d_tmem, a_lo0 + 8 * ks, b_hi, idesc, ks > 0);   // small terms first
-          mma_f16_ts(d_tmem, a_hi0 + 8 * ks, b_lo, idesc, 1);
-          mma_f16_ts(d_tmem, a_hi0 + 8 * ks, b_hi, idesc, 1);
-          b_hi += 16;
-          b_lo += 16;
+          tc_fence_after();
+          const uint32_t row_off = part ? (uint32_t)(N_PART_A / 8) * sbo : 0u;
+          const uint32_t idesc = part ? IDESC_B : IDESC_A;
+          // descriptors advance by 256 B (= 16 in the encoded start address) per K step
+          uint64_t b_hi = make_b_desc(w_addr + row_off, 128, sbo);
+          uint64_t b_lo = make_b_desc(w_addr + img_bytes + row_off, 128, sbo);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            mma_f16_ts(d_tmem, a_lo0 + 8 * ks, b_hi, idesc, ks > 0);   // small terms first
+            mma_f16_ts(d_tmem, a_hi0 + 8 * ks, b_lo, idesc, 1);
+            mma_f16_ts(d_tmem, a_hi0 + 8 * ks, b_hi, idesc, 1);
+            b_hi += 16;
+            b_lo += 16;
+          }
+          mma_commit(&sh.bar_accfull[slot]);
+          AGX_STAMP(part ? 8 : 7);
         }
-        mma_commit(&sh.bar_accfull[part]);
-        AGX_STAMP(part ? 8 : 7);
+        if (big) mma_commit(&sh.bar_wempty[buf]);
+      } else if (big) {
+        mbar_arrive(&sh.bar_wempty[buf]);   // keep the weight ring in lock step when this slot has no tile in the round
       }
-      if (big) { mma_commit(&sh.bar_wempty[buf]); buf ^= 1; }
+      if (big) buf ^= 1;
     }
-    a_cur ^= 1;   // the next tile's producer wrote the buffer the last layer was not reading
   }
 }
 
 // ------------------------------------------------------------------------------------------------ epilogue helpers
 struct EpiCtx {
+  int slot;         // which in-flight tile this warp serves
   int row;          // row of the tile this thread owns (= TMEM lane)
-  int q;            // column quarter: this thread handles columns [32c + 8q, 32c + 8q + 8) of every chunk
+  int half;         // this thread handles columns [32c + 16*half, +16) of every chunk
   int lane, warp;
-  uint32_t tmem_lane_base;   // tmem_base + (lane quarter << 16)
-  uint32_t acc_parity;       // parity to wait for on bar_accfull[0/1] (both parts advance once per layer)
-  int a_cur;        // A buffer the current layer reads (epilogues write the other one)
+  uint32_t tslot;   // tmem_base + slot*SLOT_COLS + (lane quarter << 16)
+  uint32_t acc_parity;   // parity to wait for on bar_accfull[slot] (flips after every part)
   int e_in;         // exponent of the scale applied to the current A
   float rowmax_in;  // max |a| of the current A row (unscaled)
 };
@@ -271,93 +277,127 @@ __device__ __forceinline__ void epi_signal(const EpiCtx& cx, uint64_t* bar) {
   if (cx.lane == 0) mbar_arrive(bar);
 }
 
-// combine a per-thread partial row value across the four column quarters (max or sum)
+// combine a per-thread partial row value across the two column halves of the slot (max or sum)
 template <bool IS_MAX>
 __device__ __forceinline__ float epi_exchange(const Shared& sh, const EpiCtx& cx, float v) {
-  sts32(&sh.xchg[cx.q * TILE + cx.row], v);
-  named_bar_sync(1, EPI_THREADS);
-  float r = IS_MAX ? v : 0.f;
-#pragma unroll
-  for (int j = 0; j < NQ; ++j) {
-    const float o = lds32(&sh.xchg[j * TILE + cx.row]);
-    r = IS_MAX ? fmaxf(r, o) : r + o;      // sums are formed in quarter order by every thread: identical result in all four
-  }
-  named_bar_sync(1, EPI_THREADS);
-  return r;
+  float* x = sh.xchg + cx.slot * 2 * TILE;
+  sts32(&x[cx.half * TILE + cx.row], v);
+  named_bar_sync(1 + cx.slot, SLOT_THREADS);
+  const float a = lds32(&x[cx.row]), b = lds32(&x[TILE + cx.row]);   // same order in both threads: identical result
+  named_bar_sync(1 + cx.slot, SLOT_THREADS);
+  return IS_MAX ? fmaxf(a, b) : a + b;
 }
 
-// Writes this thread's 8 values of chunk c into A buffer `buf`.
-__device__ __forceinline__ void epi_store_a(const EpiCtx& cx, int buf, int c, const float (&v)[QW], float scale) {
-  uint32_t hi[4], lo[4];
-  split8(v, scale, hi, lo);
-  tmem_st4(cx.tmem_lane_base + col_ahi(buf) + 16 * c + 4 * cx.q, hi);
-  tmem_st4(cx.tmem_lane_base + col_alo(buf) + 16 * c + 4 * cx.q, lo);
+// Writes this thread's 16 values of chunk c into the slot's A.
+__device__ __forceinline__ void epi_store_packed(const EpiCtx& cx, int c, const uint32_t (&hi)[8], const uint32_t (&lo)[8]) {
+  tmem_st8(cx.tslot + COL_AHI + 16 * c + 8 * cx.half, hi);
+  tmem_st8(cx.tslot + COL_ALO + 16 * c + 8 * cx.half, lo);
+}
+__device__ __forceinline__ void epi_store_a(const EpiCtx& cx, int c, const float (&v)[HW], float scale) {
+  uint32_t hi[8], lo[8];
+  split16(v, scale, hi, lo);
+  epi_store_packed(cx, c, hi, lo);
 }
 
-// One accumulator part (chunks CBEG..CEND-1) of a layer epilogue: wait for the part, read the thread's
-// pieces, hand the part back to the MMA warp, then per chunk
-//   v = acc * unscale (+ bias) ; extra(c, col0, v) ; [relu] ; consume(c, col0, v)
-// and, if `signal` is set (the epilogue wrote the next layer's A), one mbarrier arrival per warp for the
-// whole part after a single tcgen05.wait::st.
-// UPFRONT: all pieces of the part are read first and the part is released before any arithmetic; otherwise
-// (register-hungry epilogues) the pieces are read chunk by chunk and the part is released after the last read.
-template <int PART, int CBEG, int CEND, bool RELU, bool UPFRONT, class Extra, class Consume>
-__device__ __forceinline__ void epi_part(const Shared& sh, EpiCtx& cx, float unscale, const float* bias_s, uint64_t* signal, Extra& extra,
-                                         Consume& consume) {
-  mbar_wait(&sh.bar_accfull[PART], cx.acc_parity);
-  tc_fence_after();
-  const uint32_t acc = cx.tmem_lane_base + COL_ACC + QW * cx.q;
-  const float2 us2 = make_float2(unscale, unscale);
-  uint32_t r[UPFRONT ? CEND - CBEG : 1][QW];
-  if (UPFRONT) {
-#pragma unroll
-    for (int c = CBEG; c < CEND; ++c) tmem_ld8(acc + 32 * c, r[c - CBEG]);
-    tmem_wait_ld();
-    tc_fence_before();
-    __syncwarp();
-    if (cx.lane == 0) mbar_arrive(&sh.bar_accempty[PART]);
-  }
-#pragma unroll
-  for (int c = CBEG; c < CEND; ++c) {
-    const int col0 = 32 * c + QW * cx.q;
-    const int ri = UPFRONT ? c - CBEG : 0;
-    if (!UPFRONT) {
-      tmem_ld8(acc + 32 * c, r[0]);
-      tmem_wait_ld();
-      if (c == CEND - 1) {
-        tc_fence_before();
-        __syncwarp();
-        if (cx.lane == 0) mbar_arrive(&sh.bar_accempty[PART]);
-      }
-    }
-    float v[QW];
-    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-    if (bias_s) { b0 = lds128(bias_s + col0); b1 = lds128(bias_s + col0 + 4); }
-    {
-      const float2 p0 = __ffma2_rn(make_float2(__uint_as_float(r[ri][0]), __uint_as_float(r[ri][1])), us2, make_float2(b0.x, b0.y));
-      const float2 p1 = __ffma2_rn(make_float2(__uint_as_float(r[ri][2]), __uint_as_float(r[ri][3])), us2, make_float2(b0.z, b0.w));
-      const float2 p2 = __ffma2_rn(make_float2(__uint_as_float(r[ri][4]), __uint_as_float(r[ri][5])), us2, make_float2(b1.x, b1.y));
-      const float2 p3 = __ffma2_rn(make_float2(__uint_as_float(r[ri][6]), __uint_as_float(r[ri][7])), us2, make_float2(b1.z, b1.w));
-      v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y; v[6] = p3.x; v[7] = p3.y;
-    }
-    extra(c, col0, v);
-    if (RELU) {
-#pragma unroll
-      for (int i = 0; i < QW; ++i) v[i] = fmaxf(v[i], 0.f);
-    }
-    consume(c, col0, v);
-  }
-  if (signal) epi_signal(cx, signal);
-}
-
-// Layer epilogue over the two accumulator parts; a_out = true when consume() writes the next layer's A
-// (arrivals on bar_a[0] after chunks 0..2 and on bar_a[1] after chunks 3..4).
-template <bool RELU, bool UPFRONT = true, class Extra, class Consume>
-__device__ __forceinline__ void epi_layer(const Shared& sh, EpiCtx& cx, float unscale, const float* bias_s, bool a_out, Extra extra,
-                                          Consume consume) {
-  epi_part<0, 0, NCHUNK_A, RELU, UPFRONT>(sh, cx, unscale, bias_s, a_out ? &sh.bar_a[0] : nullptr, extra, consume);
-  epi_part<1, NCHUNK_A, NCHUNK, RELU, UPFRONT>(sh, cx, unscale, bias_s, a_out ? &sh.bar_a[1] : nullptr, extra, consume);
+// wait for the next accumulator part of the slot
+__device__ __forceinline__ void epi_wait_part(const Shared& sh, EpiCtx& cx) {
+  mbar_wait(&sh.bar_accfull[cx.slot], cx.acc_parity);
   cx.acc_parity ^= 1;
+  tc_fence_after();
+}
+// every thread of the warp has its pieces of the part in registers -> hand the accumulator back
+__device__ __forceinline__ void epi_release_part(const Shared& sh, const EpiCtx& cx) {
+  tc_fence_before();
+  __syncwarp();
+  if (cx.lane == 0) mbar_arrive(&sh.bar_accempty[cx.slot]);
+}
+
+// v = acc * unscale (+ bias) for one 16-column piece
+__device__ __forceinline__ void epi_affine(const uint32_t (&r)[HW], float unscale, const float* bias_s, int col0, float (&v)[HW]) {
+  const float2 us2 = make_float2(unscale, unscale);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias_s) b = lds128(bias_s + col0 + 4 * i);
+    const float2 p0 = __ffma2_rn(make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), us2, make_float2(b.x, b.y));
+    const float2 p1 = __ffma2_rn(make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), us2, make_float2(b.z, b.w));
+    v[4 * i] = p0.x; v[4 * i + 1] = p0.y; v[4 * i + 2] = p1.x; v[4 * i + 3] = p1.y;
+  }
+}
+
+// Layer epilogue whose result becomes the slot's next A.  per chunk: v = affine(acc) ; extra(c, col0, v) ; relu ;
+// side(c, col0, v) [e.g. store the fp32 row piece] ; split with `scale`.  Part A's packed results wait in registers until the
+// layer's last MMA (part B) has completed — only then may A be overwritten.  Returns the thread's partial row maximum.
+template <class Extra, class Side>
+__device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, float unscale, const float* bias_s, float scale, Extra extra,
+                                                Side side) {
+  float mx = 0.f;
+  uint32_t hiA[NCHUNK_A][8], loA[NCHUNK_A][8];
+  epi_wait_part(sh, cx);
+  {
+    uint32_t r[NCHUNK_A][HW];
+#pragma unroll
+    for (int c = 0; c < NCHUNK_A; ++c) tmem_ld16(cx.tslot + COL_ACC + 32 * c + HW * cx.half, r[c]);
+    tmem_wait_ld();
+    epi_release_part(sh, cx);
+#pragma unroll
+    for (int c = 0; c < NCHUNK_A; ++c) {
+      const int col0 = 32 * c + HW * cx.half;
+      float v[HW];
+      epi_affine(r[c], unscale, bias_s, col0, v);
+      extra(c, col0, v);
+#pragma unroll
+      for (int i = 0; i < HW; ++i) { v[i] = fmaxf(v[i], 0.f); mx = fmaxf(mx, v[i]); }
+      side(c, col0, v);
+      split16(v, scale, hiA[c], loA[c]);
+    }
+  }
+  epi_wait_part(sh, cx);   // part B complete => every MMA of the layer has read A
+#pragma unroll
+  for (int c = 0; c < NCHUNK_A; ++c) epi_store_packed(cx, c, hiA[c], loA[c]);
+#pragma unroll
+  for (int c = NCHUNK_A; c < NCHUNK; ++c) {
+    const int col0 = 32 * c + HW * cx.half;
+    uint32_t r[HW];
+    tmem_ld16(cx.tslot + COL_ACC + 32 * (c - NCHUNK_A) + HW * cx.half, r);
+    tmem_wait_ld();
+    if (c == NCHUNK - 1) epi_release_part(sh, cx);
+    float v[HW];
+    epi_affine(r, unscale, bias_s, col0, v);
+    extra(c, col0, v);
+#pragma unroll
+    for (int i = 0; i < HW; ++i) { v[i] = fmaxf(v[i], 0.f); mx = fmaxf(mx, v[i]); }
+    side(c, col0, v);
+    epi_store_a(cx, c, v, scale);
+  }
+  epi_signal(cx, &sh.bar_a[cx.slot]);
+  return mx;
+}
+
+// Layer epilogue that only consumes the result (fp32 rows to HBM, running dot products ...): per chunk
+// v = affine(acc) ; [relu] ; consume(c, col0, v).  A is left untouched.
+template <bool RELU, class Consume>
+__device__ __forceinline__ void epi_layer_out(const Shared& sh, EpiCtx& cx, float unscale, const float* bias_s, Consume consume) {
+#pragma unroll
+  for (int part = 0; part < 2; ++part) {
+    epi_wait_part(sh, cx);
+    const int c0 = part ? NCHUNK_A : 0, c1 = part ? NCHUNK : NCHUNK_A;
+#pragma unroll
+    for (int c = c0; c < c1; ++c) {
+      const int col0 = 32 * c + HW * cx.half;
+      uint32_t r[HW];
+      tmem_ld16(cx.tslot + COL_ACC + 32 * (c - c0) + HW * cx.half, r);
+      tmem_wait_ld();
+      if (c == c1 - 1) epi_release_part(sh, cx);
+      float v[HW];
+      epi_affine(r, unscale, bias_s, col0, v);
+      if (RELU) {
+#pragma unroll
+        for (int i = 0; i < HW; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      consume(c, col0, v);
+    }
+  }
 }
 
 }  // namespace tc

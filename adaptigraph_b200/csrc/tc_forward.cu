@@ -74,11 +74,14 @@ __device__ __forceinline__ uint32_t chain_setup(Shared& sh, uint8_t* smem_raw, c
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
     mbar_init(sh.bar_wsmall, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh.bar_wfull[i], 1); mbar_init(&sh.bar_wempty[i], 1); mbar_init(&sh.bar_accfull[i], 1); mbar_init(&sh.bar_accempty[i], EPI_WARPS); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh.bar_a[i], EPI_WARPS); mbar_init(&sh.bar_in[i], EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh.bar_wfull[i], 1); mbar_init(&sh.bar_wempty[i], NSLOT); }
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(&sh.bar_in[i], SLOT_WARPS); mbar_init(&sh.bar_a[i], SLOT_WARPS);
+      mbar_init(&sh.bar_accfull[i], 1); mbar_init(&sh.bar_accempty[i], SLOT_WARPS);
+    }
     fence_mbar_init();
   }
-  if (warp == MMA_WARP) tmem_alloc(sh.tmem_ptr, TMEM_COLS);
+  if (warp == MMA_WARP0) tmem_alloc(sh.tmem_ptr, TMEM_COLS);
   for (int b = 0; b < MAX_BIAS; ++b)
     for (int i = tid; i < FP; i += THREADS) sh.bias[b * FP + i] = bias_src[b] ? bias_src[b][i] : 0.f;
   const float4* m = reinterpret_cast<const float4*>(blob + L.meta);
@@ -93,7 +96,7 @@ __device__ __forceinline__ uint32_t chain_setup(Shared& sh, uint8_t* smem_raw, c
 __device__ __forceinline__ void chain_teardown(uint32_t tmem_base) {
   tc_fence_before();
   __syncthreads();
-  if ((threadIdx.x >> 5) == MMA_WARP) {
+  if ((threadIdx.x >> 5) == MMA_WARP0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -103,59 +106,58 @@ __device__ __forceinline__ EpiCtx make_ctx(uint32_t tmem_base) {
   EpiCtx cx;
   cx.lane = threadIdx.x & 31;
   cx.warp = threadIdx.x >> 5;
-  cx.row = (cx.warp & 3) * 32 + cx.lane;
-  cx.q = cx.warp >> 2;
-  cx.tmem_lane_base = tmem_base + ((uint32_t)((cx.warp & 3) * 32) << 16);
+  cx.slot = cx.warp / SLOT_WARPS;
+  const int w = cx.warp % SLOT_WARPS;
+  cx.row = (w & 3) * 32 + cx.lane;
+  cx.half = w >> 2;
+  cx.tslot = tmem_base + cx.slot * SLOT_COLS + ((uint32_t)((w & 3) * 32) << 16);
   cx.acc_parity = 0;
-  cx.a_cur = 0;
   cx.e_in = 0;
   cx.rowmax_in = 0.f;
   return cx;
 }
 
-__device__ __forceinline__ float max8(const float (&v)[QW], float m) {   // max |v|
+__device__ __forceinline__ float max16(const float (&v)[HW], float m) {   // max |v|
 #pragma unroll
-  for (int i = 0; i < QW; ++i) m = fmaxf(m, fabsf(v[i]));
+  for (int i = 0; i < HW; ++i) m = fmaxf(m, fabsf(v[i]));
   return m;
 }
-__device__ __forceinline__ float max8_pos(const float (&v)[QW], float m) {   // v >= 0 (after ReLU)
-#pragma unroll
-  for (int i = 0; i < QW; ++i) m = fmaxf(m, v[i]);
-  return m;
+__device__ __forceinline__ void stg16(float* p, const float (&v)[HW]) {
+  const float a[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]}, b[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+  stg256(p, a);
+  stg256(p + 8, b);
 }
-struct NoExtra { __device__ void operator()(int, int, float (&)[QW]) const {} };
+struct NoExtra { __device__ void operator()(int, int, float (&)[HW]) const {} };
+struct NoSide { __device__ void operator()(int, int, const float (&)[HW]) const {} };
 
-// relu(bias + acc) -> next A (split fp16, other buffer), tracking the row maximum for the next layer's scale
-__device__ __forceinline__ void epi_relu_to_a(const Shared& sh, EpiCtx& cx, const float4 meta_l, const float* bias_s) {
+// relu(bias + acc) -> the slot's next A; updates the row scale bookkeeping
+template <class Side>
+__device__ __forceinline__ float epi_relu_to_a(const Shared& sh, EpiCtx& cx, const float4 meta_l, const float* bias_s, Side side) {
   const int e_next = scale_exp(cx.rowmax_in * meta_l.y + meta_l.z);
-  const float sc = exp2i(e_next), unscale = exp2i(-cx.e_in) * meta_l.x;
-  const int dst = cx.a_cur ^ 1;
-  float mx = 0.f;
-  epi_layer<true>(sh, cx, unscale, bias_s, true, NoExtra{}, [&](int c, int, float (&v)[QW]) {
-    mx = max8_pos(v, mx);
-    epi_store_a(cx, dst, c, v, sc);
-  });
-  cx.rowmax_in = epi_exchange<true>(sh, cx, mx);
+  const float unscale = exp2i(-cx.e_in) * meta_l.x;
+  float mx = epi_layer_to_a(sh, cx, unscale, bias_s, exp2i(e_next), NoExtra{}, side);
+  mx = epi_exchange<true>(sh, cx, mx);
+  cx.rowmax_in = mx;
   cx.e_in = e_next;
-  cx.a_cur = dst;
+  return mx;
 }
 
-// bias + acc -> fp32 rows in HBM (A in tensor memory is left untouched); returns this thread's partial max |v|
+// bias + acc -> fp32 rows in HBM (A is left untouched); returns this thread's partial max |v|
 __device__ __forceinline__ float epi_store_rows(const Shared& sh, EpiCtx& cx, const float4 meta_l, const float* bias_s, float* out,
                                                 int64_t grow, bool valid) {
   const float unscale = exp2i(-cx.e_in) * meta_l.x;
   float mx = 0.f;
-  epi_layer<false>(sh, cx, unscale, bias_s, false, NoExtra{}, [&](int, int col0, float (&v)[QW]) {
-    mx = max8(v, mx);
-    if (valid) stg256(out + grow * FP + col0, v);
+  epi_layer_out<false>(sh, cx, unscale, bias_s, [&](int, int col0, float (&v)[HW]) {
+    mx = max16(v, mx);
+    if (valid) stg16(out + grow * FP + col0, v);
   });
   return mx;
 }
 
-// input producer tail: per-row scale from the row maximum, split, write chunk(s), signal
-__device__ __forceinline__ void produce_begin(const Shared& sh, EpiCtx& cx, float partial_max, int& e_out, float& max_out) {
-  max_out = epi_exchange<true>(sh, cx, partial_max);
-  e_out = scale_exp(max_out);
+// k-th tile of this CTA's slot, or -1
+__device__ __forceinline__ int slot_tile(int k_slot, int slot, int n_tiles) {
+  const int t = (int)blockIdx.x + (k_slot * NSLOT + slot) * (int)gridDim.x;
+  return t < n_tiles ? t : -1;
 }
 
 // ------------------------------------------------------------------------------------ edge encoder
@@ -168,25 +170,22 @@ struct EdgeArgs {
   float* C;
 };
 
-// 17 relation inputs (model.py:224-253); quarter q builds inputs [8q, 8q+8) of the K=32 first layer
-__device__ __forceinline__ void edge_inputs(const EdgeArgs& a, int64_t e, int64_t E, int q, float (&v)[QW]) {
+// 17 relation inputs (model.py:224-253) of the K=32 first layer; half 0 builds inputs 0..15, half 1 input 16 (+ zero padding)
+__device__ __forceinline__ void edge_inputs(const EdgeArgs& a, int64_t e, int64_t E, int half, float (&v)[HW]) {
 #pragma unroll
-  for (int i = 0; i < QW; ++i) v[i] = 0.f;
-  if (e < E && q < 3) {
+  for (int i = 0; i < HW; ++i) v[i] = 0.f;
+  if (e >= 0 && e < E) {
     const int r = a.recv[e];
     const int s = (r / a.N) * a.N + a.send[e];
     const float4* fr = reinterpret_cast<const float4*>(a.nfeat + (size_t)r * NFEAT);
     const float4* fs = reinterpret_cast<const float4*>(a.nfeat + (size_t)s * NFEAT);
-    if (q == 0) {          // [attr_r, attr_s, |group_r - group_s|, hist diff 0..2]
-      const float4 r3 = fr[3], s3 = fs[3], r0 = fr[0], s0 = fs[0];
+    if (half == 0) {   // [attr_r, attr_s, |group_r - group_s|, hist diff 0..10]
+      const float4 r3 = fr[3], s3 = fs[3], r0 = fr[0], s0 = fs[0], r1 = fr[1], s1 = fs[1], r2 = fr[2], s2 = fs[2];
       v[0] = r3.x; v[1] = r3.y; v[2] = s3.x; v[3] = s3.y; v[4] = fabsf(r3.z - s3.z);
-      v[5] = r0.x - s0.x; v[6] = r0.y - s0.y; v[7] = r0.z - s0.z;
-    } else if (q == 1) {   // hist diff 3..10
-      const float4 r0 = fr[0], s0 = fs[0], r1 = fr[1], s1 = fs[1], r2 = fr[2], s2 = fs[2];
-      v[0] = r0.w - s0.w;
-      v[1] = r1.x - s1.x; v[2] = r1.y - s1.y; v[3] = r1.z - s1.z; v[4] = r1.w - s1.w;
-      v[5] = r2.x - s2.x; v[6] = r2.y - s2.y; v[7] = r2.z - s2.z;
-    } else {               // hist diff 11
+      v[5] = r0.x - s0.x; v[6] = r0.y - s0.y; v[7] = r0.z - s0.z; v[8] = r0.w - s0.w;
+      v[9] = r1.x - s1.x; v[10] = r1.y - s1.y; v[11] = r1.z - s1.z; v[12] = r1.w - s1.w;
+      v[13] = r2.x - s2.x; v[14] = r2.y - s2.y; v[15] = r2.z - s2.z;
+    } else {           // hist diff 11
       v[0] = fr[2].w - fs[2].w;
     }
   }
@@ -201,39 +200,31 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
   const int64_t E = min((int64_t)a.row_ptr[a.rows], a.E_cap);
   const int n_tiles = (int)((E + TILE - 1) / TILE);
   const int warp = threadIdx.x >> 5;
-  if (warp == LOAD_WARP) {
-    loader_role(sh, prog, a.blob, a.L, n_tiles);
-  } else if (warp == MMA_WARP) {
-    mma_role(sh, prog, tmem_base, n_tiles);
+  if (warp >= EPI_WARPS) {
+    reg_dealloc_other();
+    if (warp == LOAD_WARP) loader_role(sh, prog, a.blob, a.L, n_tiles);
+    else if (warp < LOAD_WARP) mma_role(sh, prog, warp - MMA_WARP0, tmem_base, n_tiles);
   } else {
+    reg_alloc_epilogue();
     EpiCtx cx = make_ctx(tmem_base);
-    int tile = blockIdx.x;
-    int e_nx = 0;
-    float mx_nx = 0.f;
-    if (tile < n_tiles) {   // first tile's input
-      float v[QW];
-      edge_inputs(a, (int64_t)tile * TILE + cx.row, E, cx.q, v);
-      produce_begin(sh, cx, max8(v, 0.f), e_nx, mx_nx);
-      epi_store_a(cx, 0, 0, v, exp2i(e_nx));
-      epi_signal(cx, &sh.bar_in[0]);
-    }
-    for (; tile < n_tiles; tile += gridDim.x) {
+    int tile = slot_tile(0, cx.slot, n_tiles);
+    float vin[HW];
+    if (tile >= 0) edge_inputs(a, (int64_t)tile * TILE + cx.row, E, cx.half, vin);
+    for (int k = 0; tile >= 0; ++k) {
       const int64_t e = (int64_t)tile * TILE + cx.row;
-      cx.e_in = e_nx;
-      cx.rowmax_in = mx_nx;
-      const int next = tile + gridDim.x;
-      float vn[QW];
-      if (next < n_tiles) edge_inputs(a, (int64_t)next * TILE + cx.row, E, cx.q, vn);   // gather in flight during this tile
-      epi_relu_to_a(sh, cx, meta[0], sh.bias + 0 * FP);
-      epi_relu_to_a(sh, cx, meta[1], sh.bias + 1 * FP);
-      epi_relu_to_a(sh, cx, meta[2], sh.bias + 2 * FP);
-      if (next < n_tiles) {   // next tile's A goes into the buffer the last layer is not reading
-        produce_begin(sh, cx, max8(vn, 0.f), e_nx, mx_nx);
-        epi_store_a(cx, cx.a_cur ^ 1, 0, vn, exp2i(e_nx));
-        epi_signal(cx, &sh.bar_in[0]);
-      }
+      // ---- input producer: the slot's A is free (the previous tile's last layer has been read out)
+      const float mx = epi_exchange<true>(sh, cx, max16(vin, 0.f));
+      cx.e_in = scale_exp(mx);
+      cx.rowmax_in = mx;
+      epi_store_a(cx, 0, vin, exp2i(cx.e_in));
+      epi_signal(cx, &sh.bar_in[cx.slot]);
+      const int next = slot_tile(k + 1, cx.slot, n_tiles);
+      if (next >= 0) edge_inputs(a, (int64_t)next * TILE + cx.row, E, cx.half, vin);   // gather in flight during this tile
+      epi_relu_to_a(sh, cx, meta[0], sh.bias + 0 * FP, NoSide{});
+      epi_relu_to_a(sh, cx, meta[1], sh.bias + 1 * FP, NoSide{});
+      epi_relu_to_a(sh, cx, meta[2], sh.bias + 2 * FP, NoSide{});
       epi_store_rows(sh, cx, meta[3], sh.bias + 3 * FP, a.C, e, e < E);
-      cx.a_cur ^= 1;
+      tile = next;
     }
   }
   chain_teardown(tmem_base);
@@ -248,11 +239,11 @@ struct NodeArgs {
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* rowmaxP; float* rowmaxA;
 };
 
-// node inputs (model.py:168-195) + the nfeat record; only quarter 0 carries data (6 real inputs of the K=16 layer)
-__device__ __forceinline__ void node_inputs(const NodeArgs& a, int64_t r, int64_t rows, int q, float (&in)[QW]) {
+// node inputs (model.py:168-195) + the nfeat record; only half 0 carries data (6 real inputs of the K=16 layer)
+__device__ __forceinline__ void node_inputs(const NodeArgs& a, int64_t r, int64_t rows, int half, float (&in)[HW]) {
 #pragma unroll
-  for (int i = 0; i < QW; ++i) in[i] = 0.f;
-  if (r < rows && q == 0) {
+  for (int i = 0; i < HW; ++i) in[i] = 0.f;
+  if (r >= 0 && r < rows && half == 0) {
     const int b = (int)(r / a.N), n = (int)(r - (int64_t)b * a.N);
     float s[H_FIX][3];
 #pragma unroll
@@ -283,60 +274,38 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
   const int64_t rows = (int64_t)a.B * a.N;
   const int n_tiles = (int)((rows + TILE - 1) / TILE);
   const int warp = threadIdx.x >> 5;
-  if (warp == LOAD_WARP) {
-    loader_role(sh, prog, a.blob, a.L, n_tiles);
-  } else if (warp == MMA_WARP) {
-    mma_role(sh, prog, tmem_base, n_tiles);
+  if (warp >= EPI_WARPS) {
+    reg_dealloc_other();
+    if (warp == LOAD_WARP) loader_role(sh, prog, a.blob, a.L, n_tiles);
+    else if (warp < LOAD_WARP) mma_role(sh, prog, warp - MMA_WARP0, tmem_base, n_tiles);
   } else {
+    reg_alloc_epilogue();
     EpiCtx cx = make_ctx(tmem_base);
-    int tile = blockIdx.x;
-    int e_nx = 0;
-    float mx_nx = 0.f;
-    if (tile < n_tiles) {
-      float in[QW];
-      node_inputs(a, (int64_t)tile * TILE + cx.row, rows, cx.q, in);
-      produce_begin(sh, cx, max8(in, 0.f), e_nx, mx_nx);
-      if (cx.q < 2) epi_store_a(cx, 0, 0, in, exp2i(e_nx));   // quarters 0 and 1 cover the 16 K columns
-      epi_signal(cx, &sh.bar_in[0]);
-    }
-    for (; tile < n_tiles; tile += gridDim.x) {
+    int tile = slot_tile(0, cx.slot, n_tiles);
+    for (int k = 0; tile >= 0; ++k) {
       const int64_t r = (int64_t)tile * TILE + cx.row;
       const bool valid = r < rows;
-      cx.e_in = e_nx;
-      cx.rowmax_in = mx_nx;
-      const int next = tile + gridDim.x;
-      float inn[QW];
-      if (next < n_tiles) node_inputs(a, (int64_t)next * TILE + cx.row, rows, cx.q, inn);
-      epi_relu_to_a(sh, cx, meta[0], sh.bias + 0 * FP);
-      epi_relu_to_a(sh, cx, meta[1], sh.bias + 1 * FP);
-      {  // particle_encode = particle_effect_0 (model.py:268-269): next A and P rows
-        const float4 m = meta[2];
-        const int e_next = scale_exp(cx.rowmax_in * m.y + m.z);
-        const float sc = exp2i(e_next), unscale = exp2i(-cx.e_in) * m.x;
-        const int dst = cx.a_cur ^ 1;
-        float pm = 0.f;
-        epi_layer<true>(sh, cx, unscale, sh.bias + 2 * FP, true, NoExtra{}, [&](int c, int col0, float (&v)[QW]) {
-          pm = max8_pos(v, pm);
-          epi_store_a(cx, dst, c, v, sc);
-          if (valid) stg256(a.P + r * FP + col0, v);
-        });
-        pm = epi_exchange<true>(sh, cx, pm);
-        cx.rowmax_in = pm;
-        cx.e_in = e_next;
-        cx.a_cur = dst;
-        if (valid && cx.q == 0) a.rowmaxP[r] = pm;
-      }
-      if (next < n_tiles) {
-        produce_begin(sh, cx, max8(inn, 0.f), e_nx, mx_nx);
-        if (cx.q < 2) epi_store_a(cx, cx.a_cur ^ 1, 0, inn, exp2i(e_nx));
-        epi_signal(cx, &sh.bar_in[0]);
-      }
+      float in[HW];
+      node_inputs(a, r, rows, cx.half, in);
+      const float mx = epi_exchange<true>(sh, cx, max16(in, 0.f));
+      cx.e_in = scale_exp(mx);
+      cx.rowmax_in = mx;
+      if (cx.half == 0) epi_store_a(cx, 0, in, exp2i(cx.e_in));   // the K=16 layer reads A columns 0..7 only
+      epi_signal(cx, &sh.bar_in[cx.slot]);
+
+      epi_relu_to_a(sh, cx, meta[0], sh.bias + 0 * FP, NoSide{});
+      epi_relu_to_a(sh, cx, meta[1], sh.bias + 1 * FP, NoSide{});
+      // particle_encode = particle_effect_0 (model.py:268-269): next A and P rows
+      const float pm = epi_relu_to_a(sh, cx, meta[2], sh.bias + 2 * FP, [&](int, int col0, const float (&v)[HW]) {
+        if (valid) stg16(a.P + r * FP + col0, v);
+      });
+      if (valid && cx.half == 0) a.rowmaxP[r] = pm;
       float am = epi_store_rows(sh, cx, meta[3], sh.bias + 3 * FP, a.A, r, valid);   // A_n = W_enc*penc + b
       am = epi_exchange<true>(sh, cx, am);
-      if (valid && cx.q == 0) a.rowmaxA[r] = am;
+      if (valid && cx.half == 0) a.rowmaxA[r] = am;
       epi_store_rows(sh, cx, meta[4], nullptr, a.Qr, r, valid);
       epi_store_rows(sh, cx, meta[5], nullptr, a.Qs, r, valid);
-      cx.a_cur ^= 1;
+      tile = slot_tile(k + 1, cx.slot, n_tiles);
     }
   }
   chain_teardown(tmem_base);
@@ -345,38 +314,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
 // ------------------------------------------------------------------------------------ node update / head
 struct UpdArgs {
   int B, N, n_p;
-  const float* agg; const float* A; float* P; float* Qr; float* Qs; float* rowmaxP; const float* rowmaxA;
+  const uint32_t* agg_split;   // [rows][FP] : 80 packed-fp16 hi columns then 80 lo columns per row (edge_aggregate, split output)
+  const int32_t* agg_exp; const float* agg_max;   // per-row scale exponent / row maximum of agg
+  const float* A; float* P; float* Qr; float* Qs; float* rowmaxP; const float* rowmaxA;
   const uint8_t* blob; TcLayout L;
   const float* bias[MAX_BIAS];
   const float* head_w;   // fp32 [3][FP] then 4 bias floats (head only)
   const float* state; float* pred_pos; int64_t pos_stride_b; float* pred_motion;
 };
-
-__device__ __forceinline__ float agg_inputs(const UpdArgs& a, int64_t r, int64_t rows, int q, float (&g)[NCHUNK][QW]) {
-  float mx = 0.f;
-#pragma unroll
-  for (int c = 0; c < NCHUNK; ++c) {
-    if (r < rows) ldg256(a.agg + r * FP + 32 * c + QW * q, g[c]);
-    else {
-#pragma unroll
-      for (int i = 0; i < QW; ++i) g[c][i] = 0.f;
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < NCHUNK; ++c) mx = max8(g[c], mx);
-  return mx;
-}
-__device__ __forceinline__ void agg_produce(const Shared& sh, EpiCtx& cx, const float (&g)[NCHUNK][QW], float partial_max, int buf, int& e_out,
-                                            float& max_out) {
-  produce_begin(sh, cx, partial_max, e_out, max_out);
-  const float sc = exp2i(e_out);
-#pragma unroll
-  for (int c = 0; c < NCHUNK_A; ++c) epi_store_a(cx, buf, c, g[c], sc);
-  epi_signal(cx, &sh.bar_in[0]);
-#pragma unroll
-  for (int c = NCHUNK_A; c < NCHUNK; ++c) epi_store_a(cx, buf, c, g[c], sc);
-  epi_signal(cx, &sh.bar_in[1]);
-}
 
 template <bool LAST>
 __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArgs a) {
@@ -393,79 +338,74 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
   const int64_t rows = (int64_t)a.B * a.N;
   const int n_tiles = (int)((rows + TILE - 1) / TILE);
   const int warp = threadIdx.x >> 5;
-  if (warp == LOAD_WARP) {
-    loader_role(sh, prog, a.blob, a.L, n_tiles);
-  } else if (warp == MMA_WARP) {
-    mma_role(sh, prog, tmem_base, n_tiles);
+  if (warp >= EPI_WARPS) {
+    reg_dealloc_other();
+    if (warp == LOAD_WARP) loader_role(sh, prog, a.blob, a.L, n_tiles);
+    else if (warp < LOAD_WARP) mma_role(sh, prog, warp - MMA_WARP0, tmem_base, n_tiles);
   } else {
+    reg_alloc_epilogue();
     EpiCtx cx = make_ctx(tmem_base);
-    int tile = blockIdx.x;
-    int e_nx = 0;
-    float mx_nx = 0.f;
-    if (tile < n_tiles) {   // first tile: the aggregated relation effects of this row become A (K = 160)
-      float g[NCHUNK][QW];
-      const float pmx = agg_inputs(a, (int64_t)tile * TILE + cx.row, rows, cx.q, g);
-      agg_produce(sh, cx, g, pmx, 0, e_nx, mx_nx);
-    }
-    for (; tile < n_tiles; tile += gridDim.x) {
+    int tile = slot_tile(0, cx.slot, n_tiles);
+    for (int k = 0; tile >= 0; ++k) {
       const int64_t r = (int64_t)tile * TILE + cx.row;
       const bool valid = r < rows;
-      cx.e_in = e_nx;
-      cx.rowmax_in = mx_nx;
-      const int next = tile + gridDim.x;
+      // ---- producer: the aggregated relation effects arrive already scaled and split (edge_aggregate): copy to A
+      {
+        const uint32_t* row = a.agg_split + r * FP;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          uint32_t hi[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lo[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          if (valid) {
+            ldg256(reinterpret_cast<const float*>(row + 16 * c + 8 * cx.half), reinterpret_cast<float(&)[8]>(hi));
+            ldg256(reinterpret_cast<const float*>(row + 80 + 16 * c + 8 * cx.half), reinterpret_cast<float(&)[8]>(lo));
+          }
+          epi_store_packed(cx, c, hi, lo);
+        }
+        cx.e_in = valid ? a.agg_exp[r] : 0;
+        cx.rowmax_in = valid ? a.agg_max[r] : 0.f;
+        epi_signal(cx, &sh.bar_in[cx.slot]);
+      }
       {  // P <- relu((W_agg*agg + A_n) + P)   (model.py:36-40, :299-301)
         const float4 m = meta[0];
         const float extra_bound = valid ? a.rowmaxA[r] + a.rowmaxP[r] : 0.f;   // bound on |A_n + P| of this row
         const int e_next = scale_exp(cx.rowmax_in * m.y + extra_bound);
-        const float sc = exp2i(e_next), unscale = exp2i(-cx.e_in) * m.x;
-        const int dst = cx.a_cur ^ 1;
-        float pm = 0.f;
-        // residual rows A_n and P: software pipeline of depth one (chunk c+1 is requested before chunk c is used)
-        float an[2][QW], pp[2][QW];
-        const float* a_row = a.A + r * FP + QW * cx.q;
-        const float* p_row = a.P + r * FP + QW * cx.q;
-        if (valid) { ldg256(a_row, an[0]); ldg256(p_row, pp[0]); }
-        epi_layer<true, false>(sh, cx, unscale, nullptr, true,
-                        [&](int c, int, float (&v)[QW]) {
-                          if (valid) {
-                            if (c + 1 < NCHUNK) { ldg256(a_row + 32 * (c + 1), an[(c + 1) & 1]); ldg256(p_row + 32 * (c + 1), pp[(c + 1) & 1]); }
+        const float unscale = exp2i(-cx.e_in) * m.x;
+        const float* a_row = a.A + r * FP;
+        float* p_row = a.P + r * FP;
+        float pm = epi_layer_to_a(sh, cx, unscale, nullptr, exp2i(e_next),
+                                  [&](int, int col0, float (&v)[HW]) {
+                                    if (valid) {
+                                      float t[8];
 #pragma unroll
-                            for (int i = 0; i < QW; ++i) v[i] = (v[i] + an[c & 1][i]) + pp[c & 1][i];
-                          }
-                        },
-                        [&](int c, int col0, float (&v)[QW]) {
-                          pm = max8_pos(v, pm);
-                          epi_store_a(cx, dst, c, v, sc);
-                          if (!LAST && valid) stg256(a.P + r * FP + col0, v);
-                        });
+                                      for (int h = 0; h < 2; ++h) {
+                                        ldg256(a_row + col0 + 8 * h, t);
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) v[8 * h + i] += t[i];
+                                        ldg256(p_row + col0 + 8 * h, t);
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) v[8 * h + i] += t[i];
+                                      }
+                                    }
+                                  },
+                                  [&](int, int col0, const float (&v)[HW]) {
+                                    if (!LAST && valid) stg16(p_row + col0, v);
+                                  });
         pm = epi_exchange<true>(sh, cx, pm);
         cx.rowmax_in = pm;
         cx.e_in = e_next;
-        cx.a_cur = dst;
-        if (!LAST && valid && cx.q == 0) a.rowmaxP[r] = pm;
+        if (!LAST && valid && cx.half == 0) a.rowmaxP[r] = pm;
       }
-      // the next tile's aggregated effects are fetched and written into the free A buffer while the MMA warp is
-      // busy with the remaining layers of this tile (the epilogue threads have slack there)
-      auto produce_next = [&]() {
-        if (next < n_tiles) {
-          float gn[NCHUNK][QW];
-          const float pmx_n = agg_inputs(a, (int64_t)next * TILE + cx.row, rows, cx.q, gn);
-          agg_produce(sh, cx, gn, pmx_n, cx.a_cur ^ 1, e_nx, mx_nx);
-        }
-      };
       if (!LAST) {
         epi_store_rows(sh, cx, meta[1], nullptr, a.Qr, r, valid);
-        produce_next();
         epi_store_rows(sh, cx, meta[2], nullptr, a.Qs, r, valid);
       } else {
-        epi_relu_to_a(sh, cx, meta[1], sh.bias + 0 * FP);
-        produce_next();
+        epi_relu_to_a(sh, cx, meta[1], sh.bias + 0 * FP, NoSide{});
         // motion head (model.py:306-309): relu(linear_1) then the 3-row linear_2 as running dot products
         const float unscale = exp2i(-cx.e_in) * meta[2].x;
         float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-        epi_layer<true>(sh, cx, unscale, sh.bias + 1 * FP, false, NoExtra{}, [&](int, int col0, float (&v)[QW]) {
+        epi_layer_out<true>(sh, cx, unscale, sh.bias + 1 * FP, [&](int, int col0, float (&v)[HW]) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < 4; ++h) {
             const float4 w0 = lds128(sh.head_w + col0 + 4 * h), w1 = lds128(sh.head_w + FP + col0 + 4 * h),
                          w2 = lds128(sh.head_w + 2 * FP + col0 + 4 * h);
             m0 = fmaf(v[4 * h + 3], w0.w, fmaf(v[4 * h + 2], w0.z, fmaf(v[4 * h + 1], w0.y, fmaf(v[4 * h], w0.x, m0))));
@@ -476,7 +416,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
         m0 = epi_exchange<false>(sh, cx, m0);
         m1 = epi_exchange<false>(sh, cx, m1);
         m2 = epi_exchange<false>(sh, cx, m2);
-        if (valid && cx.q == 0) {
+        if (valid && cx.half == 0) {
           const int b = (int)(r / a.N), n = (int)(r - (int64_t)b * a.N);
           if (n < a.n_p) {
             m0 += lds32(sh.head_w + 3 * FP + 0); m1 += lds32(sh.head_w + 3 * FP + 1); m2 += lds32(sh.head_w + 3 * FP + 2);
@@ -490,10 +430,69 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
           }
         }
       }
-      cx.a_cur ^= 1;
+      tile = slot_tile(k + 1, cx.slot, n_tiles);
     }
   }
   chain_teardown(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------ edge aggregate (split output)
+// Same reduction as forward.cu's edge_aggregate_kernel, but the row leaves the kernel the way the update chain's
+// tensor-memory A wants it: scaled by an exact per-row power of two and split into packed fp16 hi / lo columns.
+constexpr int AGG_NODES = 8;
+constexpr int AGG_THREADS = AGG_NODES * (FP / 4);  // 320
+
+__device__ __forceinline__ float4 relu_add3(const float4 c, const float4 qr, const float4 qs) {
+  return make_float4(fmaxf((c.x + qr.x) + qs.x, 0.f), fmaxf((c.y + qr.y) + qs.y, 0.f),
+                     fmaxf((c.z + qr.z) + qs.z, 0.f), fmaxf((c.w + qr.w) + qs.w, 0.f));
+}
+
+__global__ void __launch_bounds__(AGG_THREADS) edge_aggregate_split_kernel(
+    const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send, int64_t rows, int N, int64_t E_cap,
+    const float4* __restrict__ C, const float4* __restrict__ Qr, const float4* __restrict__ Qs, uint32_t* __restrict__ agg_split,
+    int32_t* __restrict__ agg_exp, float* __restrict__ agg_max) {
+  __shared__ int smax[AGG_NODES];
+  const int slot = threadIdx.x / (FP / 4), j = threadIdx.x - slot * (FP / 4);
+  const int64_t r = (int64_t)blockIdx.x * AGG_NODES + slot;
+  if (threadIdx.x < AGG_NODES) smax[threadIdx.x] = 0;
+  __syncthreads();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < rows) {
+    const int64_t beg = row_ptr[r];
+    const int64_t end = min((int64_t)row_ptr[r + 1], E_cap);
+    const int64_t gb = (r / N) * N;
+    const float4 qr = Qr[r * (FP / 4) + j];
+    int64_t e = beg;
+    for (; e + 1 < end; e += 2) {
+      const int64_t s0 = gb + send[e], s1 = gb + send[e + 1];
+      const float4 c0 = C[e * (FP / 4) + j], c1 = C[(e + 1) * (FP / 4) + j];
+      const float4 q0 = Qs[s0 * (FP / 4) + j], q1 = Qs[s1 * (FP / 4) + j];
+      const float4 v0 = relu_add3(c0, qr, q0), v1 = relu_add3(c1, qr, q1);
+      acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+      acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+    }
+    if (e < end) {
+      const int64_t s0 = gb + send[e];
+      const float4 v0 = relu_add3(C[e * (FP / 4) + j], qr, Qs[s0 * (FP / 4) + j]);
+      acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+    }
+    // agg >= 0 (sum of ReLUs): the int view of the floats orders like the floats
+    atomicMax(&smax[slot], __float_as_int(fmaxf(fmaxf(acc.x, acc.y), fmaxf(acc.z, acc.w))));
+  }
+  __syncthreads();
+  if (r < rows) {
+    const float mx = __int_as_float(smax[slot]);
+    const int e = scale_exp(mx);
+    const float sc = exp2i(e);
+    const float2 s0 = __fmul2_rn(make_float2(acc.x, acc.y), make_float2(sc, sc)), s1 = __fmul2_rn(make_float2(acc.z, acc.w), make_float2(sc, sc));
+    const __half2 h0 = __float22half2_rn(s0), h1 = __float22half2_rn(s1);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __float22half2_rn(make_float2(s0.x - f0.x, s0.y - f0.y)), l1 = __float22half2_rn(make_float2(s1.x - f1.x, s1.y - f1.y));
+    uint32_t* row = agg_split + r * FP;
+    *reinterpret_cast<uint2*>(row + 2 * j) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(row + 80 + 2 * j) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    if (j == 0) { agg_exp[r] = e; agg_max[r] = mx; }
+  }
 }
 
 }  // namespace tc
@@ -533,6 +532,7 @@ int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_
 
 struct TcFwdBuffers {
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
+  int32_t* agg_exp; float* agg_max;
 };
 
 static int tc_ensure_attrs() {
@@ -575,6 +575,17 @@ int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
   return AGX_OK;
 }
 
+int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st) {
+  using namespace tc;
+  const int64_t rows = (int64_t)g->B * g->N;
+  { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
+    edge_aggregate_split_kernel<<<(unsigned)((rows + AGG_NODES - 1) / AGG_NODES), AGG_THREADS, 0, st>>>(
+        g->row_ptr, g->send, rows, g->N, g->E_cap, reinterpret_cast<const float4*>(w.C), reinterpret_cast<const float4*>(w.Qr),
+        reinterpret_cast<const float4*>(w.Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max); }
+  AGX_LAUNCH_CHECK();
+  return AGX_OK;
+}
+
 int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool last,
                    float* pred_pos, int64_t pos_stride_b, float* pred_motion, cudaStream_t st) {
   using namespace tc;
@@ -582,7 +593,7 @@ int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL
   const int64_t rows = (int64_t)g->B * g->N;
   const int tiles = (int)((rows + TILE - 1) / TILE);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  UpdArgs a{g->B, g->N, g->n_p, w.agg, w.A, w.P, w.Qr, w.Qs, w.rowmaxP, w.rowmaxA,
+  UpdArgs a{g->B, g->N, g->n_p, reinterpret_cast<const uint32_t*>(w.agg), w.agg_exp, w.agg_max, w.A, w.P, w.Qr, w.Qs, w.rowmaxP, w.rowmaxA,
             reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
             {wts + PL.pred0_b, wts + PL.pred1_b, nullptr, nullptr},
             wts + PL.pred2_w, g->state, pred_pos, pos_stride_b, pred_motion};

@@ -152,6 +152,11 @@ __device__ __forceinline__ float lds32(const float* p) {
 }
 __device__ __forceinline__ void sts32(float* p, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory"); }
 
+// Register re-partitioning between warpgroups (20 warps: 4 epilogue warpgroups + 1 warpgroup of MMA / loader / idle warps)
+// The pool only holds what the dec side releases: 128 threads x (96 - 40) = 7168 registers >= 512 threads x (104 - 96) = 4096.
+__device__ __forceinline__ void reg_alloc_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory"); }
+__device__ __forceinline__ void reg_dealloc_other() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 }  // namespace tc

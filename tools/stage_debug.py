@@ -66,8 +66,15 @@ def main(fname="forward_cloth64_pad_k3.npz", precision=0):
     A = take(rows * 160).view(rows, 160)[:, :150]
     Qr = take(rows * 160).view(rows, 160)[:, :150]
     Qs = take(rows * 160).view(rows, 160)[:, :150]
-    aggb = take(rows * 160).view(rows, 160)[:, :150]
+    agg_raw = take(rows * 160).view(rows, 160)
     Cb = take(max(E, 1) * 160).view(max(E, 1), 160)[:E, :150]
+    take(rows); take(rows)                      # rowmaxP, rowmaxA
+    agg_exp = take(rows).view(torch.int32)
+    if precision == 1:                          # tensor-core path: agg rows are stored scaled and split (80 packed hi + 80 packed lo columns)
+        halves = agg_raw.contiguous().view(torch.float16).view(rows, 320).float()
+        aggb = ((halves[:, :160] + halves[:, 160:]) * torch.exp2(-agg_exp.float())[:, None])[:, :150]
+    else:
+        aggb = agg_raw[:, :150]
 
     # expectations from golden per-stage tensors
     hist, p_in, group = orc.node_and_relation_inputs(state, attrs, p_inst, action, phys)
