@@ -36,6 +36,7 @@ EXPORTS = [
     "agx_forward_workspace_bytes", "agx_forward",
     "agx_rollout_workspace_bytes", "agx_rollout",
     "agx_profile_enable", "agx_profile_read", "agx_kind_name",
+    "agx_train_saved_bytes", "agx_train_scratch_bytes", "agx_forward_train", "agx_backward",
 ]
 AGX_NUM_KINDS = 12
 
@@ -46,6 +47,10 @@ class AgxModelDims(C.Structure):
 
 
 class AgxWeights(C.Structure):
+    _fields_ = [("weight", C.c_void_p * AGX_NUM_LAYERS), ("bias", C.c_void_p * AGX_NUM_LAYERS)]
+
+
+class AgxWeightGrads(C.Structure):
     _fields_ = [("weight", C.c_void_p * AGX_NUM_LAYERS), ("bias", C.c_void_p * AGX_NUM_LAYERS)]
 
 
@@ -87,6 +92,10 @@ def _load() -> C.CDLL:
         "agx_forward": (C.c_int, [P(AgxModelDims), vp, P(AgxGraphIn), vp, i64, vp, i32, vp, sz, vp]),
         "agx_rollout_workspace_bytes": (sz, [P(AgxModelDims), i32, i32, i64, i32]),
         "agx_rollout": (C.c_int, [P(AgxModelDims), vp, P(AgxRolloutIn), vp, vp, vp, i32, vp, sz, vp]),
+        "agx_train_saved_bytes": (sz, [P(AgxModelDims), i32, i32, i64]),
+        "agx_train_scratch_bytes": (sz, [P(AgxModelDims), i32, i32, i64]),
+        "agx_forward_train": (C.c_int, [P(AgxModelDims), vp, P(AgxGraphIn), vp, i64, vp, vp, sz, vp]),
+        "agx_backward": (C.c_int, [P(AgxModelDims), vp, P(AgxGraphIn), vp, vp, vp, vp, vp, vp, P(AgxWeightGrads), vp, vp, sz, vp]),
         "agx_profile_enable": (C.c_int, [i32]),
         "agx_profile_read": (C.c_int, [P(C.c_double), P(i64)]),
         "agx_kind_name": (C.c_char_p, [i32]),

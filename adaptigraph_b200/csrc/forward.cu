@@ -36,6 +36,8 @@ struct TcFwdBuffers {
 };
 int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st);
 size_t tc_blob_bytes(size_t base_bytes);
+size_t train_blob_bytes();
+int train_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, cudaStream_t st);
 int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_t base_bytes, cudaStream_t st);
 int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, cudaStream_t st);
 int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, cudaStream_t st);
@@ -538,7 +540,7 @@ extern "C" {
 
 size_t agx_packed_weights_bytes(const AgxModelDims* dims) {
   (void)dims;
-  return agx::tc_blob_bytes(agx::packed_layout().total * sizeof(float));
+  return agx::train_blob_bytes();   // fp32 k-major section + tensor-core fp16 images + plain copies for the dgrad products
 }
 
 int agx_pack_weights(const AgxModelDims* dims, const AgxWeights* raw, void* packed, agx_stream_t stream) {
@@ -582,7 +584,8 @@ int agx_pack_weights(const AgxModelDims* dims, const AgxWeights* raw, void* pack
   pack_rows_kernel<<<(3 * FP + 255) / 256, 256, 0, st>>>(raw->weight[AGX_W_PRED2], 3, F, out + L.pred2_w);
   AGX_LAUNCH_CHECK();
   if (int rc2 = vec(AGX_W_PRED2, 3, 4, L.pred2_b)) return rc2;
-  return tc_pack(dims, raw, packed, L.total * sizeof(float), st);   // scaled fp16 hi/lo images for the tensor-core path
+  if (int rc3 = tc_pack(dims, raw, packed, L.total * sizeof(float), st)) return rc3;   // scaled fp16 hi/lo images for the tensor-core path
+  return train_pack(dims, raw, packed, st);                                             // plain padded copies for the backward
 }
 
 size_t agx_forward_workspace_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap) {

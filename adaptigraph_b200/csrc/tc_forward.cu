@@ -208,18 +208,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
     reg_alloc_epilogue();
     EpiCtx cx = make_ctx(tmem_base);
     int tile = slot_tile(0, cx.slot, n_tiles);
-    float vin[HW];
-    if (tile >= 0) edge_inputs(a, (int64_t)tile * TILE + cx.row, E, cx.half, vin);
     for (int k = 0; tile >= 0; ++k) {
       const int64_t e = (int64_t)tile * TILE + cx.row;
-      // ---- input producer: the slot's A is free (the previous tile's last layer has been read out)
-      const float mx = epi_exchange<true>(sh, cx, max16(vin, 0.f));
-      cx.e_in = scale_exp(mx);
-      cx.rowmax_in = mx;
-      epi_store_a(cx, 0, vin, exp2i(cx.e_in));
-      epi_signal(cx, &sh.bar_in[cx.slot]);
+      // ---- input producer: the slot's A is free (the previous tile's last layer has been read out); the gather
+      // latency is covered by the other slot's MMAs
+      {
+        float vin[HW];
+        edge_inputs(a, e, E, cx.half, vin);
+        const float mx = epi_exchange<true>(sh, cx, max16(vin, 0.f));
+        cx.e_in = scale_exp(mx);
+        cx.rowmax_in = mx;
+        epi_store_a(cx, 0, vin, exp2i(cx.e_in));
+        epi_signal(cx, &sh.bar_in[cx.slot]);
+      }
       const int next = slot_tile(k + 1, cx.slot, n_tiles);
-      if (next >= 0) edge_inputs(a, (int64_t)next * TILE + cx.row, E, cx.half, vin);   // gather in flight during this tile
       epi_relu_to_a(sh, cx, meta[0], sh.bias + 0 * FP, NoSide{});
       epi_relu_to_a(sh, cx, meta[1], sh.bias + 1 * FP, NoSide{});
       epi_relu_to_a(sh, cx, meta[2], sh.bias + 2 * FP, NoSide{});

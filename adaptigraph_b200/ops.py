@@ -217,3 +217,49 @@ def profile_read() -> dict:
     cnt = (C.c_int64 * L.AGX_NUM_KINDS)()
     L.check(lib.agx_profile_read(ms, cnt), "agx_profile_read")
     return {lib.agx_kind_name(i).decode(): (ms[i], cnt[i]) for i in range(L.AGX_NUM_KINDS) if cnt[i]}
+
+
+# --------------------------------------------------------------------------- training (forward with saved activations, backward)
+def _graph_in(state, attrs, action, p_inst, physics, row_ptr, send, recv):
+    B, H, N, _ = state.shape
+    n_p = p_inst.shape[1]
+    return L.AgxGraphIn(B, N, n_p, state.data_ptr(), attrs.data_ptr(), action.data_ptr(), p_inst.data_ptr(), physics.data_ptr(),
+                        row_ptr.data_ptr(), send.data_ptr(), recv.data_ptr(), int(send.numel()))
+
+
+def forward_train(packed: Tensor, state: Tensor, attrs: Tensor, action: Tensor, p_inst: Tensor, physics: Tensor, row_ptr: Tensor,
+                  send: Tensor, recv: Tensor, F: int, pstep: int):
+    """Exact-fp32 forward that keeps every activation the backward needs.  Inputs must already be contiguous fp32 / int32
+    CUDA tensors (p_inst is (B, n_p)).  Returns pred_pos, pred_motion, saved (opaque uint8 buffer)."""
+    _need_cuda(packed, state, attrs, action, p_inst, physics, row_ptr, send, recv)
+    B, H, N, _ = state.shape
+    n_p = p_inst.shape[1]
+    dims = make_dims(F, H, attrs.shape[2], physics.shape[1], action.shape[2], pstep)
+    g = _graph_in(state, attrs, action, p_inst, physics, row_ptr, send, recv)
+    dev = state.device
+    pred_pos = torch.empty(B, n_p, 3, dtype=torch.float32, device=dev)
+    pred_motion = torch.empty(B, n_p, 3, dtype=torch.float32, device=dev)
+    nsv = lib.agx_train_saved_bytes(C.byref(dims), B, N, int(send.numel()))
+    saved = torch.empty(nsv, dtype=torch.uint8, device=dev)
+    L.check(lib.agx_forward_train(C.byref(dims), _ptr(packed), C.byref(g), _ptr(pred_pos), n_p * 3, _ptr(pred_motion), _ptr(saved), nsv,
+                                  _stream()), "agx_forward_train")
+    return pred_pos, pred_motion, saved
+
+
+def backward(packed: Tensor, state: Tensor, attrs: Tensor, action: Tensor, p_inst: Tensor, physics: Tensor, row_ptr: Tensor,
+             send: Tensor, recv: Tensor, send_ptr: Tensor, send_perm: Tensor, saved: Tensor, pred_motion: Tensor, d_pos, d_motion,
+             grad_w: List[Tensor], grad_b: List[Tensor], d_state, F: int, pstep: int) -> None:
+    """Accumulates parameter gradients into grad_w / grad_b (reference layout, fp32, contiguous) and into d_state (nullable)."""
+    B, H, N, _ = state.shape
+    dims = make_dims(F, H, attrs.shape[2], physics.shape[1], action.shape[2], pstep)
+    g = _graph_in(state, attrs, action, p_inst, physics, row_ptr, send, recv)
+    wg = L.AgxWeightGrads()
+    for i in range(L.AGX_NUM_LAYERS):
+        wg.weight[i] = grad_w[i].data_ptr()
+        wg.bias[i] = grad_b[i].data_ptr()
+    nsc = lib.agx_train_scratch_bytes(C.byref(dims), B, N, int(send.numel()))
+    scratch = torch.empty(nsc, dtype=torch.uint8, device=state.device)
+    nul = C.c_void_p(None)
+    L.check(lib.agx_backward(C.byref(dims), _ptr(packed), C.byref(g), _ptr(saved), _ptr(send_ptr), _ptr(send_perm), _ptr(pred_motion),
+                             _ptr(d_pos) if d_pos is not None else nul, _ptr(d_motion) if d_motion is not None else nul, C.byref(wg),
+                             _ptr(d_state) if d_state is not None else nul, _ptr(scratch), nsc, _stream()), "agx_backward")

@@ -166,6 +166,25 @@ AGX_API int agx_rollout(const AgxModelDims* dims, const void* packed_weights, co
                 float* pred_seq, int32_t* n_edges_seq, int32_t* status,
                 int32_t precision, void* workspace, size_t workspace_bytes, agx_stream_t stream);
 
+/* ---- training (replaces torch autograd through model.py:129-313 in dynamics/train/train.py:90-112)
+ * agx_forward_train is agx_forward in exact fp32 that additionally keeps every activation the backward needs in the
+ * caller's `saved` buffer.  agx_backward consumes it: parameter gradients are ACCUMULATED (+=) into reference-layout
+ * tensors (null entries are skipped), d_state (B,H,N,3) is accumulated too (nullable).  send_ptr (B*N+1) / send_perm (E)
+ * list the same relations grouped by (flattened) sender, in a fixed order, so the sender-side reductions are
+ * deterministic.  pred_motion is the forward's output (needed for the clamp mask, model.py:309). */
+typedef struct AgxWeightGrads {
+  float* weight[AGX_NUM_LAYERS];
+  float* bias[AGX_NUM_LAYERS];
+} AgxWeightGrads;
+AGX_API size_t agx_train_saved_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap);
+AGX_API size_t agx_train_scratch_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap);
+AGX_API int agx_forward_train(const AgxModelDims* dims, const void* packed_weights, const AgxGraphIn* g, float* pred_pos,
+                              int64_t pos_stride_b, float* pred_motion, void* saved, size_t saved_bytes, agx_stream_t stream);
+AGX_API int agx_backward(const AgxModelDims* dims, const void* packed_weights, const AgxGraphIn* g, const void* saved,
+                         const int32_t* send_ptr, const int32_t* send_perm, const float* pred_motion, const float* d_pred_pos,
+                         const float* d_pred_motion, const AgxWeightGrads* grads, float* d_state, void* scratch,
+                         size_t scratch_bytes, agx_stream_t stream);
+
 /* ---- per-kernel timing for bench.py's roofline block.  When enabled, every kernel launched by the
  * calling thread is bracketed by CUDA events on its launch stream; agx_profile_read synchronises on
  * those events and ADDS elapsed milliseconds / launch counts per kernel kind into ms[] / count[]

@@ -204,13 +204,65 @@ def test_full_size_properties_cloth_2k(agx, precision):
     assert int(a["n_edges"].min()) > 2000 * 5 and int(a["n_edges"].max()) <= 2000 * 7 + 2 * 2 + 2002
 
 
-def test_missing_backward_fails_loudly(agx):
-    g = H.load_npz("forward_rope100_k1.npz")
-    m = _model(agx, "rope", 1).train()
+GRAD_TOL = 1e-4   # relative to the largest entry of each reference gradient (fp32 summation order differs)
+
+
+def test_training_unroll_gradients_match_reference(agx):
+    """train.py:90-112: three forwards on fixed relations with BPTT through `state`, MSE summed, one backward.
+    Loss, every parameter gradient and d(loss)/d(state) against the reference's autograd (tests/golden/train_unroll_rope40.npz)."""
+    g = H.load_npz("train_unroll_rope40.npz")
+    m = _model(agx, "rope", int(g["pstep"])).train()
     t = lambda k: torch.from_numpy(g[k]).cuda()  # noqa: E731
-    Rr, Rs = H.onehots_from_lists(g["recv"], g["send"], g["attrs"].shape[1])
-    with pytest.raises(NotImplementedError):
-        m(t("state"), t("attrs"), Rr.cuda(), Rs.cuda(), t("p_instance"), action=t("action"), rope_physics_param=t("physics_param"))
+    N = g["attrs"].shape[1]
+    Rr, Rs = H.onehots_from_lists(g["recv"], g["send"], N)
+    data = {"state": t("state").requires_grad_(True), "attrs": t("attrs"), "action": t("action"), "p_instance": t("p_instance"),
+            "Rr": Rr.cuda(), "Rs": Rs.cuda(), "rope_physics_param": t("physics_param")}
+    state_leaf = data["state"]
+    state_future, eef_future, action_future = t("state_future"), t("eef_future"), t("action_future")
+    n_future = state_future.shape[1]
+    loss_sum = 0
+    for fi in range(n_future):
+        gt = state_future[:, fi].clone()
+        pred, _ = m(**data)
+        pred_p = pred[:, :gt.shape[1], :3].clone()
+        loss_sum = loss_sum + torch.nn.functional.mse_loss(pred_p, gt)
+        if fi < n_future - 1:
+            nxt = eef_future[:, fi].clone().unsqueeze(1)
+            nxt[:, -1, :pred_p.shape[1]] = pred_p
+            data["state"] = torch.cat([data["state"][:, 1:], nxt], dim=1)
+            data["action"] = action_future[:, fi].clone()
+    loss_sum.backward()
+    assert abs(loss_sum.item() - float(g["loss"])) <= 1e-6
+    ref = g["grad_state"]
+    assert np.abs(state_leaf.grad.cpu().numpy() - ref).max() <= GRAD_TOL * max(1e-3, np.abs(ref).max())
+    for k, v in m.named_parameters():
+        ref = g["grad/" + k]
+        assert v.grad is not None, k
+        assert np.abs(v.grad.cpu().numpy() - ref).max() <= GRAD_TOL * max(1e-3, np.abs(ref).max()), k
+
+
+def test_backward_is_deterministic_and_edges_path_matches_dense_path(agx):
+    from adaptigraph_b200 import synthetic as syn
+    w = syn.make_workload("cloth", 120, 3, seed=8, n_pad=5).to("cuda")
+    m = _model(agx, "cloth", 3).train()
+    el = agx.build_edges(w.state[:, -1], w.adj_thresh, w.state_mask, w.eef_mask, w.topk, w.connect_tools_all).check()
+    Rr, Rs = el.to_dense()
+
+    def run(**kw):
+        m.zero_grad()
+        st = w.state.clone().requires_grad_(True)
+        d = w.graph_dict()
+        d["state"] = st
+        pos, mot = m(**d, **kw)
+        (pos.square().mean() + 0.1 * mot.abs().mean()).backward()
+        return st.grad.clone(), [p.grad.clone() for p in m.parameters()]
+
+    a = run(edges=el)
+    b = run(edges=el)
+    c = run(Rr=Rr, Rs=Rs)
+    assert torch.equal(a[0], b[0]) and all(torch.equal(x, y) for x, y in zip(a[1], b[1]))        # bitwise deterministic
+    assert (a[0] - c[0]).abs().max() <= 1e-6 and all((x - y).abs().max() <= 1e-5 * max(1.0, float(x.abs().max())) for x, y in zip(a[1], c[1]))
+    assert float(a[0].abs().max()) > 0 and all(float(x.abs().max()) > 0 for x in a[1])
 
 
 def test_tensor_core_path_agrees_with_fp32_path_at_scale(agx):
