@@ -1,0 +1,94 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  CPU restatement of the MPC rollout drivers
+src/planning/forward_dynamics.py:11-205 (`dynamics`) and :208-399 (`dynamics_masked`), on top of
+oracle.dynamics_oracle.rollout_dense.  Pinned by tests/test_oracle_golden.py against
+tests/golden/planning_dynamics.npz (outputs of the reference's own functions)."""
+import math
+
+import torch
+
+from . import dynamics_oracle as orc
+
+
+def decode(action, push_length):
+    """plan_utils.py:11-20"""
+    x, z, th = action[..., 0], action[..., 1], action[..., 2]
+    return torch.stack([x, z, x - push_length * torch.cos(th), z - push_length * torch.sin(th)], -1), action[..., 3].to(torch.int32)
+
+
+def _eef(pusher, ratio, dec, theta, y, gripper):
+    bsz = dec.shape[0]
+    k = len(pusher)
+    eef = torch.zeros(bsz, k, 3)
+    delta = torch.zeros(bsz, k, 3)
+    delta[:, :, 0] = (dec[:, 2] - dec[:, 0])[:, None]
+    delta[:, :, 2] = (dec[:, 3] - dec[:, 1])[:, None]
+    eef[:, :, 1] = y[:, None]
+    for i in range(k):
+        off = float(pusher[i][1]) * ratio if (k == 5 and i > 0) else 0.0          # forward_dynamics.py:64-75
+        eef[:, i, 0] = dec[:, 0] + off * torch.sin(theta)
+        eef[:, i, 2] = dec[:, 1] - off * torch.cos(theta)
+    if gripper:
+        eef[:, :, 1] += 0.01 * ratio                                                # :80-81
+    return eef, delta
+
+
+def _step_capture(p, pstep, states, attrs, p_inst, delta_full, phys, mask, eef_mask, thr, topk, cta, repeat, y_mode, raise_):
+    T = int(repeat.max())
+    out = torch.zeros(states.shape[0], p_inst.shape[1], 3)
+    if T < 1:
+        return out
+    preds, _ = orc.rollout_dense(p, pstep, states, attrs, p_inst, delta_full, phys, mask, eef_mask, thr, topk, cta, T,
+                                 y_mode=y_mode, gripper_raise=raise_)
+    for b in range(states.shape[0]):
+        if int(repeat[b]) >= 1:
+            out[b] = preds[b, int(repeat[b]) - 1]                                   # :160-161
+    return out
+
+
+def dynamics(p, pstep, state, action, cfg):
+    """cfg: dict(pusher, ratio, push_length, gripper, thr, topk, cta, n_his, phys)"""
+    bsz, n_look = action.shape[:2]
+    dec, rep = decode(action, cfg["push_length"])
+    n_obj, k = state.shape[0], len(cfg["pusher"])
+    N = n_obj + k
+    seq = torch.zeros(bsz, n_look, n_obj, 3)
+    attrs = torch.zeros(bsz, N, 2); attrs[:, :n_obj, 0] = 1; attrs[:, n_obj:, 1] = 1
+    mask = torch.ones(bsz, N, dtype=torch.bool)
+    eef_mask = torch.zeros(bsz, N, dtype=torch.bool); eef_mask[:, n_obj:] = True
+    p_inst = torch.ones(bsz, n_obj, 1)
+    phys = torch.full((bsz, 1), cfg["phys"])
+    raise_ = 0.01 * cfg["ratio"] if cfg["gripper"] else 0.0
+    for li in range(n_look):
+        obj = state[None].repeat(bsz, 1, 1) if li == 0 else seq[:, li - 1]
+        y = obj[:, :, 1].min(1).values
+        eef, delta = _eef(cfg["pusher"], cfg["ratio"], dec[:, li], action[:, li, 2], y, cfg["gripper"])
+        cur = torch.cat([obj, eef], 1)
+        states = cur[:, None].repeat(1, cfg["n_his"], 1, 1)
+        dfull = torch.zeros(bsz, N, 3); dfull[:, n_obj:] = delta
+        seq[:, li] = _step_capture(p, pstep, states, attrs, p_inst, dfull, phys, mask, eef_mask, cfg["thr"], cfg["topk"], cfg["cta"],
+                                   rep[:, li], "min", raise_)
+    return seq, dec
+
+
+def dynamics_masked(p, pstep, state, state_mask, action, cfg):
+    bsz, n_obj = state.shape[:2]
+    dec, rep = decode(action[:, None], cfg["push_length"])
+    dec, rep = dec[:, 0], rep[:, 0]
+    k = len(cfg["pusher"])
+    N = n_obj + k
+    m = state_mask.float()
+    y = (state[:, :, 1] * m).sum(1) / m.sum(1)
+    eef, delta = _eef(cfg["pusher"], cfg["ratio"], dec, action[:, 2], y, cfg["gripper"])
+    cur = torch.cat([state, eef], 1)
+    states = cur[:, None].repeat(1, cfg["n_his"], 1, 1)
+    dfull = torch.zeros(bsz, N, 3); dfull[:, n_obj:] = delta
+    attrs = torch.zeros(bsz, N, 2); attrs[:, :n_obj, 0] = m; attrs[:, n_obj:, 1] = 1
+    p_inst = torch.zeros(bsz, n_obj, 1)
+    for b in range(bsz):
+        p_inst[b, :int(state_mask[b].sum()), 0] = 1                                 # :304-310 (prefix, not the mask positions)
+    mask = torch.cat([state_mask, torch.ones(bsz, k, dtype=torch.bool)], 1)
+    eef_mask = torch.zeros(bsz, N, dtype=torch.bool); eef_mask[:, n_obj:] = True
+    phys = torch.full((bsz, 1), cfg["phys"])
+    raise_ = 0.01 * cfg["ratio"] if cfg["gripper"] else 0.0
+    return _step_capture(p, pstep, states, attrs, p_inst, dfull, phys, mask, eef_mask, cfg["thr"], cfg["topk"], cfg["cta"], rep,
+                         "masked_mean", raise_), dec

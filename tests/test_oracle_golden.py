@@ -143,3 +143,28 @@ def test_c_graph_oracle_matches_reference(name):
         for b in range(B):
             r1, s1, _ = build_oracle.edges(c["pos"][b:b + 1], c["mask"][b:b + 1], c["tool_mask"][b:b + 1], t2, int(c["topk"]), bool(c["cta"]), 1)
             assert np.array_equal(r1, c[f"single_recv_{b}"]) and np.array_equal(s1, c[f"single_send_{b}"])
+
+
+PLAN = H.load_npz("planning_dynamics.npz")
+
+
+def _plan_cfg(name):
+    from adaptigraph_b200 import synthetic as syn
+    c = {k.split("/", 1)[1]: v for k, v in PLAN.items() if k.startswith(name + "/")}
+    thr, topk, cta, _ = syn.MATERIALS[str(c["material"])]
+    cfg = dict(pusher=c["pusher"].tolist(), ratio=10.0, push_length=0.1, gripper=bool(c["gripper"]), thr=thr, topk=topk, cta=cta, n_his=4, phys=0.4)
+    return c, cfg
+
+
+@pytest.mark.parametrize("name", ["rope1pt", "granular5pt", "cloth_gripper"])
+def test_mpc_drivers_match_reference(name):
+    """forward_dynamics.py `dynamics` and `dynamics_masked` (reference outputs) vs the oracle restatement."""
+    from oracle import planning_oracle as po
+    c, cfg = _plan_cfg(name)
+    p = H.golden_weights()
+    seq, dec = po.dynamics(p, 3, torch.from_numpy(c["state"]), torch.from_numpy(c["action"]), cfg)
+    assert np.abs(dec.numpy() - c["action_seqs"]).max() <= 1e-6
+    assert np.abs(seq.numpy() - c["state_seqs"]).max() <= 2e-5
+    seq_m, dec_m = po.dynamics_masked(p, 3, torch.from_numpy(c["m_state"]), torch.from_numpy(c["m_mask"]), torch.from_numpy(c["action"][:, 0]), cfg)
+    assert np.abs(dec_m.numpy() - c["m_action_seqs"]).max() <= 1e-6
+    assert np.abs(seq_m.numpy() - c["m_state_seqs"]).max() <= 2e-5

@@ -294,3 +294,28 @@ def test_graph_build_matches_c_oracle_at_baseline_sizes(agx, material, n_p, B):
     assert E == recv.shape[0] and np.array_equal(el.n_edges.cpu().numpy(), n_edges)
     assert np.array_equal(el.send[:E].cpu().numpy(), send)
     assert np.array_equal((el.recv[:E].cpu().numpy() % w.N), recv)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", ["rope1pt", "granular5pt", "cloth_gripper"])
+def test_mpc_drivers_match_reference(agx, name, precision):
+    """Drop-in `dynamics` / `dynamics_masked` (planning/forward_dynamics.py:11-399) against the reference's own outputs:
+    1- and 5-point pushers, gripper raise, per-sample repeat counts, two look-ahead pushes, masked particles."""
+    import types
+    from adaptigraph_b200 import planning, synthetic as syn
+    PLAN = H.load_npz("planning_dynamics.npz")
+    c = {k.split("/", 1)[1]: v for k, v in PLAN.items() if k.startswith(name + "/")}
+    material = str(c["material"])
+    thr, topk, cta, _ = syn.MATERIALS[material]
+    pusher = c["pusher"].tolist()
+    ppm = types.SimpleNamespace(
+        task_config=dict(max_n=1, max_nR=1200, n_his=4, sim_real_ratio=10.0, push_length=0.1, pusher_points=pusher, gripper_enable=bool(c["gripper"]),
+                         topk=topk, connect_tools_all=cta),
+        eef_num=len(pusher), material=material, material_dims={material: 1}, material_indices={material: 0},
+        physics_param={material: torch.tensor([0.4])}, adj_thresh=thr)
+    m = _model(agx, material, 3, precision)
+    out = planning.dynamics(torch.from_numpy(c["state"]), torch.from_numpy(c["action"]), m, "cuda", ppm)
+    assert np.abs(out["action_seqs"].cpu().numpy() - c["action_seqs"]).max() <= 1e-6
+    assert np.abs(out["state_seqs"].cpu().numpy() - c["state_seqs"]).max() <= 5e-5
+    out = planning.dynamics_masked(torch.from_numpy(c["m_state"]), torch.from_numpy(c["m_mask"]), torch.from_numpy(c["action"][:, 0]), m, "cuda", ppm)
+    assert np.abs(out["state_seqs"].cpu().numpy() - c["m_state_seqs"]).max() <= 5e-5

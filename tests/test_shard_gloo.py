@@ -54,6 +54,44 @@ def test_sharded_forward_equals_whole_batch_gloo(tmp_path):
     assert res["t"] == 2.0         # max over ranks
 
 
+def _grad_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from adaptigraph_b200 import synthetic as syn
+    from adaptigraph_b200.shard import allreduce_gradients, shard_slice
+    from oracle import dynamics_oracle as orc
+    B = 4
+    w = syn.make_workload("rope", 20, B, seed=9)
+    p = {k: v.clone().requires_grad_(True) for k, v in orc.init_params(2).items()}
+
+    def loss_of(sl):
+        ww = w.take(sl)
+        Rr, Rs = orc.edges_dense_batch(ww.state[:, -1], w.adj_thresh, ww.state_mask, ww.eef_mask, w.topk, False)
+        pos, _ = orc.forward_dense(p, 2, ww.state, ww.attrs, Rr, Rs, ww.p_instance, ww.action, ww.physics_param)
+        return pos.square().mean()
+
+    loss_of(shard_slice(B, world, rank)).backward()              # every rank: its shard (the oracle stands in for the engine)
+
+    class _P:                                                     # minimal parameter-like view
+        def __init__(self, t): self.grad = t.grad
+    allreduce_gradients([_P(t) for t in p.values()])
+    if rank == 0:
+        q = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+        ww = w
+        Rr, Rs = orc.edges_dense_batch(ww.state[:, -1], w.adj_thresh, ww.state_mask, ww.eef_mask, w.topk, False)
+        pos, _ = orc.forward_dense(q, 2, ww.state, ww.attrs, Rr, Rs, ww.p_instance, ww.action, ww.physics_param)
+        pos.square().mean().backward()                            # whole batch on one rank
+        err = max(float((p[k].grad - q[k].grad).abs().max()) for k in p)
+        torch.save({"err": err}, out)
+    dist.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_equals_whole_batch_gloo(tmp_path):
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_grad_worker, args=(2, 29533, out), nprocs=2, join=True)
+    assert torch.load(out)["err"] <= 1e-6      # mean over equal shards == whole-batch mean
+
+
 def test_bench_reference_arm_under_torchrun_prints_one_line():
     env = dict(os.environ, AGX_BENCH_CPU_B="1", OMP_NUM_THREADS="4")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",

@@ -11,3 +11,4 @@ if [ $RC -ne 0 ]; then
 fi
 echo "== pytest gpu"; timeout 900 python -m pytest tests -q -m gpu --tb=short -p no:cacheprovider -x > $OUT/${TAG}_pytest.log 2>&1; echo "rc=$?"; tail -25 $OUT/${TAG}_pytest.log
 echo "== bench tc"; AGX_PRECISION=tc timeout 600 python bench.py --steps 5 --warmup 3 > $OUT/${TAG}_bench_tc.json 2> $OUT/${TAG}_bench_tc.err; echo "rc=$?"; cat $OUT/${TAG}_bench_tc.json; tail -5 $OUT/${TAG}_bench_tc.err
+echo "== bench train (cfg2)"; timeout 300 python tools/bench_train.py > $OUT/${TAG}_bench_train.json 2> $OUT/${TAG}_bench_train.err; echo "rc=$?"; cat $OUT/${TAG}_bench_train.json; tail -3 $OUT/${TAG}_bench_train.err
