@@ -237,7 +237,11 @@ __global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
           d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
           ok = (fj & 1) && !(tool_i && (fj & 2)) && (__fsub_rn(d, t2) < 0.f);
         }
-        unsigned m = __ballot_sync(FULL, ok);
+        total += __popc(__ballot_sync(FULL, ok));   // every in-radius sender counts towards min(total, topk)
+        // only senders that beat the current k-th best can enter the list (the bound only tightens while the batch is inserted)
+        const float kd = __shfl_sync(FULL, ld, topk - 1);
+        const int kj = __shfl_sync(FULL, lj, topk - 1);
+        unsigned m = __ballot_sync(FULL, ok && ((d < kd) || (d == kd && jc_mine < kj)));
         while (m) {
           const int src = __ffs(m) - 1;
           m &= m - 1;
@@ -251,7 +255,6 @@ __global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
             if (lane == at) { ld = dc; lj = jc; }
             else if (lane > at) { ld = ud; lj = uj; }
           }
-          ++total;
         }
       }
     }
