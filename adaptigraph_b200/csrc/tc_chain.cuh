@@ -13,6 +13,11 @@
 //     engine as one bulk copy per layer, double buffered, shared by both slots;
 //   * a layer is issued as two column parts (N = 96, then N = 64, same accumulator columns), each
 //     3 MMAs per 16-wide K step:  D += Alo*Whi + Ahi*Wlo + Ahi*Whi  (dropped lo*lo term: 2^-22);
+//   * biases ride in the MMA: the weight image carries bias[n] in the first padding column (k = 6 / 17 / 150) and every A row
+//     carries a 1 there, so the epilogue of a plain layer is  s = acc * 2^(e_next - e_in - sw)  followed by the split, with
+//     ReLU folded into the fp16 conversions (hi = cvt.rz.relu, lo = cvt.rn.relu of the residual);
+//   * row scales come from propagated bounds (bound_out = bound_in * max_n(sum_k |W_nk| + |b_n|)), so a plain layer needs no
+//     row maximum and no cross-warp exchange; actual row maxima are only taken where fp32 rows are stored anyway;
 //   * 8 epilogue warps per slot (thread = row = tensor-memory lane; the two warps of a 32-lane
 //     quarter split every 32-column chunk into 16-column halves) read an accumulator part with
 //     tcgen05.ld, undo the power-of-two scales exactly, apply bias / residual / ReLU and either
@@ -56,7 +61,7 @@ enum TcLayer {
 __host__ __device__ constexpr int tc_kpad(int t) { return t == T_PENC0 ? 16 : (t == T_RENC0 ? 32 : FP); }
 
 struct TcLayout {
-  size_t meta;          // byte offset of float4 meta[T_NUM] = {2^-sw, inf-norm of W, max|bias|, 0}
+  size_t meta;          // byte offset of float4 meta[T_NUM] = {2^-sw, max_n (sum_k |W_nk| + |b_n|), 0, 0}
   size_t img[T_NUM];    // byte offset of the hi image; the lo image follows at + FP*kpad*2
   size_t total;         // bytes
 };
@@ -87,8 +92,30 @@ __device__ __forceinline__ int scale_exp(float bound) {
 }
 __device__ __forceinline__ float exp2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
 
-// scale 16 fp32 values and split them into packed fp16 hi / lo columns (hi = round-to-nearest, lo = residual);
-// fp32 arithmetic on register pairs (FMUL2 / FADD2)
+// packed conversions with ReLU folded in: {lo16: cvt(a), hi16: cvt(b)}
+__device__ __forceinline__ uint32_t cvt_rz_relu_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_rn_relu_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// relu(s) split into packed fp16 hi / lo columns.  hi truncates towards zero, so the residual of a positive value is
+// non-negative and the second relu-conversion only clips what belongs to negative inputs (hi = 0, residual = s < 0).
+__device__ __forceinline__ void split16_relu(const float (&s)[HW], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t h = cvt_rz_relu_f16x2(s[2 * i], s[2 * i + 1]);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
+    const float2 l = __fadd2_rn(make_float2(s[2 * i], s[2 * i + 1]), make_float2(-hf.x, -hf.y));
+    hi[i] = h;
+    lo[i] = cvt_rn_relu_f16x2(l.x, l.y);
+  }
+}
+// signed variant for layer inputs that may be negative (hi = round-to-nearest, lo = residual)
 __device__ __forceinline__ void split16(const float (&v)[HW], float scale, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
   const float2 sc2 = make_float2(scale, scale);
 #pragma unroll
@@ -101,12 +128,12 @@ __device__ __forceinline__ void split16(const float (&v)[HW], float scale, uint3
     lo[i] = *reinterpret_cast<const uint32_t*>(&l);
   }
 }
+constexpr int ONE_COL = 150;   // A column that carries the constant 1 feeding the bias column of a 160-wide layer
 
 // ------------------------------------------------------------------------------------------------
 struct Shared {
   uint8_t* wbig[2];      // two 2*IMG_BIG weight buffers (hi image then lo image), shared by both slots
   uint8_t* wsmall;       // first-layer weights (K = 16 or 32)
-  float* bias;           // [MAX_BIAS][FP]
   float* xchg;           // [NSLOT][2][TILE] row exchange between the two column halves of a slot
   float* head_w;         // [3][FP] + [4] (head program only)
   uint64_t* bar_wsmall;
@@ -118,8 +145,7 @@ struct Shared {
   uint64_t* bar_accempty;// [NSLOT]  accumulator part read by all epilogue warps of the slot
   uint32_t* tmem_ptr;
 };
-constexpr int MAX_BIAS = 4;
-constexpr size_t SMEM_BYTES = 2 * (2 * (size_t)IMG_BIG) + 2 * (size_t)FP * 32 * 2 + MAX_BIAS * FP * 4 + NSLOT * 2 * TILE * 4 +
+constexpr size_t SMEM_BYTES = 2 * (2 * (size_t)IMG_BIG) + 2 * (size_t)FP * 32 * 2 + NSLOT * 2 * TILE * 4 +
                               (3 * FP + 4) * 4 + 16 * 8 + 16 + 128 /* alignment slack */;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit of a CTA");
 
@@ -129,7 +155,6 @@ __device__ __forceinline__ Shared carve_shared(uint8_t* raw) {
   s.wbig[0] = p; p += 2 * IMG_BIG;
   s.wbig[1] = p; p += 2 * IMG_BIG;
   s.wsmall = p; p += 2 * FP * 32 * 2;
-  s.bias = reinterpret_cast<float*>(p); p += MAX_BIAS * FP * 4;
   s.xchg = reinterpret_cast<float*>(p); p += NSLOT * 2 * TILE * 4;
   s.head_w = reinterpret_cast<float*>(p); p += (3 * FP + 4) * 4;
   uint64_t* b = reinterpret_cast<uint64_t*>(p);
@@ -151,12 +176,21 @@ __device__ __forceinline__ int cta_tile_count(int n_tiles) {
   return (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 }
 
-// Optional timeline capture (tools/tc_timeline.py builds with -DAGX_TC_TIMELINE): CTA 0's slot-0 MMA thread records stamps.
+// Optional timeline capture (tools/tc_timeline.py builds with -DAGX_TC_TIMELINE): in the edge-encoder kernel (NL == 4) CTA 0
+// records clock64 stamps of its two MMA threads (regions 0, 1), the weight loader (2) and lane 0 of epilogue warps 0 / 4 (3, 4:
+// the two column halves of slot 0).  Region r holds 800 stamps at [r * 800, ...): (id << 48) | clock.
 #ifdef AGX_TC_TIMELINE
 __device__ long long* g_tc_timeline = nullptr;
-#define AGX_STAMP(slot_id) do { if (g_tc_timeline && blockIdx.x == 0 && slot == 0 && stamp_i < 1024) g_tc_timeline[(NL == 4 ? 0 : NL == 6 ? 1024 : 2048) + stamp_i++] = ((long long)(slot_id) << 48) | (clock64() & 0xffffffffffffll); } while (0)
+__device__ __forceinline__ void tl_stamp(int region, int& i, int id) {
+  if (g_tc_timeline && blockIdx.x == 0 && i < 800) g_tc_timeline[region * 800 + i++] = ((long long)id << 48) | (clock64() & 0xffffffffffffll);
+}
+#define AGX_STAMP(id) do { if (NL == 4) tl_stamp(slot, stamp_i, id); } while (0)
+#define AGX_STAMP_LOADER(id) do { if (NL == 4) tl_stamp(2, stamp_i, id); } while (0)
+#define AGX_STAMP_EPI(cx, id) do { if ((cx).tl_region >= 0) tl_stamp((cx).tl_region, (cx).tl_i, id); } while (0)
 #else
-#define AGX_STAMP(slot_id) do { } while (0)
+#define AGX_STAMP(id) do { } while (0)
+#define AGX_STAMP_LOADER(id) do { } while (0)
+#define AGX_STAMP_EPI(cx, id) do { } while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------------ roles
@@ -176,12 +210,15 @@ __device__ __forceinline__ void loader_role(const Shared& sh, const LayerStep (&
     }
   }
   uint32_t buf = 0, empty_parity = 0x3;   // bit b = parity to wait for on bar_wempty[b] (starts at 1: free)
+  int stamp_i = 0; (void)stamp_i;
   const int rounds = (my_tiles + NSLOT - 1) / NSLOT;
   for (int round = 0; round < rounds; ++round) {
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       if (prog[l].ksteps < 10) continue;
+      AGX_STAMP_LOADER(10);
       mbar_wait(&sh.bar_wempty[buf], (empty_parity >> buf) & 1);
+      AGX_STAMP_LOADER(11);
       empty_parity ^= 1u << buf;
       mbar_arrive_expect_tx(&sh.bar_wfull[buf], 2 * IMG_BIG);
       bulk_g2s(sh.wbig[buf], blob + L.img[prog[l].layer], 2 * IMG_BIG, &sh.bar_wfull[buf]);
@@ -266,7 +303,10 @@ struct EpiCtx {
   uint32_t tslot;   // tmem_base + slot*SLOT_COLS + (lane quarter << 16)
   uint32_t acc_parity;   // parity to wait for on bar_accfull[slot] (flips after every part)
   int e_in;         // exponent of the scale applied to the current A
-  float rowmax_in;  // max |a| of the current A row (unscaled)
+  float bound_in;   // upper bound on max |a| of the current A row (unscaled; >= 1 when the row carries the bias 1)
+#ifdef AGX_TC_TIMELINE
+  int tl_region, tl_i;
+#endif
 };
 
 // all of this warp's tensor-memory stores are complete and visible to the MMA warp -> one arrival per warp
@@ -312,25 +352,67 @@ __device__ __forceinline__ void epi_release_part(const Shared& sh, const EpiCtx&
   if (cx.lane == 0) mbar_arrive(&sh.bar_accempty[cx.slot]);
 }
 
-// v = acc * unscale (+ bias) for one 16-column piece
-__device__ __forceinline__ void epi_affine(const uint32_t (&r)[HW], float unscale, const float* bias_s, int col0, float (&v)[HW]) {
-  const float2 us2 = make_float2(unscale, unscale);
+// v = acc * f for one 16-column piece
+__device__ __forceinline__ void epi_scale(const uint32_t (&r)[HW], float f, float (&v)[HW]) {
+  const float2 f2 = make_float2(f, f);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias_s) b = lds128(bias_s + col0 + 4 * i);
-    const float2 p0 = __ffma2_rn(make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), us2, make_float2(b.x, b.y));
-    const float2 p1 = __ffma2_rn(make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), us2, make_float2(b.z, b.w));
-    v[4 * i] = p0.x; v[4 * i + 1] = p0.y; v[4 * i + 2] = p1.x; v[4 * i + 3] = p1.y;
+  for (int i = 0; i < 8; ++i) {
+    const float2 p = __fmul2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), f2);
+    v[2 * i] = p.x; v[2 * i + 1] = p.y;
   }
 }
+// the thread that owns A column ONE_COL (chunk 4, upper half, element 6)
+__device__ __forceinline__ bool owns_one(const EpiCtx& cx, int c) { return c == ONE_COL / 32 && cx.half == (ONE_COL % 32) / HW; }
 
-// Layer epilogue whose result becomes the slot's next A.  per chunk: v = affine(acc) ; extra(c, col0, v) ; relu ;
-// side(c, col0, v) [e.g. store the fp32 row piece] ; split with `scale`.  Part A's packed results wait in registers until the
-// layer's last MMA (part B) has completed — only then may A be overwritten.  Returns the thread's partial row maximum.
+// Plain hidden layer: next A = relu(acc * 2^-(e_in + sw))  (the bias is already inside acc), rescaled by `scale` and split.
+// Part A's packed results wait in registers until the layer's last MMA (part B) has completed — only then may A be overwritten.
+__device__ __forceinline__ void epi_layer_plain(const Shared& sh, EpiCtx& cx, float unscale, float scale) {
+  const float f = unscale * scale;
+  uint32_t hiA[NCHUNK_A][8], loA[NCHUNK_A][8];
+  AGX_STAMP_EPI(cx, 20);
+  epi_wait_part(sh, cx);
+  AGX_STAMP_EPI(cx, 21);
+  {
+    uint32_t r[NCHUNK_A][HW];
+#pragma unroll
+    for (int c = 0; c < NCHUNK_A; ++c) tmem_ld16(cx.tslot + COL_ACC + 32 * c + HW * cx.half, r[c]);
+    tmem_wait_ld();
+    epi_release_part(sh, cx);
+    AGX_STAMP_EPI(cx, 22);
+#pragma unroll
+    for (int c = 0; c < NCHUNK_A; ++c) {
+      float v[HW];
+      epi_scale(r[c], f, v);
+      split16_relu(v, hiA[c], loA[c]);
+    }
+  }
+  AGX_STAMP_EPI(cx, 23);
+  epi_wait_part(sh, cx);   // part B complete => every MMA of the layer has read A
+  AGX_STAMP_EPI(cx, 24);
+#pragma unroll
+  for (int c = 0; c < NCHUNK_A; ++c) epi_store_packed(cx, c, hiA[c], loA[c]);
+#pragma unroll
+  for (int c = NCHUNK_A; c < NCHUNK; ++c) {
+    uint32_t r[HW];
+    tmem_ld16(cx.tslot + COL_ACC + 32 * (c - NCHUNK_A) + HW * cx.half, r);
+    tmem_wait_ld();
+    if (c == NCHUNK - 1) epi_release_part(sh, cx);
+    float v[HW];
+    epi_scale(r, f, v);
+    if (owns_one(cx, c)) v[ONE_COL % HW] = scale;   // the 1 that multiplies the next layer's bias column
+    uint32_t hi[8], lo[8];
+    split16_relu(v, hi, lo);
+    epi_store_packed(cx, c, hi, lo);
+  }
+  AGX_STAMP_EPI(cx, 25);
+  epi_signal(cx, &sh.bar_a[cx.slot]);
+  AGX_STAMP_EPI(cx, 26);
+}
+
+// General layer whose result becomes the slot's next A.  per chunk: v = acc * unscale ; extra(c, col0, v) ; relu ;
+// side(c, col0, v) [e.g. store the fp32 row piece] ; split with `scale`.  Returns the thread's partial row maximum.
 template <class Extra, class Side>
-__device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, float unscale, const float* bias_s, float scale, Extra extra,
-                                                Side side) {
+__device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, float unscale, float scale, Extra extra, Side side) {
   float mx = 0.f;
   uint32_t hiA[NCHUNK_A][8], loA[NCHUNK_A][8];
   epi_wait_part(sh, cx);
@@ -344,7 +426,7 @@ __device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, fl
     for (int c = 0; c < NCHUNK_A; ++c) {
       const int col0 = 32 * c + HW * cx.half;
       float v[HW];
-      epi_affine(r[c], unscale, bias_s, col0, v);
+      epi_scale(r[c], unscale, v);
       extra(c, col0, v);
 #pragma unroll
       for (int i = 0; i < HW; ++i) { v[i] = fmaxf(v[i], 0.f); mx = fmaxf(mx, v[i]); }
@@ -363,11 +445,12 @@ __device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, fl
     tmem_wait_ld();
     if (c == NCHUNK - 1) epi_release_part(sh, cx);
     float v[HW];
-    epi_affine(r, unscale, bias_s, col0, v);
+    epi_scale(r, unscale, v);
     extra(c, col0, v);
 #pragma unroll
     for (int i = 0; i < HW; ++i) { v[i] = fmaxf(v[i], 0.f); mx = fmaxf(mx, v[i]); }
     side(c, col0, v);
+    if (owns_one(cx, c)) v[ONE_COL % HW] = 1.f;   // after the fp32 side store: only the tensor-memory copy carries the 1
     epi_store_a(cx, c, v, scale);
   }
   epi_signal(cx, &sh.bar_a[cx.slot]);
@@ -375,9 +458,9 @@ __device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, fl
 }
 
 // Layer epilogue that only consumes the result (fp32 rows to HBM, running dot products ...): per chunk
-// v = affine(acc) ; [relu] ; consume(c, col0, v).  A is left untouched.
+// v = acc * unscale ; [relu] ; consume(c, col0, v).  A is left untouched.
 template <bool RELU, class Consume>
-__device__ __forceinline__ void epi_layer_out(const Shared& sh, EpiCtx& cx, float unscale, const float* bias_s, Consume consume) {
+__device__ __forceinline__ void epi_layer_out(const Shared& sh, EpiCtx& cx, float unscale, Consume consume) {
 #pragma unroll
   for (int part = 0; part < 2; ++part) {
     epi_wait_part(sh, cx);
@@ -390,7 +473,7 @@ __device__ __forceinline__ void epi_layer_out(const Shared& sh, EpiCtx& cx, floa
       tmem_wait_ld();
       if (c == c1 - 1) epi_release_part(sh, cx);
       float v[HW];
-      epi_affine(r, unscale, bias_s, col0, v);
+      epi_scale(r, unscale, v);
       if (RELU) {
 #pragma unroll
         for (int i = 0; i < HW; ++i) v[i] = fmaxf(v[i], 0.f);

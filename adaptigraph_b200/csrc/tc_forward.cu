@@ -20,12 +20,13 @@ struct PackArgs {
 };
 
 __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
-  __shared__ float red_w[8], red_s[8], red_b[8];
+  __shared__ float red_w[8], red_s[8];
   __shared__ float sw_s;
   const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const PackSpec s = a.spec[t];
   const int kpad = tc_kpad(t);
-  float wmax = 0.f, smax = 0.f, bmax = 0.f;
+  // the bias occupies the first padding column (k = K): it is multiplied by the constant 1 every A row carries there
+  float wmax = 0.f, smax = 0.f;
   for (int n = tid; n < s.F; n += 256) {
     float rs = 0.f;
     for (int k = 0; k < s.K; ++k) {
@@ -33,23 +34,23 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
       wmax = fmaxf(wmax, w);
       rs += w;
     }
+    if (s.bias) { const float b = fabsf(s.bias[n]); wmax = fmaxf(wmax, b); rs += b; }
     smax = fmaxf(smax, rs);
-    if (s.bias) bmax = fmaxf(bmax, fabsf(s.bias[n]));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
     smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
-    bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
   }
-  if (lane == 0) { red_w[warp] = wmax; red_s[warp] = smax; red_b[warp] = bmax; }
+  if (lane == 0) { red_w[warp] = wmax; red_s[warp] = smax; }
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < 8; ++w) { red_w[0] = fmaxf(red_w[0], red_w[w]); red_s[0] = fmaxf(red_s[0], red_s[w]); red_b[0] = fmaxf(red_b[0], red_b[w]); }
+    for (int w = 1; w < 8; ++w) { red_w[0] = fmaxf(red_w[0], red_w[w]); red_s[0] = fmaxf(red_s[0], red_s[w]); }
     const int sw = scale_exp(red_w[0]);
     sw_s = exp2i(sw);
     float4* meta = reinterpret_cast<float4*>(a.blob + a.L.meta);
-    meta[t] = make_float4(exp2i(-sw), red_s[0] * 1.0001f, red_b[0], 0.f);   // inf-norm padded for fp32 summation slack
+    // {2^-sw, max_n (sum_k |W_nk| + |b_n|) padded for fp32 summation slack, -, -}
+    meta[t] = make_float4(exp2i(-sw), red_s[0] * 1.0001f, 0.f, 0.f);
   }
   __syncthreads();
   const float sc = sw_s;
@@ -57,7 +58,11 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
   uint8_t* lo_img = hi_img + (size_t)FP * kpad * 2;
   for (int i = tid; i < FP * kpad; i += 256) {
     const int n = i / kpad, k = i - n * kpad;
-    const float v = (n < s.F && k < s.K) ? s.W[(size_t)n * s.ld + s.col0 + k] * sc : 0.f;
+    float v = 0.f;
+    if (n < s.F) {
+      if (k < s.K) v = s.W[(size_t)n * s.ld + s.col0 + k] * sc;
+      else if (k == s.K && s.bias) v = s.bias[n] * sc;
+    }
     const __half h = __float2half_rn(v);
     const __half l = __float2half_rn(v - __half2float(h));
     const uint32_t off = img_offset(n, k, kpad);
@@ -69,7 +74,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
 // ------------------------------------------------------------------------------------ common kernel prologue / epilogue
 template <int NL>
 __device__ __forceinline__ uint32_t chain_setup(Shared& sh, uint8_t* smem_raw, const LayerStep (&prog)[NL], const uint8_t* blob,
-                                                const TcLayout& L, const float* const (&bias_src)[MAX_BIAS], float4 (&meta)[NL]) {
+                                                const TcLayout& L, float4 (&meta)[NL]) {
   sh = carve_shared(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
@@ -82,8 +87,6 @@ __device__ __forceinline__ uint32_t chain_setup(Shared& sh, uint8_t* smem_raw, c
     fence_mbar_init();
   }
   if (warp == MMA_WARP0) tmem_alloc(sh.tmem_ptr, TMEM_COLS);
-  for (int b = 0; b < MAX_BIAS; ++b)
-    for (int i = tid; i < FP; i += THREADS) sh.bias[b * FP + i] = bias_src[b] ? bias_src[b][i] : 0.f;
   const float4* m = reinterpret_cast<const float4*>(blob + L.meta);
 #pragma unroll
   for (int l = 0; l < NL; ++l) meta[l] = m[prog[l].layer];
@@ -113,7 +116,11 @@ __device__ __forceinline__ EpiCtx make_ctx(uint32_t tmem_base) {
   cx.tslot = tmem_base + cx.slot * SLOT_COLS + ((uint32_t)((w & 3) * 32) << 16);
   cx.acc_parity = 0;
   cx.e_in = 0;
-  cx.rowmax_in = 0.f;
+  cx.bound_in = 1.f;
+#ifdef AGX_TC_TIMELINE
+  cx.tl_region = -1;
+  cx.tl_i = 0;
+#endif
   return cx;
 }
 
@@ -130,24 +137,20 @@ __device__ __forceinline__ void stg16(float* p, const float (&v)[HW]) {
 struct NoExtra { __device__ void operator()(int, int, float (&)[HW]) const {} };
 struct NoSide { __device__ void operator()(int, int, const float (&)[HW]) const {} };
 
-// relu(bias + acc) -> the slot's next A; updates the row scale bookkeeping
-template <class Side>
-__device__ __forceinline__ float epi_relu_to_a(const Shared& sh, EpiCtx& cx, const float4 meta_l, const float* bias_s, Side side) {
-  const int e_next = scale_exp(cx.rowmax_in * meta_l.y + meta_l.z);
-  const float unscale = exp2i(-cx.e_in) * meta_l.x;
-  float mx = epi_layer_to_a(sh, cx, unscale, bias_s, exp2i(e_next), NoExtra{}, side);
-  mx = epi_exchange<true>(sh, cx, mx);
-  cx.rowmax_in = mx;
+// plain hidden layer (bias inside the MMA): relu(acc) -> the slot's next A; the row bound is propagated, no row maximum needed
+__device__ __forceinline__ void epi_hidden(const Shared& sh, EpiCtx& cx, const float4 meta_l) {
+  const float bound_next = fmaxf(cx.bound_in * meta_l.y, 1.f);
+  const int e_next = scale_exp(bound_next);
+  epi_layer_plain(sh, cx, exp2i(-cx.e_in) * meta_l.x, exp2i(e_next));
+  cx.bound_in = bound_next;
   cx.e_in = e_next;
-  return mx;
 }
 
-// bias + acc -> fp32 rows in HBM (A is left untouched); returns this thread's partial max |v|
-__device__ __forceinline__ float epi_store_rows(const Shared& sh, EpiCtx& cx, const float4 meta_l, const float* bias_s, float* out,
-                                                int64_t grow, bool valid) {
+// acc (bias inside the MMA) -> fp32 rows in HBM (A is left untouched); returns this thread's partial max |v|
+__device__ __forceinline__ float epi_store_rows(const Shared& sh, EpiCtx& cx, const float4 meta_l, float* out, int64_t grow, bool valid) {
   const float unscale = exp2i(-cx.e_in) * meta_l.x;
   float mx = 0.f;
-  epi_layer_out<false>(sh, cx, unscale, bias_s, [&](int, int col0, float (&v)[HW]) {
+  epi_layer_out<false>(sh, cx, unscale, [&](int, int col0, float (&v)[HW]) {
     mx = max16(v, mx);
     if (valid) stg16(out + grow * FP + col0, v);
   });
@@ -166,7 +169,6 @@ struct EdgeArgs {
   int64_t rows; int N; int64_t E_cap;
   const float* nfeat;
   const uint8_t* blob; TcLayout L;
-  const float* bias[MAX_BIAS];
   float* C;
 };
 
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
   constexpr LayerStep prog[4] = {{T_RENC0, 2, IN_PRODUCER}, {T_RENC2, 10, IN_EPILOGUE}, {T_RENC4, 10, IN_EPILOGUE}, {T_RP_REL, 10, IN_EPILOGUE}};
   Shared sh;
   float4 meta[4];
-  const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, a.bias, meta);
+  const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, meta);
   const int64_t E = min((int64_t)a.row_ptr[a.rows], a.E_cap);
   const int n_tiles = (int)((E + TILE - 1) / TILE);
   const int warp = threadIdx.x >> 5;
@@ -207,25 +209,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
   } else {
     reg_alloc_epilogue();
     EpiCtx cx = make_ctx(tmem_base);
+#ifdef AGX_TC_TIMELINE
+    if (cx.lane == 0 && (cx.warp == 0 || cx.warp == 4)) cx.tl_region = 3 + cx.warp / 4;
+#endif
     int tile = slot_tile(0, cx.slot, n_tiles);
     for (int k = 0; tile >= 0; ++k) {
       const int64_t e = (int64_t)tile * TILE + cx.row;
+      AGX_STAMP_EPI(cx, 30);
       // ---- input producer: the slot's A is free (the previous tile's last layer has been read out); the gather
       // latency is covered by the other slot's MMAs
       {
         float vin[HW];
         edge_inputs(a, e, E, cx.half, vin);
-        const float mx = epi_exchange<true>(sh, cx, max16(vin, 0.f));
+        const float mx = fmaxf(epi_exchange<true>(sh, cx, max16(vin, 0.f)), 1.f);
+        if (cx.half == 1) vin[1] = 1.f;   // input 17: the constant that multiplies the bias column of relation_encoder.model.0
         cx.e_in = scale_exp(mx);
-        cx.rowmax_in = mx;
+        cx.bound_in = mx;
         epi_store_a(cx, 0, vin, exp2i(cx.e_in));
         epi_signal(cx, &sh.bar_in[cx.slot]);
       }
+      AGX_STAMP_EPI(cx, 31);
       const int next = slot_tile(k + 1, cx.slot, n_tiles);
-      epi_relu_to_a(sh, cx, meta[0], sh.bias + 0 * FP, NoSide{});
-      epi_relu_to_a(sh, cx, meta[1], sh.bias + 1 * FP, NoSide{});
-      epi_relu_to_a(sh, cx, meta[2], sh.bias + 2 * FP, NoSide{});
-      epi_store_rows(sh, cx, meta[3], sh.bias + 3 * FP, a.C, e, e < E);
+      epi_hidden(sh, cx, meta[0]);
+      epi_hidden(sh, cx, meta[1]);
+      epi_hidden(sh, cx, meta[2]);
+      AGX_STAMP_EPI(cx, 32);
+      epi_store_rows(sh, cx, meta[3], a.C, e, e < E);
+      AGX_STAMP_EPI(cx, 33);
       tile = next;
     }
   }
@@ -237,7 +247,6 @@ struct NodeArgs {
   const float* state; const float* attrs; const float* action; const float* p_instance; const float* physics;
   int B, N, n_p;
   const uint8_t* blob; TcLayout L;
-  const float* bias[MAX_BIAS];
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* rowmaxP; float* rowmaxA;
 };
 
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
                                  {T_PP_ENC, 10, IN_EPILOGUE}, {T_RP_RECV, 10, IN_SAME}, {T_RP_SEND, 10, IN_SAME}};
   Shared sh;
   float4 meta[6];
-  const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, a.bias, meta);
+  const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, meta);
   const int64_t rows = (int64_t)a.B * a.N;
   const int n_tiles = (int)((rows + TILE - 1) / TILE);
   const int warp = threadIdx.x >> 5;
@@ -289,24 +298,32 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
       const bool valid = r < rows;
       float in[HW];
       node_inputs(a, r, rows, cx.half, in);
-      const float mx = epi_exchange<true>(sh, cx, max16(in, 0.f));
+      const float mx = fmaxf(epi_exchange<true>(sh, cx, max16(in, 0.f)), 1.f);
+      if (cx.half == 0) in[6] = 1.f;      // input 6: the constant that multiplies the bias column of particle_encoder.model.0
       cx.e_in = scale_exp(mx);
-      cx.rowmax_in = mx;
+      cx.bound_in = mx;
       if (cx.half == 0) epi_store_a(cx, 0, in, exp2i(cx.e_in));   // the K=16 layer reads A columns 0..7 only
       epi_signal(cx, &sh.bar_in[cx.slot]);
 
-      epi_relu_to_a(sh, cx, meta[0], sh.bias + 0 * FP, NoSide{});
-      epi_relu_to_a(sh, cx, meta[1], sh.bias + 1 * FP, NoSide{});
-      // particle_encode = particle_effect_0 (model.py:268-269): next A and P rows
-      const float pm = epi_relu_to_a(sh, cx, meta[2], sh.bias + 2 * FP, [&](int, int col0, const float (&v)[HW]) {
-        if (valid) stg16(a.P + r * FP + col0, v);
-      });
-      if (valid && cx.half == 0) a.rowmaxP[r] = pm;
-      float am = epi_store_rows(sh, cx, meta[3], sh.bias + 3 * FP, a.A, r, valid);   // A_n = W_enc*penc + b
+      epi_hidden(sh, cx, meta[0]);
+      epi_hidden(sh, cx, meta[1]);
+      {  // particle_encode = particle_effect_0 (model.py:268-269): next A and the fp32 P rows (with their row maximum)
+        const float4 m = meta[2];
+        const float bound_next = fmaxf(cx.bound_in * m.y, 1.f);
+        const int e_next = scale_exp(bound_next);
+        float pm = epi_layer_to_a(sh, cx, exp2i(-cx.e_in) * m.x, exp2i(e_next), NoExtra{}, [&](int, int col0, const float (&v)[HW]) {
+          if (valid) stg16(a.P + r * FP + col0, v);
+        });
+        pm = epi_exchange<true>(sh, cx, pm);
+        cx.bound_in = bound_next;
+        cx.e_in = e_next;
+        if (valid && cx.half == 0) a.rowmaxP[r] = pm;
+      }
+      float am = epi_store_rows(sh, cx, meta[3], a.A, r, valid);   // A_n = W_enc*penc + b
       am = epi_exchange<true>(sh, cx, am);
       if (valid && cx.half == 0) a.rowmaxA[r] = am;
-      epi_store_rows(sh, cx, meta[4], nullptr, a.Qr, r, valid);
-      epi_store_rows(sh, cx, meta[5], nullptr, a.Qs, r, valid);
+      epi_store_rows(sh, cx, meta[4], a.Qr, r, valid);
+      epi_store_rows(sh, cx, meta[5], a.Qs, r, valid);
       tile = slot_tile(k + 1, cx.slot, n_tiles);
     }
   }
@@ -320,7 +337,6 @@ struct UpdArgs {
   const int32_t* agg_exp; const float* agg_max;   // per-row scale exponent / row maximum of agg
   const float* A; float* P; float* Qr; float* Qs; float* rowmaxP; const float* rowmaxA;
   const uint8_t* blob; TcLayout L;
-  const float* bias[MAX_BIAS];
   const float* head_w;   // fp32 [3][FP] then 4 bias floats (head only)
   const float* state; float* pred_pos; int64_t pos_stride_b; float* pred_motion;
 };
@@ -332,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
                                  {LAST ? T_PRED1 : T_RP_SEND, 10, LAST ? IN_EPILOGUE : IN_SAME}};
   Shared sh;
   float4 meta[3];
-  const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, a.bias, meta);
+  const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, meta);
   if (LAST) {
     for (int i = threadIdx.x; i < 3 * FP + 4; i += THREADS) sh.head_w[i] = a.head_w[i];
     __syncthreads();
@@ -364,17 +380,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
           epi_store_packed(cx, c, hi, lo);
         }
         cx.e_in = valid ? a.agg_exp[r] : 0;
-        cx.rowmax_in = valid ? a.agg_max[r] : 0.f;
+        cx.bound_in = valid ? a.agg_max[r] : 0.f;     // actual row maximum (W_agg has no bias: no constant column needed)
         epi_signal(cx, &sh.bar_in[cx.slot]);
       }
       {  // P <- relu((W_agg*agg + A_n) + P)   (model.py:36-40, :299-301)
         const float4 m = meta[0];
         const float extra_bound = valid ? a.rowmaxA[r] + a.rowmaxP[r] : 0.f;   // bound on |A_n + P| of this row
-        const int e_next = scale_exp(cx.rowmax_in * m.y + extra_bound);
+        const float bound_next = fmaxf(cx.bound_in * m.y + extra_bound, 1.f);
+        const int e_next = scale_exp(bound_next);
         const float unscale = exp2i(-cx.e_in) * m.x;
         const float* a_row = a.A + r * FP;
         float* p_row = a.P + r * FP;
-        float pm = epi_layer_to_a(sh, cx, unscale, nullptr, exp2i(e_next),
+        float pm = epi_layer_to_a(sh, cx, unscale, exp2i(e_next),
                                   [&](int, int col0, float (&v)[HW]) {
                                     if (valid) {
                                       float t[8];
@@ -393,19 +410,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
                                     if (!LAST && valid) stg16(p_row + col0, v);
                                   });
         pm = epi_exchange<true>(sh, cx, pm);
-        cx.rowmax_in = pm;
+        cx.bound_in = fmaxf(pm, 1.f);                  // actual maximum of the new P row (tighter than the propagated bound)
         cx.e_in = e_next;
         if (!LAST && valid && cx.half == 0) a.rowmaxP[r] = pm;
       }
       if (!LAST) {
-        epi_store_rows(sh, cx, meta[1], nullptr, a.Qr, r, valid);
-        epi_store_rows(sh, cx, meta[2], nullptr, a.Qs, r, valid);
+        epi_store_rows(sh, cx, meta[1], a.Qr, r, valid);
+        epi_store_rows(sh, cx, meta[2], a.Qs, r, valid);
       } else {
-        epi_relu_to_a(sh, cx, meta[1], sh.bias + 0 * FP, NoSide{});
+        epi_hidden(sh, cx, meta[1]);
         // motion head (model.py:306-309): relu(linear_1) then the 3-row linear_2 as running dot products
         const float unscale = exp2i(-cx.e_in) * meta[2].x;
         float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-        epi_layer_out<true>(sh, cx, unscale, sh.bias + 1 * FP, [&](int, int col0, float (&v)[HW]) {
+        epi_layer_out<true>(sh, cx, unscale, [&](int, int col0, float (&v)[HW]) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             const float4 w0 = lds128(sh.head_w + col0 + 4 * h), w1 = lds128(sh.head_w + FP + col0 + 4 * h),
@@ -506,7 +523,8 @@ int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_
   using namespace tc;
   const int F = dims->F;
   const int d_node = dims->d_attr + dims->d_phys + dims->d_act, d_rel = 2 * dims->d_attr + 1 + 3 * dims->n_his;
-  AGX_REQUIRE(d_node <= tc_kpad(T_PENC0) && d_rel <= tc_kpad(T_RENC0), AGX_ERR_ARG, "tc_pack: input dims exceed the padded K");
+  // the kernels place the bias constants at fixed A columns (6 / 17 / ONE_COL)
+  AGX_REQUIRE(d_node == 6 && d_rel == 17 && F == ONE_COL, AGX_ERR_ARG, "tc_pack: the tensor-core path is built for 6/17/150 input dims");
   PackArgs a;
   auto set = [&](int t, int layer, int ld, int col0, int K, bool bias) {
     a.spec[t] = PackSpec{raw->weight[layer], bias ? raw->bias[layer] : nullptr, ld, col0, K, F};
@@ -556,7 +574,6 @@ int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
   const int tiles = (int)((rows + TILE - 1) / TILE);
   NodeArgs a{g->state, g->attrs, g->action, g->p_instance, g->physics, g->B, g->N, g->n_p,
              reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
-             {wts + PL.penc0_b, wts + PL.penc2_b, wts + PL.penc4_b, wts + PL.pp_b},
              w.nfeat, w.P, w.A, w.Qr, w.Qs, w.rowmaxP, w.rowmaxA};
   { ProfScope ps(AGX_KIND_NODE_ENCODER, st);
     tc_node_encoder_kernel<<<tiles < num_sms() ? tiles : num_sms(), THREADS, SMEM_BYTES, st>>>(a); }
@@ -570,7 +587,7 @@ int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
   const int64_t rows = (int64_t)g->B * g->N;
   const int64_t tiles = (g->E_cap + TILE - 1) / TILE;
   EdgeArgs a{g->row_ptr, g->send, g->recv, rows, g->N, g->E_cap, w.nfeat, reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
-             {wts + PL.renc0_b, wts + PL.renc2_b, wts + PL.renc4_b, wts + PL.rp_b}, w.C};
+             w.C};
   { ProfScope ps(AGX_KIND_EDGE_ENCODER, st);
     tc_edge_encoder_kernel<<<(int)(tiles < num_sms() ? tiles : num_sms()), THREADS, SMEM_BYTES, st>>>(a); }
   AGX_LAUNCH_CHECK();
@@ -597,7 +614,6 @@ int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL
   const int grid = tiles < num_sms() ? tiles : num_sms();
   UpdArgs a{g->B, g->N, g->n_p, reinterpret_cast<const uint32_t*>(w.agg), w.agg_exp, w.agg_max, w.A, w.P, w.Qr, w.Qs, w.rowmaxP, w.rowmaxA,
             reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
-            {wts + PL.pred0_b, wts + PL.pred1_b, nullptr, nullptr},
             wts + PL.pred2_w, g->state, pred_pos, pos_stride_b, pred_motion};
   if (last) {
     ProfScope ps(AGX_KIND_NODE_HEAD, st);

@@ -2,8 +2,10 @@
 
     python tools/tc_timeline.py build      # here (no GPU): builds adaptigraph_b200/libagx_timeline.so
     AGX_LIB=adaptigraph_b200/libagx_timeline.so python tools/tc_timeline.py run   # on the GPU box
-Slots: 1 layer start, 2 weights ready, 3 part-A accumulator free, 4 first A chunk ready, 5 last A chunk ready,
-7 part-A issued+committed, 6 part-B accumulator free, 8 part-B issued+committed.
+Columns: the two MMA threads, the weight loader, lane 0 of epilogue warps 0 and 4 (slot 0's two column halves).
+MMA: L layer start, w weights ready, eA part-A accumulator free, in A ready, A! part A issued, eB part-B accumulator free, B! issued.
+Loader: lw waiting for a free buffer, le got it (copy issued).  Epilogue: T tile start, pr producer done, l layer start,
+fA part A full, rA read+released, mA part-A math done, fB part B full, sB stores issued, sg signalled, o/O last layer begin/end.
 """
 import ctypes as C
 import os
@@ -30,21 +32,23 @@ el = agx.build_edges(w.state[:, -1], w.adj_thresh, w.state_mask, w.eef_mask, w.t
 with torch.no_grad():
     m(**w.graph_dict(), edges=el)
     torch.cuda.synchronize()
-    buf = torch.zeros(4096, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(4000, dtype=torch.int64, device="cuda")
     assert L.lib.agx_debug_set_timeline(C.c_void_p(buf.data_ptr())) == 0
     m(**w.graph_dict(), edges=el)
     torch.cuda.synchronize()
     L.lib.agx_debug_set_timeline(None)
-for name, base in (("edge_encoder", 0), ("node_encoder", 1024), ("node_update/head (last launched)", 2048)):
-    st = [(s >> 48, s & 0xffffffffffff) for s in buf[base:base + 1024].cpu().tolist() if s]
-    print("==", name, "stamps", len(st))
-    if not st:
-        continue
-    t0 = prev = st[0][1]
-    line = []
-    for slot, t in st[:260]:
-        if slot == 1 and line:
-            print(" ".join(line)); line = []
-        line.append(f"{slot}:{t - t0}(+{t - prev})")
-        prev = t
-    print(" ".join(line))
+names = {1: "L", 2: "w", 3: "eA", 4: "in", 7: "A!", 6: "eB", 8: "B!", 10: "lw", 11: "le", 20: "l", 21: "fA", 22: "rA", 23: "mA",
+         24: "fB", 25: "sB", 26: "sg", 30: "T", 31: "pr", 32: "o", 33: "O"}
+ev = []
+t0 = None
+for region, rname in enumerate(("mma0", "mma1", "load", "epi0", "epi4")):
+    for s in buf[region * 800:(region + 1) * 800].cpu().tolist():
+        if s:
+            ev.append((s & 0xffffffffffff, rname, names.get(s >> 48, str(s >> 48))))
+ev.sort()
+t0 = ev[0][0]
+skip = [e for e in ev if e[0] - t0 > 60000]      # steady state: skip the first rounds
+cols = ("mma0", "mma1", "load", "epi0", "epi4")
+print("clk      " + "".join(f"{c:>8s}" for c in cols))
+for t, r, n in skip[:700]:
+    print(f"{t - t0:8d} " + "".join(f"{(n if c == r else ''):>8s}" for c in cols))
