@@ -417,12 +417,14 @@ static size_t fwd_ws_carve(void* base, int64_t rows, int64_t E_cap, FwdWs* out) 
   Carver c(base);
   FwdWs w;
   w.nfeat = c.take<float>((size_t)rows * NFEAT);
-  w.P = c.take<float>((size_t)rows * FP);
-  w.A = c.take<float>((size_t)rows * FP);
-  w.Qr = c.take<float>((size_t)rows * FP);
-  w.Qs = c.take<float>((size_t)rows * FP);
-  w.agg = c.take<float>((size_t)rows * FP);
-  w.C = c.take<float>((size_t)(E_cap > 0 ? E_cap : 1) * FP);
+  // padded to whole 128-row tiles: the tensor-core path keeps these matrices tile-blocked (tc_chain.cuh: blk_off)
+  const size_t rows_pad = (size_t)((rows + 127) / 128 * 128), e_pad = (size_t)(((E_cap > 0 ? E_cap : 1) + 127) / 128 * 128);
+  w.P = c.take<float>(rows_pad * FP);
+  w.A = c.take<float>(rows_pad * FP);
+  w.Qr = c.take<float>(rows_pad * FP);
+  w.Qs = c.take<float>(rows_pad * FP);
+  w.agg = c.take<float>(rows_pad * FP);
+  w.C = c.take<float>(e_pad * FP);
   w.rowmaxP = c.take<float>((size_t)rows);
   w.rowmaxA = c.take<float>((size_t)rows);
   w.agg_exp = c.take<int32_t>((size_t)rows);

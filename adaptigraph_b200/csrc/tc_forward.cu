@@ -72,6 +72,10 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
 }
 
 // ------------------------------------------------------------------------------------ common kernel prologue / epilogue
+#ifdef AGX_TC_STAGGER
+// experiment: CTA i starts (i % 4) * g_tc_stagger clocks late so that the SMs' memory phases do not line up
+__device__ int g_tc_stagger = 0;
+#endif
 template <int NL>
 __device__ __forceinline__ uint32_t chain_setup(Shared& sh, uint8_t* smem_raw, const LayerStep (&prog)[NL], const uint8_t* blob,
                                                 const TcLayout& L, float4 (&meta)[NL]) {
@@ -90,6 +94,12 @@ __device__ __forceinline__ uint32_t chain_setup(Shared& sh, uint8_t* smem_raw, c
   const float4* m = reinterpret_cast<const float4*>(blob + L.meta);
 #pragma unroll
   for (int l = 0; l < NL; ++l) meta[l] = m[prog[l].layer];
+#ifdef AGX_TC_STAGGER
+  if (tid == 0 && g_tc_stagger > 0) {
+    const long long t0 = clock64(), d = (long long)(blockIdx.x & 3) * g_tc_stagger;
+    while (clock64() - t0 < d) __nanosleep(200);
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -147,13 +157,15 @@ __device__ __forceinline__ void epi_hidden(const Shared& sh, EpiCtx& cx, const f
 }
 
 // acc (bias inside the MMA) -> fp32 rows in HBM (A is left untouched); returns this thread's partial max |v|
-__device__ __forceinline__ float epi_store_rows(const Shared& sh, EpiCtx& cx, const float4 meta_l, float* out, int64_t grow, bool valid) {
+template <class AllRead = NoHook>
+__device__ __forceinline__ float epi_store_rows(const Shared& sh, EpiCtx& cx, const float4 meta_l, float* out, int64_t grow, bool valid,
+                                                AllRead all_read = AllRead{}) {
   const float unscale = exp2i(-cx.e_in) * meta_l.x;
   float mx = 0.f;
   epi_layer_out<false>(sh, cx, unscale, [&](int, int col0, float (&v)[HW]) {
     mx = max16(v, mx);
-    if (valid) stg16(out + grow * FP + col0, v);
-  });
+    if (valid) stg16(out + blk_off(grow, col0), v);
+  }, all_read);
   return mx;
 }
 
@@ -204,38 +216,45 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
   const int warp = threadIdx.x >> 5;
   if (warp >= EPI_WARPS) {
     reg_dealloc_other();
-    if (warp == LOAD_WARP) loader_role(sh, prog, a.blob, a.L, n_tiles);
-    else if (warp < LOAD_WARP) mma_role(sh, prog, warp - MMA_WARP0, tmem_base, n_tiles);
+    if (warp == LOAD_WARP) loader_role(sh, prog, a.blob, a.L, n_tiles, 4);
+    else if (warp < LOAD_WARP) mma_role(sh, prog, warp - MMA_WARP0, tmem_base, n_tiles, 4);
   } else {
     reg_alloc_epilogue();
     EpiCtx cx = make_ctx(tmem_base);
 #ifdef AGX_TC_TIMELINE
-    if (cx.lane == 0 && (cx.warp == 0 || cx.warp == 4)) cx.tl_region = 3 + cx.warp / 4;
+    if ((4) == AGX_TC_TIMELINE && cx.lane == 0 && (cx.warp == 0 || cx.warp == 4)) cx.tl_region = 3 + cx.warp / 4;
 #endif
+    // The input of a tile is gathered, scaled and split into registers while the previous tile's last layer is still in the
+    // tensor pipe, and committed to the slot's A the moment that layer's MMAs have read it.
+    uint32_t in_hi[8], in_lo[8];
+    int in_exp = 0;
+    float in_bound = 1.f;
+    auto produce = [&](int tile) {
+      float vin[HW];
+      edge_inputs(a, (int64_t)tile * TILE + cx.row, E, cx.half, vin);
+      in_bound = fmaxf(epi_exchange<true>(sh, cx, max16(vin, 0.f)), 1.f);
+      if (cx.half == 1) vin[1] = 1.f;   // input 17: the constant that multiplies the bias column of relation_encoder.model.0
+      in_exp = scale_exp(in_bound);
+      split16(vin, exp2i(in_exp), in_hi, in_lo);
+    };
+    auto commit = [&]() {
+      epi_store_packed(cx, 0, in_hi, in_lo);
+      epi_signal(cx, &sh.bar_in[cx.slot]);
+    };
     int tile = slot_tile(0, cx.slot, n_tiles);
+    if (tile >= 0) { produce(tile); commit(); }
     for (int k = 0; tile >= 0; ++k) {
       const int64_t e = (int64_t)tile * TILE + cx.row;
       AGX_STAMP_EPI(cx, 30);
-      // ---- input producer: the slot's A is free (the previous tile's last layer has been read out); the gather
-      // latency is covered by the other slot's MMAs
-      {
-        float vin[HW];
-        edge_inputs(a, e, E, cx.half, vin);
-        const float mx = fmaxf(epi_exchange<true>(sh, cx, max16(vin, 0.f)), 1.f);
-        if (cx.half == 1) vin[1] = 1.f;   // input 17: the constant that multiplies the bias column of relation_encoder.model.0
-        cx.e_in = scale_exp(mx);
-        cx.bound_in = mx;
-        epi_store_a(cx, 0, vin, exp2i(cx.e_in));
-        epi_signal(cx, &sh.bar_in[cx.slot]);
-      }
-      AGX_STAMP_EPI(cx, 31);
+      cx.e_in = in_exp;
+      cx.bound_in = in_bound;
       const int next = slot_tile(k + 1, cx.slot, n_tiles);
       epi_hidden(sh, cx, meta[0]);
       epi_hidden(sh, cx, meta[1]);
       epi_hidden(sh, cx, meta[2]);
-      AGX_STAMP_EPI(cx, 32);
-      epi_store_rows(sh, cx, meta[3], a.C, e, e < E);
-      AGX_STAMP_EPI(cx, 33);
+      AGX_STAMP_EPI(cx, 31);
+      if (next >= 0) produce(next);
+      epi_store_rows(sh, cx, meta[3], a.C, e, e < E, [&]() { if (next >= 0) commit(); });
       tile = next;
     }
   }
@@ -287,11 +306,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
   const int warp = threadIdx.x >> 5;
   if (warp >= EPI_WARPS) {
     reg_dealloc_other();
-    if (warp == LOAD_WARP) loader_role(sh, prog, a.blob, a.L, n_tiles);
-    else if (warp < LOAD_WARP) mma_role(sh, prog, warp - MMA_WARP0, tmem_base, n_tiles);
+    if (warp == LOAD_WARP) loader_role(sh, prog, a.blob, a.L, n_tiles, 6);
+    else if (warp < LOAD_WARP) mma_role(sh, prog, warp - MMA_WARP0, tmem_base, n_tiles, 6);
   } else {
     reg_alloc_epilogue();
     EpiCtx cx = make_ctx(tmem_base);
+#ifdef AGX_TC_TIMELINE
+    if ((6) == AGX_TC_TIMELINE && cx.lane == 0 && (cx.warp == 0 || cx.warp == 4)) cx.tl_region = 3 + cx.warp / 4;
+#endif
     int tile = slot_tile(0, cx.slot, n_tiles);
     for (int k = 0; tile >= 0; ++k) {
       const int64_t r = (int64_t)tile * TILE + cx.row;
@@ -312,7 +334,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
         const float bound_next = fmaxf(cx.bound_in * m.y, 1.f);
         const int e_next = scale_exp(bound_next);
         float pm = epi_layer_to_a(sh, cx, exp2i(-cx.e_in) * m.x, exp2i(e_next), NoExtra{}, [&](int, int col0, const float (&v)[HW]) {
-          if (valid) stg16(a.P + r * FP + col0, v);
+          if (valid) stg16(a.P + blk_off(r, col0), v);
         });
         pm = epi_exchange<true>(sh, cx, pm);
         cx.bound_in = bound_next;
@@ -333,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
 // ------------------------------------------------------------------------------------ node update / head
 struct UpdArgs {
   int B, N, n_p;
-  const uint32_t* agg_split;   // [rows][FP] : 80 packed-fp16 hi columns then 80 lo columns per row (edge_aggregate, split output)
+  const uint32_t* agg_split;   // blocked; per (row, 16-column piece) 8 packed-fp16 hi words then 8 lo words (edge_aggregate, split output)
   const int32_t* agg_exp; const float* agg_max;   // per-row scale exponent / row maximum of agg
   const float* A; float* P; float* Qr; float* Qs; float* rowmaxP; const float* rowmaxA;
   const uint8_t* blob; TcLayout L;
@@ -358,24 +380,34 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
   const int warp = threadIdx.x >> 5;
   if (warp >= EPI_WARPS) {
     reg_dealloc_other();
-    if (warp == LOAD_WARP) loader_role(sh, prog, a.blob, a.L, n_tiles);
-    else if (warp < LOAD_WARP) mma_role(sh, prog, warp - MMA_WARP0, tmem_base, n_tiles);
+    if (warp == LOAD_WARP) loader_role(sh, prog, a.blob, a.L, n_tiles, LAST ? 13 : 3);
+    else if (warp < LOAD_WARP) mma_role(sh, prog, warp - MMA_WARP0, tmem_base, n_tiles, LAST ? 13 : 3);
   } else {
     reg_alloc_epilogue();
     EpiCtx cx = make_ctx(tmem_base);
+#ifdef AGX_TC_TIMELINE
+    if ((LAST ? 13 : 3) == AGX_TC_TIMELINE && cx.lane == 0 && (cx.warp == 0 || cx.warp == 4)) cx.tl_region = 3 + cx.warp / 4;
+#endif
     int tile = slot_tile(0, cx.slot, n_tiles);
     for (int k = 0; tile >= 0; ++k) {
       const int64_t r = (int64_t)tile * TILE + cx.row;
       const bool valid = r < rows;
+      const int next = slot_tile(k + 1, cx.slot, n_tiles);
+      AGX_STAMP_EPI(cx, 30);
+      if (cx.warp % SLOT_WARPS == 0 && cx.lane == 0) {
+        // the residual rows of this tile are read by the first layer's epilogue: start them towards L2 now
+        bulk_prefetch_l2(a.A + (int64_t)tile * TILE * FP, TILE * FP * 4);   // (buffers are padded to whole tiles)
+        bulk_prefetch_l2(a.P + (int64_t)tile * TILE * FP, TILE * FP * 4);
+      }
       // ---- producer: the aggregated relation effects arrive already scaled and split (edge_aggregate): copy to A
       {
-        const uint32_t* row = a.agg_split + r * FP;
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
           uint32_t hi[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lo[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          if (valid) {
-            ldg256(reinterpret_cast<const float*>(row + 16 * c + 8 * cx.half), reinterpret_cast<float(&)[8]>(hi));
-            ldg256(reinterpret_cast<const float*>(row + 80 + 16 * c + 8 * cx.half), reinterpret_cast<float(&)[8]>(lo));
+          if (valid) {   // 16 words per (row, piece): 8 hi then 8 lo
+            const uint32_t* piece = a.agg_split + blk_off(r, 32 * c + HW * cx.half);
+            ldg256(reinterpret_cast<const float*>(piece), reinterpret_cast<float(&)[8]>(hi));
+            ldg256(reinterpret_cast<const float*>(piece + 8), reinterpret_cast<float(&)[8]>(lo));
           }
           epi_store_packed(cx, c, hi, lo);
         }
@@ -383,37 +415,40 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
         cx.bound_in = valid ? a.agg_max[r] : 0.f;     // actual row maximum (W_agg has no bias: no constant column needed)
         epi_signal(cx, &sh.bar_in[cx.slot]);
       }
+      AGX_STAMP_EPI(cx, 31);
       {  // P <- relu((W_agg*agg + A_n) + P)   (model.py:36-40, :299-301)
         const float4 m = meta[0];
         const float extra_bound = valid ? a.rowmaxA[r] + a.rowmaxP[r] : 0.f;   // bound on |A_n + P| of this row
         const float bound_next = fmaxf(cx.bound_in * m.y + extra_bound, 1.f);
         const int e_next = scale_exp(bound_next);
         const float unscale = exp2i(-cx.e_in) * m.x;
-        const float* a_row = a.A + r * FP;
-        float* p_row = a.P + r * FP;
+        const float* a_row = a.A + blk_off(r, 0);      // + (col0 / 16) * TILE * 16 selects the piece
+        float* p_row = a.P + blk_off(r, 0);
         float pm = epi_layer_to_a(sh, cx, unscale, exp2i(e_next),
                                   [&](int, int col0, float (&v)[HW]) {
                                     if (valid) {
                                       float t[8];
 #pragma unroll
                                       for (int h = 0; h < 2; ++h) {
-                                        ldg256(a_row + col0 + 8 * h, t);
+                                        ldg256(a_row + (col0 >> 4) * (TILE * BLK_W) + 8 * h, t);
 #pragma unroll
                                         for (int i = 0; i < 8; ++i) v[8 * h + i] += t[i];
-                                        ldg256(p_row + col0 + 8 * h, t);
+                                        ldg256(p_row + (col0 >> 4) * (TILE * BLK_W) + 8 * h, t);
 #pragma unroll
                                         for (int i = 0; i < 8; ++i) v[8 * h + i] += t[i];
                                       }
                                     }
                                   },
                                   [&](int, int col0, const float (&v)[HW]) {
-                                    if (!LAST && valid) stg16(p_row + col0, v);
+                                    if (!LAST && valid) stg16(p_row + (col0 >> 4) * (TILE * BLK_W), v);
                                   });
         pm = epi_exchange<true>(sh, cx, pm);
         cx.bound_in = fmaxf(pm, 1.f);                  // actual maximum of the new P row (tighter than the propagated bound)
         cx.e_in = e_next;
         if (!LAST && valid && cx.half == 0) a.rowmaxP[r] = pm;
       }
+      if (next >= 0 && cx.warp % SLOT_WARPS == 0 && cx.lane == 0)   // the next tile's input rows: two layers of lead time
+        bulk_prefetch_l2(a.agg_split + (int64_t)next * TILE * FP, TILE * FP * 4);
       if (!LAST) {
         epi_store_rows(sh, cx, meta[1], a.Qr, r, valid);
         epi_store_rows(sh, cx, meta[2], a.Qs, r, valid);
@@ -449,7 +484,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
           }
         }
       }
-      tile = slot_tile(k + 1, cx.slot, n_tiles);
+      tile = next;
     }
   }
   chain_teardown(tmem_base);
@@ -480,19 +515,21 @@ __global__ void __launch_bounds__(AGG_THREADS) edge_aggregate_split_kernel(
     const int64_t beg = row_ptr[r];
     const int64_t end = min((int64_t)row_ptr[r + 1], E_cap);
     const int64_t gb = (r / N) * N;
-    const float4 qr = Qr[r * (FP / 4) + j];
+    // float4 j of a row in the blocked layout (tc_chain.cuh: blk_off)
+    auto at = [j](const float4* m, int64_t row) { return m[blk_off(row, 4 * j) >> 2]; };
+    const float4 qr = at(Qr, r);
     int64_t e = beg;
     for (; e + 1 < end; e += 2) {
       const int64_t s0 = gb + send[e], s1 = gb + send[e + 1];
-      const float4 c0 = C[e * (FP / 4) + j], c1 = C[(e + 1) * (FP / 4) + j];
-      const float4 q0 = Qs[s0 * (FP / 4) + j], q1 = Qs[s1 * (FP / 4) + j];
+      const float4 c0 = at(C, e), c1 = at(C, e + 1);
+      const float4 q0 = at(Qs, s0), q1 = at(Qs, s1);
       const float4 v0 = relu_add3(c0, qr, q0), v1 = relu_add3(c1, qr, q1);
       acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
       acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
     }
     if (e < end) {
       const int64_t s0 = gb + send[e];
-      const float4 v0 = relu_add3(C[e * (FP / 4) + j], qr, Qs[s0 * (FP / 4) + j]);
+      const float4 v0 = relu_add3(at(C, e), qr, at(Qs, s0));
       acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
     }
     // agg >= 0 (sum of ReLUs): the int view of the floats orders like the floats
@@ -507,9 +544,10 @@ __global__ void __launch_bounds__(AGG_THREADS) edge_aggregate_split_kernel(
     const __half2 h0 = __float22half2_rn(s0), h1 = __float22half2_rn(s1);
     const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
     const __half2 l0 = __float22half2_rn(make_float2(s0.x - f0.x, s0.y - f0.y)), l1 = __float22half2_rn(make_float2(s1.x - f1.x, s1.y - f1.y));
-    uint32_t* row = agg_split + r * FP;
-    *reinterpret_cast<uint2*>(row + 2 * j) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-    *reinterpret_cast<uint2*>(row + 80 + 2 * j) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    // the 16 words of (row, piece = 16 columns): 8 packed hi pairs then 8 packed lo pairs
+    uint32_t* piece = agg_split + blk_off(r, 16 * (j >> 2));
+    *reinterpret_cast<uint2*>(piece + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(piece + 8 + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
     if (j == 0) { agg_exp[r] = e; agg_max[r] = mx; }
   }
 }
@@ -559,6 +597,12 @@ static int tc_ensure_attrs() {
   static thread_local bool done = false;
   if (done) return AGX_OK;
   using namespace tc;
+#ifdef AGX_TC_STAGGER
+  if (const char* e = getenv("AGX_TC_STAGGER")) {
+    const int v = atoi(e);
+    AGX_CUDA_OK(cudaMemcpyToSymbol(g_tc_stagger, &v, sizeof(v)));
+  }
+#endif
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_edge_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));

@@ -47,6 +47,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// asynchronous prefetch of a contiguous range into L2 (no destination: later loads of the range hit L2); bytes % 16 == 0
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------- tensor memory
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {  // warp-collective
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");

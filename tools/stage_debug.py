@@ -62,17 +62,27 @@ def main(fname="forward_cloth64_pad_k3.npz", precision=0):
         off += n
         return out
     nfeat = take(rows * 16).view(rows, 16)
-    P = take(rows * 160).view(rows, 160)[:, :150]
-    A = take(rows * 160).view(rows, 160)[:, :150]
-    Qr = take(rows * 160).view(rows, 160)[:, :150]
-    Qs = take(rows * 160).view(rows, 160)[:, :150]
-    agg_raw = take(rows * 160).view(rows, 160)
-    Cb = take(max(E, 1) * 160).view(max(E, 1), 160)[:E, :150]
+    pad = lambda n: (n + 127) // 128 * 128      # the matrices are padded to whole 128-row tiles
+
+    def matrix(n):
+        """[n][160] matrix: row-major in the fp32 path, [tile][piece of 16 columns][row in tile][16] in the tensor-core path."""
+        raw = take(pad(n) * 160)
+        if precision == 1:
+            return raw.view(pad(n) // 128, 10, 128, 16).permute(0, 2, 1, 3).reshape(pad(n), 160)[:n]
+        return raw.view(pad(n), 160)[:n]
+    P = matrix(rows)[:, :150]
+    A = matrix(rows)[:, :150]
+    Qr = matrix(rows)[:, :150]
+    Qs = matrix(rows)[:, :150]
+    agg_raw = matrix(rows)
+    Cb = matrix(max(E, 1))[:E, :150]
     take(rows); take(rows)                      # rowmaxP, rowmaxA
     agg_exp = take(rows).view(torch.int32)
-    if precision == 1:                          # tensor-core path: agg rows are stored scaled and split (80 packed hi + 80 packed lo columns)
-        halves = agg_raw.contiguous().view(torch.float16).view(rows, 320).float()
-        aggb = ((halves[:, :160] + halves[:, 160:]) * torch.exp2(-agg_exp.float())[:, None])[:, :150]
+    if precision == 1:                          # tensor-core path: every 16-word piece holds 8 packed fp16 hi pairs then 8 lo pairs
+        words = agg_raw.contiguous().view(rows, 10, 16)
+        hi = words[:, :, :8].contiguous().view(torch.float16).view(rows, 160).float()
+        lo = words[:, :, 8:].contiguous().view(torch.float16).view(rows, 160).float()
+        aggb = ((hi + lo) * torch.exp2(-agg_exp.float())[:, None])[:, :150]
     else:
         aggb = agg_raw[:, :150]
 

@@ -1,7 +1,7 @@
 """Timeline of CTA 0's MMA-issuing thread in tc_edge_encoder_kernel (debug library with -DAGX_TC_TIMELINE).
 
-    python tools/tc_timeline.py build      # here (no GPU): builds adaptigraph_b200/libagx_timeline.so
-    AGX_LIB=adaptigraph_b200/libagx_timeline.so python tools/tc_timeline.py run   # on the GPU box
+    python tools/tc_timeline.py build edge|node|update|head    # here (no GPU): builds adaptigraph_b200/libagx_timeline_<k>.so
+    AGX_LIB=adaptigraph_b200/libagx_timeline_edge.so python tools/tc_timeline.py run   # on the GPU box
 Columns: the two MMA threads, the weight loader, lane 0 of epilogue warps 0 and 4 (slot 0's two column halves).
 MMA: L layer start, w weights ready, eA part-A accumulator free, in A ready, A! part A issued, eB part-B accumulator free, B! issued.
 Loader: lw waiting for a free buffer, le got it (copy issued).  Epilogue: T tile start, pr producer done, l layer start,
@@ -15,16 +15,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 DBG = os.path.join(ROOT, "adaptigraph_b200", "libagx_timeline.so")
 
-if sys.argv[1:] == ["build"]:
+KIDS = {"edge": 4, "node": 6, "update": 3, "head": 13}
+if sys.argv[1:2] == ["build"]:
     from adaptigraph_b200 import build
-    print(build.build(force=True, defines=["AGX_TC_TIMELINE"], out=DBG))
+    which = sys.argv[2] if len(sys.argv) > 2 else "edge"
+    print(build.build(force=True, defines=[f"AGX_TC_TIMELINE={KIDS[which]}"], out=DBG.replace(".so", f"_{which}.so")))
     sys.exit(0)
 
 import torch  # noqa: E402
 import adaptigraph_b200 as agx  # noqa: E402
 from adaptigraph_b200 import _lib as L, synthetic as syn  # noqa: E402
 
-which = sys.argv[2] if len(sys.argv) > 2 else "edge"
 L.lib.agx_debug_set_timeline.argtypes = [C.c_void_p]
 w = syn.make_workload("cloth", 2000, 128, seed=1238).to("cuda")
 m = agx.DynamicsPredictor(*syn.configs("cloth", 3), "cuda").cuda().eval()
@@ -38,7 +39,8 @@ with torch.no_grad():
     torch.cuda.synchronize()
     L.lib.agx_debug_set_timeline(None)
 names = {1: "L", 2: "w", 3: "eA", 4: "in", 7: "A!", 6: "eB", 8: "B!", 10: "lw", 11: "le", 20: "l", 21: "fA", 22: "rA", 23: "mA",
-         24: "fB", 25: "sB", 26: "sg", 30: "T", 31: "pr", 32: "o", 33: "O"}
+         24: "fB", 25: "sB", 26: "sg", 30: "T", 31: "pr", 32: "o", 33: "O", 34: "ofA", 35: "orA", 36: "ocA", 37: "ofB", 38: "orB",
+         40: "r", 41: "rfA", 43: "rmA", 44: "rfB", 45: "rsB"}
 ev = []
 t0 = None
 for region, rname in enumerate(("mma0", "mma1", "load", "epi0", "epi4")):
@@ -47,7 +49,7 @@ for region, rname in enumerate(("mma0", "mma1", "load", "epi0", "epi4")):
             ev.append((s & 0xffffffffffff, rname, names.get(s >> 48, str(s >> 48))))
 ev.sort()
 t0 = ev[0][0]
-skip = [e for e in ev if e[0] - t0 > 60000]      # steady state: skip the first rounds
+skip = [e for e in ev if e[0] - t0 > int(os.environ.get("TL_SKIP", "60000"))]      # steady state: skip the first rounds
 cols = ("mma0", "mma1", "load", "epi0", "epi4")
 print("clk      " + "".join(f"{c:>8s}" for c in cols))
 for t, r, n in skip[:700]:
