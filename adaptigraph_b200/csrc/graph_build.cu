@@ -6,13 +6,14 @@
 // B x n_rel x N one-hots; here nothing quadratic ever reaches HBM:
 //
 //   G0 tool_list     (only with connect_tools_all) ascending list of tool particles per graph
-//   G0b sort_axis    per graph: pick the coordinate axis with the largest extent and sort the particles
-//                    along it (bitonic sort in shared memory); emits the permuted SoA copy of the graph
-//   G1 knn_rows      one warp per receiver: only senders whose sorted coordinate lies within the radius
-//                    of the receiver's can be in range, so the warp binary-searches that window and
-//                    streams it from shared memory (each CTA stages just the slot range its 64
-//                    receivers need); the k nearest in-radius senders live in a warp-resident sorted
-//                    list (one entry per lane), then are bitonic-sorted by sender id -> <= k candidates
+//   G0b sort_cells   per graph: lay a uniform grid of cells no narrower than the radius over the two coordinate
+//                    axes of largest extent, sort the particles by cell id (bitonic sort in shared memory), emit
+//                    the permuted SoA copy of the graph and the first slot of every cell
+//   G1 knn_rows      one warp per receiver: a sender in range lies in the receiver's cell or one of its 8
+//                    neighbours, i.e. in three contiguous slot runs (cells b-1..b+1 of grid rows a-1..a+1), which
+//                    the warp streams from shared memory (each CTA stages just the grid rows its 64 receivers
+//                    can reach); the k nearest in-radius senders live in a warp-resident sorted list (one
+//                    entry per lane), then are bitonic-sorted by sender id -> <= k candidates
 //   G2 degrees_scan  per-row relation count after the tool rules (:134-144 / :77-80) + block scan
 //   G2b scan_blocks  scan of the block sums -> row offsets, total
 //   G3 fill_rows     one thread per receiver merges candidates and tool senders in ascending sender order
@@ -29,6 +30,8 @@ constexpr int G1_THREADS = 256;
 constexpr int G1_ROWS_PER_CTA = 64;
 constexpr int SCAN_BLOCK = 1024;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int GRID_MAX_AXIS = 64;                                  // cells per grid axis (cells widen beyond the radius past that)
+constexpr int GRID_MAX_CELLS = GRID_MAX_AXIS * GRID_MAX_AXIS;
 
 struct GraphWs {
   int32_t* cand;       // [B*N][topk]
@@ -40,9 +43,12 @@ struct GraphWs {
   int32_t* flags;      // [B]     probe: some tool receiver kept a non-tool sender (graph.py:135)
   int32_t* n_tools;    // [B]
   int32_t* tools;      // [B*N]
-  float* sx; float* sy; float* sz; float* skey;   // [B*N] particles permuted into sorted order (SoA)
+  float* sx; float* sy; float* sz;   // [B*N] particles permuted into sorted order (SoA)
+  int32_t* scell;      // [B*N] cell id of each sorted slot
   int32_t* sidx;       // [B*N] original particle id of each sorted slot
   uint8_t* sflag;      // [B*N] bit0 valid, bit1 tool
+  int32_t* cell_start; // [B][GRID_MAX_CELLS + 1] first sorted slot of every cell (entries past the graph's cell count = N)
+  int32_t* grid_dims;  // [B][2] cells along the two grid axes (a = slow, b = fast)
 };
 
 static size_t graph_ws_carve(void* base, int B, int N, int topk, GraphWs* ws) {
@@ -59,9 +65,12 @@ static size_t graph_ws_carve(void* base, int B, int N, int topk, GraphWs* ws) {
   w.flags = c.take<int32_t>(B);
   w.n_tools = c.take<int32_t>(B);
   w.tools = c.take<int32_t>(rows);
-  w.sx = c.take<float>(rows); w.sy = c.take<float>(rows); w.sz = c.take<float>(rows); w.skey = c.take<float>(rows);
+  w.sx = c.take<float>(rows); w.sy = c.take<float>(rows); w.sz = c.take<float>(rows);
+  w.scell = c.take<int32_t>(rows);
   w.sidx = c.take<int32_t>(rows);
   w.sflag = c.take<uint8_t>(rows);
+  w.cell_start = c.take<int32_t>((size_t)B * (GRID_MAX_CELLS + 1));
+  w.grid_dims = c.take<int32_t>((size_t)B * 2);
   if (ws) *ws = w;
   return align_up(c.off, 256);
 }
@@ -96,22 +105,33 @@ __global__ void __launch_bounds__(256) tool_list_kernel(const uint8_t* __restric
 }
 
 // ------------------------------------------------------------------------------------ G0b
-// One CTA per graph.  Sort key = coordinate along the axis of largest extent, ties by particle id.
-__global__ void __launch_bounds__(1024) sort_axis_kernel(const float* __restrict__ pos, int64_t pos_stride_b,
-                                                          const uint8_t* __restrict__ mask, const uint8_t* __restrict__ tool_mask,
-                                                          int N, int NP2, float* __restrict__ sx, float* __restrict__ sy,
-                                                          float* __restrict__ sz, float* __restrict__ skey, int32_t* __restrict__ sidx,
-                                                          uint8_t* __restrict__ sflag) {
-  extern __shared__ float smem[];
-  float* key = smem;
-  int32_t* val = reinterpret_cast<int32_t*>(smem + NP2);
+// One CTA per graph.  Grid over the two axes of largest extent of the valid particles; cell width >= the radius (with slack
+// for the fp32 rounding of the reference's distance and of the cell coordinate itself), so that two particles within the
+// radius differ by at most one cell along each axis.  Sort key = cell id (a * nb + b), ties by particle id.
+__device__ __forceinline__ int cell_coord(float x, float lo, float w, int n) {
+  const float u = __fdiv_rn(__fsub_rn(x, lo), w);
+  return min(max((int)fminf(fmaxf(u, 0.f), (float)GRID_MAX_AXIS), 0), n - 1);   // NaN -> 0
+}
+
+__global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restrict__ pos, int64_t pos_stride_b,
+                                                           const uint8_t* __restrict__ mask, const uint8_t* __restrict__ tool_mask,
+                                                           const float* __restrict__ thr2, int N, int NP2, float* __restrict__ sx,
+                                                           float* __restrict__ sy, float* __restrict__ sz, int32_t* __restrict__ scell,
+                                                           int32_t* __restrict__ sidx, uint8_t* __restrict__ sflag,
+                                                           int32_t* __restrict__ cell_start, int32_t* __restrict__ grid_dims) {
+  extern __shared__ int32_t smem_i[];
+  int32_t* key = smem_i;
+  int32_t* val = smem_i + NP2;
   __shared__ float red[6][32];
-  __shared__ int axis_s;
+  __shared__ float lo_s[2], w_s[2];
+  __shared__ int axis_s[2], n_s[2];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* p = pos + (size_t)b * pos_stride_b;
+  const uint8_t* mk = mask + (size_t)b * N;
   const float INF = __int_as_float(0x7f800000);
   float mn[3] = {INF, INF, INF}, mx[3] = {-INF, -INF, -INF};
   for (int j = tid; j < N; j += 1024) {
+    if (!mk[j]) continue;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const float v = p[3 * j + a];
@@ -130,18 +150,36 @@ __global__ void __launch_bounds__(1024) sort_axis_kernel(const float* __restrict
   }
   __syncthreads();
   if (tid == 0) {
-    float ext[3];
+    float ext[3], lo3[3], amax = 0.f;
     for (int a = 0; a < 3; ++a) {
       float lo = INF, hi = -INF;
       for (int w = 0; w < 32; ++w) { lo = fminf(lo, red[a][w]); hi = fmaxf(hi, red[3 + a][w]); }
-      ext[a] = hi - lo;
+      const bool ok = lo <= hi && hi < INF && lo > -INF;   // no valid particle, or non-finite coordinates: a single cell on this axis
+      ext[a] = ok ? hi - lo : 0.f;
+      lo3[a] = ok ? lo : 0.f;
+      if (ok) amax = fmaxf(amax, fmaxf(fabsf(lo), fabsf(hi)));
     }
-    axis_s = (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[1] >= ext[2] ? 1 : 2);
+    const int a0 = (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[1] >= ext[2] ? 1 : 2);
+    const int r1 = (a0 + 1) % 3, r2 = (a0 + 2) % 3;
+    const int a1 = ext[r1] >= ext[r2] ? r1 : r2;
+    // every sender with (dis - thr^2) < 0 has |x_i - x_j| <= sqrt(thr^2) up to fp32 rounding: widen by 0.1 % + coordinate ulps
+    const float hw = sqrtf(fmaxf(thr2[b], 0.f)) * 1.001f + amax * 1e-6f + 1e-30f;
+    const int ax[2] = {a0, a1};
+    for (int g = 0; g < 2; ++g) {
+      const float e = ext[ax[g]];
+      const float w = fmaxf(hw, e * (1.0001f / GRID_MAX_AXIS));
+      const float cells = floorf(e / w) + 1.f;                       // <= GRID_MAX_AXIS by construction
+      axis_s[g] = ax[g]; lo_s[g] = lo3[ax[g]]; w_s[g] = w;
+      n_s[g] = !(cells >= 1.f) ? 1 : (cells > (float)GRID_MAX_AXIS ? GRID_MAX_AXIS : (int)cells);
+    }
+    grid_dims[2 * b] = n_s[0];
+    grid_dims[2 * b + 1] = n_s[1];
   }
   __syncthreads();
-  const int axis = axis_s;
+  const int axa = axis_s[0], axb = axis_s[1], na = n_s[0], nb = n_s[1];
+  const float loa = lo_s[0], lob = lo_s[1], wa = w_s[0], wb = w_s[1];
   for (int j = tid; j < NP2; j += 1024) {
-    key[j] = j < N ? p[3 * j + axis] : INF;
+    key[j] = j < N ? cell_coord(p[3 * j + axa], loa, wa, na) * nb + cell_coord(p[3 * j + axb], lob, wb, nb) : 0x7fffffff;
     val[j] = j;
   }
   __syncthreads();
@@ -151,7 +189,7 @@ __global__ void __launch_bounds__(1024) sort_axis_kernel(const float* __restrict
         const int lo = 2 * t - (t & (stride - 1));   // index with the `stride` bit clear
         const int hi = lo + stride;
         const bool up = (lo & size) == 0;
-        const float ka = key[lo], kb = key[hi];
+        const int ka = key[lo], kb = key[hi];
         const int va = val[lo], vb = val[hi];
         const bool a_gt_b = (ka > kb) || (ka == kb && va > vb);
         if (a_gt_b == up) { key[lo] = kb; key[hi] = ka; val[lo] = vb; val[hi] = va; }
@@ -159,57 +197,49 @@ __global__ void __launch_bounds__(1024) sort_axis_kernel(const float* __restrict
       __syncthreads();
     }
   }
-  for (int s = tid; s < N; s += 1024) {
-    const int j = val[s];
-    const size_t o = (size_t)b * N + s;
-    sx[o] = p[3 * j + 0]; sy[o] = p[3 * j + 1]; sz[o] = p[3 * j + 2];
-    skey[o] = key[s];
-    sidx[o] = j;
-    sflag[o] = (mask[(size_t)b * N + j] ? 1 : 0) | (tool_mask[(size_t)b * N + j] ? 2 : 0);
+  int32_t* cs = cell_start + (size_t)b * (GRID_MAX_CELLS + 1);
+  const int n_cells = na * nb;
+  for (int s = tid; s <= N; s += 1024) {
+    // cells (key[s-1], key[s]] start at slot s; slot N closes every remaining cell
+    const int c_prev = s > 0 ? key[s - 1] : -1;
+    const int c_here = s < N ? key[s] : n_cells;
+    for (int c = c_prev + 1; c <= c_here; ++c) cs[c] = s;
+    if (s < N) {
+      const int j = val[s];
+      const size_t o = (size_t)b * N + s;
+      sx[o] = p[3 * j + 0]; sy[o] = p[3 * j + 1]; sz[o] = p[3 * j + 2];
+      scell[o] = c_here;
+      sidx[o] = j;
+      sflag[o] = (mk[j] ? 1 : 0) | (tool_mask[(size_t)b * N + j] ? 2 : 0);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------ G1
-// first slot in [lo, hi) whose key is >= x (lower_bound) / > x (upper_bound); `key` may be global or shared
-__device__ __forceinline__ int lower_bound_f(const float* key, int lo, int hi, float x) {
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (key[mid] < x) lo = mid + 1; else hi = mid; }
-  return lo;
-}
-__device__ __forceinline__ int upper_bound_f(const float* key, int lo, int hi, float x) {
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (key[mid] <= x) lo = mid + 1; else hi = mid; }
-  return lo;
-}
-// conservative half-width of the window along the sort axis: every sender with (dis - thr^2) < 0 has
-// |x_i - x_j| <= sqrt(thr^2); the slack covers the fp32 rounding of the window bounds themselves
-__device__ __forceinline__ float window_halfwidth(float thr2, float x) { return sqrtf(fmaxf(thr2, 0.f)) * 1.001f + fabsf(x) * 2.4e-7f + 1e-30f; }
-
 __global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
-    const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sz, const float* __restrict__ skey,
-    const int32_t* __restrict__ sidx, const uint8_t* __restrict__ sflag, const float* __restrict__ thr2, int N, int topk,
+    const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sz, const int32_t* __restrict__ scell,
+    const int32_t* __restrict__ sidx, const uint8_t* __restrict__ sflag, const int32_t* __restrict__ cell_start,
+    const int32_t* __restrict__ grid_dims, const float* __restrict__ thr2, int N, int topk,
     int probe_tools, int smem_cap, int32_t* __restrict__ cand, int32_t* __restrict__ cnt_out, int32_t* __restrict__ flags) {
   extern __shared__ float smem[];
-  __shared__ int range_s[2];
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t gb = (size_t)b * N;
   const float t2 = thr2[b];
+  const int na = grid_dims[2 * b], nb = grid_dims[2 * b + 1];
+  const int32_t* cs = cell_start + (size_t)b * (GRID_MAX_CELLS + 1);
   const int s_beg = blockIdx.x * G1_ROWS_PER_CTA, s_end = min(N, s_beg + G1_ROWS_PER_CTA);
-  if (tid == 0) {   // slot range this CTA's receivers can reach
-    const float k0 = skey[gb + s_beg], k1 = skey[gb + s_end - 1];
-    range_s[0] = lower_bound_f(skey + gb, 0, s_beg, k0 - window_halfwidth(t2, k0));
-    range_s[1] = upper_bound_f(skey + gb, s_end, N, k1 + window_halfwidth(t2, k1));
-  }
-  __syncthreads();
-  const int r_lo = range_s[0], r_hi = range_s[1], M = r_hi - r_lo;
+  // slot range this CTA's receivers can reach: whole grid rows a_first - 1 .. a_last + 1
+  const int a_first = scell[gb + s_beg] / nb, a_last = scell[gb + s_end - 1] / nb;
+  const int r_lo = cs[max(a_first - 1, 0) * nb], r_hi = cs[(min(a_last + 1, na - 1) + 1) * nb], M = r_hi - r_lo;
   if (M > smem_cap) __trap();   // host sizes shared memory for the whole graph, so this cannot happen
   float* px = smem;
   float* py = px + M;
   float* pz = py + M;
-  float* pk = pz + M;
-  int32_t* pj = reinterpret_cast<int32_t*>(pk + M);
+  int32_t* pj = reinterpret_cast<int32_t*>(pz + M);
   uint8_t* fl = reinterpret_cast<uint8_t*>(pj + M);
   for (int s = tid; s < M; s += G1_THREADS) {
     const size_t o = gb + r_lo + s;
-    px[s] = sx[o]; py[s] = sy[o]; pz[s] = sz[o]; pk[s] = skey[o]; pj[s] = sidx[o]; fl[s] = sflag[o];
+    px[s] = sx[o]; py[s] = sy[o]; pz[s] = sz[o]; pj[s] = sidx[o]; fl[s] = sflag[o];
   }
   __syncthreads();
 
@@ -221,10 +251,17 @@ __global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
     int lj = 0x7fffffff;
     int total = 0;
     if (fi & 1) {
-      const float xi = px[li], yi = py[li], zi = pz[li], ki = pk[li];
+      const float xi = px[li], yi = py[li], zi = pz[li];
       const bool tool_i = fi & 2;
-      const float w = window_halfwidth(t2, ki);
-      const int w_lo = lower_bound_f(pk, 0, li, ki - w), w_hi = upper_bound_f(pk, li + 1, M, ki + w);
+      const int ci = scell[gb + slot], ca = ci / nb, cb = ci - ca * nb;
+      // lanes 0..2 fetch the slot run of grid row ca - 1 + lane: cells cb - 1 .. cb + 1
+      int run_lo = 0, run_hi = 0;
+      if (lane < 3) {
+        const int a = ca - 1 + lane;
+        if (a >= 0 && a < na) { run_lo = cs[a * nb + max(cb - 1, 0)] - r_lo; run_hi = cs[a * nb + min(cb + 1, nb - 1) + 1] - r_lo; }
+      }
+      for (int run = 0; run < 3; ++run) {
+      const int w_lo = __shfl_sync(FULL, run_lo, run), w_hi = __shfl_sync(FULL, run_hi, run);
       for (int j0 = w_lo; j0 < w_hi; j0 += 32) {
         const int s = j0 + lane;
         bool ok = false;
@@ -256,6 +293,7 @@ __global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
             else if (lane > at) { ld = ud; lj = uj; }
           }
         }
+      }
       }
     }
     const int cnt = min(total, topk);
@@ -467,7 +505,7 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
   int NP2 = 1;
   while (NP2 < N) NP2 <<= 1;
   const size_t sort_smem = (size_t)NP2 * 8;
-  const size_t smem = (size_t)N * 21 + 32;   // worst case: a CTA's window spans the whole graph
+  const size_t smem = (size_t)N * 17 + 32;   // worst case: a CTA's window spans the whole graph
   AGX_REQUIRE(smem <= 227 * 1024 && sort_smem <= 227 * 1024, AGX_ERR_ARG, "graph_build: N=%d exceeds the shared-memory staging limit", N);
   static thread_local size_t smem_set = 0, sort_smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
@@ -475,7 +513,7 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
     smem_set = smem;
   }
   if (sort_smem > 48 * 1024 && sort_smem > sort_smem_set) {
-    AGX_CUDA_OK(cudaFuncSetAttribute(sort_axis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    AGX_CUDA_OK(cudaFuncSetAttribute(sort_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
     sort_smem_set = sort_smem;
   }
   const int rows = B * N;
@@ -486,11 +524,12 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
     AGX_LAUNCH_CHECK();
   }
   { ProfScope ps(AGX_KIND_GRAPH_SORT, st);
-    sort_axis_kernel<<<B, 1024, sort_smem, st>>>(pos, pos_stride_b, mask, tool_mask, N, NP2, ws.sx, ws.sy, ws.sz, ws.skey, ws.sidx, ws.sflag); }
+    sort_cells_kernel<<<B, 1024, sort_smem, st>>>(pos, pos_stride_b, mask, tool_mask, thr2, N, NP2, ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx,
+                                                  ws.sflag, ws.cell_start, ws.grid_dims); }
   AGX_LAUNCH_CHECK();
   dim3 g1((N + G1_ROWS_PER_CTA - 1) / G1_ROWS_PER_CTA, B);
   { ProfScope ps(AGX_KIND_GRAPH_KNN, st);
-    knn_rows_kernel<<<g1, G1_THREADS, smem, st>>>(ws.sx, ws.sy, ws.sz, ws.skey, ws.sidx, ws.sflag, thr2, N, topk,
+    knn_rows_kernel<<<g1, G1_THREADS, smem, st>>>(ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx, ws.sflag, ws.cell_start, ws.grid_dims, thr2, N, topk,
                                                    cta && sem == AGX_SEM_BATCH, N, ws.cand, ws.cnt, ws.flags); }
   AGX_LAUNCH_CHECK();
   { ProfScope ps(AGX_KIND_GRAPH_SCAN, st);
