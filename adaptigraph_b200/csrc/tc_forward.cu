@@ -511,7 +511,9 @@ constexpr int AGG_BATCH = 8;   // relations in flight per thread
 constexpr int AGG_CTAS_PER_SM = 2;
 // Measured on cloth-2k x 128 (B200, ms per launch): one CTA per 8 rows with 2 relations in flight 0.392; this kernel with
 // (batch, CTAs/SM) = (8, 2) 0.349, (4, 3) 0.386, (2, 4) 0.370, (6, 2) 0.436; visiting runs of 16 consecutive groups per CTA 0.387;
-// a warp-per-row variant staging C through per-warp TMA rings 0.658 (150 instructions per relation: issue-latency bound).
+// a warp-per-row variant staging C through per-warp TMA rings 0.658 (150 instructions per relation: issue-latency bound);
+// this kernel plus a bulk L2 prefetch of the next group's C / Qr rows 0.389 (the memory system is request-throughput bound on the
+// 64-byte pieces of the blocked layout, not latency bound: more requests in flight only queue).
 __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_split_kernel(
     const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send, int64_t rows, int N, int64_t E_cap,
     const float4* __restrict__ C, const float4* __restrict__ Qr, const float4* __restrict__ Qs, uint32_t* __restrict__ agg_split,
