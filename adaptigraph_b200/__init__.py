@@ -4,7 +4,8 @@ Importing the compute API loads libadaptigraph_b200.so and fails loudly if it is
 `adaptigraph_b200.synthetic` (workload generators) is importable without it.
 """
 __all__ = ["DynamicsPredictor", "EdgeList", "build_edges", "construct_edges_from_states",
-           "construct_edges_from_states_batch", "edges_from_onehots", "pad_torch", "truncate_graph"]
+           "construct_edges_from_states_batch", "edges_from_onehots", "pad_torch", "truncate_graph",
+           "fps", "fps_rad_idx", "farthest_point_sampler", "fps_batch"]
 
 
 def __getattr__(name):
@@ -18,4 +19,7 @@ def __getattr__(name):
     if name in ("pad_torch", "truncate_graph"):
         from . import utils
         return getattr(utils, name)
+    if name in ("fps", "fps_rad_idx", "farthest_point_sampler", "fps_batch"):
+        from . import sampling
+        return getattr(sampling, name)
     raise AttributeError(name)

@@ -1,0 +1,116 @@
+// Farthest-point sampling on the device: the step that produces the model's particles from raw point
+// clouds / simulator states.  Replaces, with identical selections,
+//
+//   * dgl.geometry.farthest_point_sampler(pos, npoints, start_idx) as called at dynamics/dataset/graph.py:11-12 and
+//     planning/perception.py:271 (third-party; restated from DGL's CPU operator, see oracle/sampling_oracle.py):
+//     squared distances ((dx*dx + dy*dy) + dz*dz, fp32, no FMA contraction), d[j] = min over the chosen points, next = the
+//     FIRST index of the maximum;
+//   * fps_rad_idx(pcd, radius) of dynamics/utils.py:10-24: the same recurrence on np.linalg.norm distances (fp32 sqrt of the
+//     same sum), continued while max_j d[j] > radius (compared in double, as numpy compares a float32 with a Python float).
+//
+// One CTA per cloud: the points and their running distances stay in shared memory; one iteration = one pass over the points
+// (each thread its strided share), a warp-shuffle arg-max, a 32-entry shared-memory exchange and one more warp arg-max.
+#include "common.cuh"
+
+namespace agx {
+
+constexpr int FPS_THREADS = 1024;
+constexpr unsigned FPS_FULL = 0xffffffffu;
+
+// (value, index) arg-max with ties towards the lower index
+__device__ __forceinline__ void argmax_merge(float& v, int& i, float ov, int oi) {
+  if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+
+template <bool SQRT_DOMAIN>
+__global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restrict__ pos, const int32_t* __restrict__ n_points, int N,
+                                                          int max_samples, const int32_t* __restrict__ start_idx, double radius,
+                                                          int32_t* __restrict__ idx_out, int32_t* __restrict__ n_out) {
+  extern __shared__ float fps_smem[];
+  float* px = fps_smem;
+  float* py = px + N;
+  float* pz = py + N;
+  float* dist = pz + N;
+  __shared__ float red_v[32];
+  __shared__ int red_i[32];
+  __shared__ int cur_s;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = n_points ? min(max(n_points[b], 0), N) : N;
+  const float* p = pos + (size_t)b * N * 3;
+  int32_t* out = idx_out + (size_t)b * max_samples;
+  if (n == 0 || max_samples == 0) { if (tid == 0) n_out[b] = 0; return; }
+  const float INF = __int_as_float(0x7f800000);
+  for (int j = tid; j < n; j += FPS_THREADS) { px[j] = p[3 * j]; py[j] = p[3 * j + 1]; pz[j] = p[3 * j + 2]; dist[j] = INF; }
+  if (tid == 0) {
+    const int s = min(max(start_idx[b], 0), n - 1);
+    cur_s = s;
+    out[0] = s;
+  }
+  __syncthreads();
+  int count = 1;
+  const int limit = min(max_samples, SQRT_DOMAIN ? n : max_samples);
+  while (true) {
+    const int cur = cur_s;
+    const float cx = px[cur], cy = py[cur], cz = pz[cur];
+    float bv = -1.f;
+    int bi = 0x7fffffff;
+    for (int j = tid; j < n; j += FPS_THREADS) {
+      const float dx = __fsub_rn(px[j], cx), dy = __fsub_rn(py[j], cy), dz = __fsub_rn(pz[j], cz);
+      float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (SQRT_DOMAIN) d = __fsqrt_rn(d);
+      const float m = fminf(dist[j], d);
+      dist[j] = m;
+      if (m > bv) { bv = m; bi = j; }   // ascending j: strict > keeps the first maximum
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) argmax_merge(bv, bi, __shfl_xor_sync(FPS_FULL, bv, o), __shfl_xor_sync(FPS_FULL, bi, o));
+    if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+    __syncthreads();
+    bv = red_v[lane];
+    bi = red_i[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) argmax_merge(bv, bi, __shfl_xor_sync(FPS_FULL, bv, o), __shfl_xor_sync(FPS_FULL, bi, o));
+    // every warp now holds the same (bv, bi)
+    bool stop = count >= limit;
+    if (SQRT_DOMAIN) stop = stop || !((double)bv > radius);   // utils.py:17  while dist.max() > radius
+    if (stop) break;
+    if (tid == 0) { cur_s = bi; out[count] = bi; }
+    ++count;
+    __syncthreads();
+  }
+  if (tid == 0) n_out[b] = count;
+}
+
+}  // namespace agx
+
+extern "C" {
+
+int agx_fps(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int32_t max_samples, const int32_t* start_idx,
+            double radius, int32_t* idx_out, int32_t* n_out, agx_stream_t stream) {
+  using namespace agx;
+  AGX_REQUIRE(pos && start_idx && idx_out && n_out, AGX_ERR_ARG, "fps: null pointer argument");
+  AGX_REQUIRE(B > 0 && N > 0 && max_samples > 0, AGX_ERR_ARG, "fps: B=%d N=%d max_samples=%d must be positive", B, N, max_samples);
+  const size_t smem = (size_t)N * 16;
+  AGX_REQUIRE(smem <= 200 * 1024, AGX_ERR_ARG, "fps: N=%d exceeds the shared-memory staging limit (12800 points per cloud)", N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static thread_local size_t set_count = 0, set_radius = 0;
+  if (radius < 0.0) {
+    if (smem > 48 * 1024 && smem > set_count) {
+      AGX_CUDA_OK(cudaFuncSetAttribute(fps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set_count = smem;
+    }
+    ProfScope ps(AGX_KIND_OTHER, st);
+    fps_kernel<false><<<B, FPS_THREADS, smem, st>>>(pos, n_points, N, max_samples, start_idx, radius, idx_out, n_out);
+  } else {
+    if (smem > 48 * 1024 && smem > set_radius) {
+      AGX_CUDA_OK(cudaFuncSetAttribute(fps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set_radius = smem;
+    }
+    ProfScope ps(AGX_KIND_OTHER, st);
+    fps_kernel<true><<<B, FPS_THREADS, smem, st>>>(pos, n_points, N, max_samples, start_idx, radius, idx_out, n_out);
+  }
+  AGX_LAUNCH_CHECK();
+  return AGX_OK;
+}
+
+}  // extern "C"

@@ -139,6 +139,30 @@ def _(row_ptr, send, B, N, n_rel):
     return (row_ptr.new_empty((B, n_rel, N), dtype=torch.float32), row_ptr.new_empty((B, n_rel, N), dtype=torch.float32))
 
 
+# --------------------------------------------------------------------------- particle sampling
+@torch.library.custom_op("agx::fps", mutates_args=())
+def fps(pos: Tensor, n_points: Tensor, start_idx: Tensor, max_samples: int, radius: float) -> Tuple[Tensor, Tensor]:
+    """Farthest-point sampling of B clouds: pos (B,N,3), n_points (B) int32 valid prefix lengths, start_idx (B) int32.
+    radius < 0: exactly max_samples picks (dgl.geometry.farthest_point_sampler); radius >= 0: picks until every point lies
+    within `radius` of a pick (fps_rad_idx, utils.py:10-24).  Returns idx (B, max_samples) int32 and counts (B) int32."""
+    _need_cuda(pos, n_points, start_idx)
+    pos = _f32(pos)
+    B, N, _ = pos.shape
+    n_points = n_points.to(torch.int32).contiguous()
+    start_idx = start_idx.to(torch.int32).contiguous()
+    idx = torch.zeros(B, max_samples, dtype=torch.int32, device=pos.device)
+    cnt = torch.empty(B, dtype=torch.int32, device=pos.device)
+    L.check(lib.agx_fps(_ptr(pos), _ptr(n_points), B, N, max_samples, _ptr(start_idx), float(radius), _ptr(idx), _ptr(cnt),
+                        _stream()), "agx_fps")
+    return idx, cnt
+
+
+@fps.register_fake
+def _(pos, n_points, start_idx, max_samples, radius):
+    B = pos.shape[0]
+    return pos.new_empty((B, max_samples), dtype=torch.int32), pos.new_empty((B,), dtype=torch.int32)
+
+
 # --------------------------------------------------------------------------- forward / rollout
 @torch.library.custom_op("agx::forward", mutates_args=())
 def forward(packed: Tensor, state: Tensor, attrs: Tensor, action: Tensor, p_instance: Tensor, physics: Tensor,

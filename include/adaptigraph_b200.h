@@ -8,6 +8,7 @@
  *   model forward        dynamics/gnn/model.py:129-313
  *   rollout step         planning/forward_dynamics.py:156-197 (and :351-393)
  *   pad / truncate       dynamics/utils.py:37-46, :127-137
+ *   particle sampling    dynamics/dataset/graph.py:8-36, dynamics/utils.py:10-24 (the step in front of the path)
  *
  * The reference exposes no FFI on this path (its boundary is three Python call
  * signatures); these entry points are what a ctypes binding on the
@@ -133,6 +134,16 @@ AGX_API int agx_onehot_to_ids(const float* R, int32_t B, int32_t n_rel, int32_t 
 /* CSR -> dense one-hot rows (graph.py:152-155): Rr, Rs (B, n_rel, N) must be zero-filled by the caller. */
 AGX_API int agx_edges_to_onehot(const int32_t* row_ptr, const int32_t* send, int32_t B, int32_t N, int32_t n_rel,
                         float* Rr, float* Rs, agx_stream_t stream);
+
+/* ---- farthest-point sampling: the particle sampler in front of the path.
+ * radius < 0  : dgl.geometry.farthest_point_sampler(pos, max_samples, start_idx) as called at graph.py:11-12 and
+ *               perception.py:271 — exactly max_samples picks per cloud (squared fp32 distances, first index on ties).
+ * radius >= 0 : fps_rad_idx(pcd, radius), utils.py:10-24 — picks until every point is within `radius` of a pick
+ *               (fp32 norms, compared with the double `radius`), at most max_samples.
+ * pos (B,N,3); n_points (B) valid prefix length of every cloud or NULL (= N); start_idx (B) first pick;
+ * idx_out (B, max_samples) picks in selection order; n_out (B) number of picks.  N <= 12800. */
+AGX_API int agx_fps(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int32_t max_samples,
+            const int32_t* start_idx, double radius, int32_t* idx_out, int32_t* n_out, agx_stream_t stream);
 
 /* ---- model forward (replaces model.py:129-313) */
 AGX_API size_t agx_forward_workspace_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap);

@@ -1,0 +1,121 @@
+"""Particle samplers: the oracle against vectors produced by the reference's own fps_rad_idx / fps
+(tests/golden/make_golden_fps.py), and — on the GPU — agx_fps through the reference-signature wrappers against both."""
+import numpy as np
+import pytest
+import torch
+
+import agx_helpers as H
+from oracle import sampling_oracle as so
+
+FPS = H.load_npz("fps_cases.npz")
+CLOUDS = sorted({k.split("/")[0] for k in FPS})
+
+
+def _replay_fps_draws(pcd, max_nobj, rr, seed):
+    """The reference's order of numpy draws inside fps() (graph.py:11-27, utils.py:14): start, [radius], second start."""
+    np.random.seed(seed)
+    start_1 = np.random.randint(0, pcd.shape[0])
+    radius = float(rr[0]) if len(rr) == 1 else np.random.uniform(rr[0], rr[1])
+    start_2 = np.random.randint(min(max_nobj, pcd.shape[0]))
+    return start_1, radius, start_2
+
+
+@pytest.mark.parametrize("name", CLOUDS)
+def test_oracle_matches_reference_fps_rad_idx(name):
+    pcd = FPS[f"{name}/pcd"]
+    for k in range(3):
+        np.random.seed(int(FPS[f"{name}/rad{k}/seed"]))
+        rand_idx = np.random.randint(pcd.shape[0])
+        pts, idx = so.fps_rad_idx(pcd, float(FPS[f"{name}/rad{k}/radius"]), rand_idx)
+        np.testing.assert_array_equal(np.asarray(idx).reshape(-1), FPS[f"{name}/rad{k}/idx"])
+        np.testing.assert_array_equal(pts, pcd[FPS[f"{name}/rad{k}/idx"]])
+
+
+@pytest.mark.parametrize("name", CLOUDS)
+def test_oracle_matches_reference_fps_wrapper(name):
+    pcd = FPS[f"{name}/pcd"]
+    for k in range(3):
+        max_nobj, rr = int(FPS[f"{name}/fps{k}/max_nobj"]), FPS[f"{name}/fps{k}/range"]
+        s1, radius, s2 = _replay_fps_draws(pcd, max_nobj, rr, int(FPS[f"{name}/fps{k}/seed"]))
+        idx = so.fps(pcd, max_nobj, radius, s1, s2)
+        np.testing.assert_array_equal(idx, FPS[f"{name}/fps{k}/idx"])
+
+
+def test_oracle_sampler_properties():
+    rng = np.random.default_rng(0)
+    pos = rng.normal(size=(3, 200, 3)).astype(np.float32)
+    idx = so.farthest_point_sampler(pos, 50, [0, 7, 199])
+    assert idx.shape == (3, 50) and list(idx[:, 0]) == [0, 7, 199]
+    for b in range(3):
+        assert len(set(idx[b])) == 50                                   # distinct points: no re-picks before exhaustion
+        d = np.linalg.norm(pos[b][:, None] - pos[b][idx[b, :2]][None], axis=-1)
+        assert idx[b, 1] == np.argmax(d[:, 0])                          # second pick = farthest from the first
+
+
+# ------------------------------------------------------------------------------------------- GPU
+@pytest.fixture(scope="module")
+def sampling():
+    import adaptigraph_b200.ops  # noqa: F401  (loads the .so; raises if missing)
+    from adaptigraph_b200 import sampling as s
+    assert torch.cuda.is_available()
+    return s
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CLOUDS)
+def test_gpu_fps_rad_idx_matches_reference(sampling, name):
+    pcd = FPS[f"{name}/pcd"]
+    for k in range(3):
+        np.random.seed(int(FPS[f"{name}/rad{k}/seed"]))
+        pts, idx = sampling.fps_rad_idx(pcd, float(FPS[f"{name}/rad{k}/radius"]))
+        np.testing.assert_array_equal(idx, FPS[f"{name}/rad{k}/idx"])
+        np.testing.assert_array_equal(pts, pcd[idx])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CLOUDS)
+def test_gpu_fps_wrapper_matches_reference(sampling, name):
+    pcd = FPS[f"{name}/pcd"]
+    for k in range(3):
+        rr = FPS[f"{name}/fps{k}/range"]
+        np.random.seed(int(FPS[f"{name}/fps{k}/seed"]))
+        idx = sampling.fps(pcd, int(FPS[f"{name}/fps{k}/max_nobj"]), float(rr[0]) if len(rr) == 1 else list(rr))
+        np.testing.assert_array_equal(idx, FPS[f"{name}/fps{k}/idx"])
+
+
+@pytest.mark.gpu
+def test_gpu_sampler_matches_oracle_batched(sampling):
+    rng = np.random.default_rng(3)
+    for B, N, k in [(4, 257, 64), (2, 2025, 300), (3, 33, 33), (1, 12800, 40)]:
+        pos = rng.normal(size=(B, N, 3)).astype(np.float32)
+        start = rng.integers(0, N, B)
+        ref = so.farthest_point_sampler(pos, k, start)
+        got = sampling.farthest_point_sampler(torch.from_numpy(pos).cuda(), k, torch.from_numpy(start).cuda())
+        assert got.dtype == torch.int64 and got.is_cuda
+        np.testing.assert_array_equal(got.cpu().numpy(), ref)
+    # scalar start index and CPU input (the reference's call form, graph.py:11-12): result comes back on the CPU
+    pos = rng.normal(size=(1, 500, 3)).astype(np.float32)
+    got = sampling.farthest_point_sampler(torch.from_numpy(pos), 100, start_idx=17)
+    np.testing.assert_array_equal(got.numpy(), so.farthest_point_sampler(pos, 100, [17]))
+    with pytest.raises(ValueError):
+        sampling.farthest_point_sampler(torch.from_numpy(pos), 10, start_idx=500)
+    with pytest.raises(ValueError):   # beyond the shared-memory staging limit: an error, not a fallback
+        sampling.farthest_point_sampler(torch.zeros(1, 12801, 3), 4, start_idx=0)
+
+
+@pytest.mark.gpu
+def test_gpu_fps_batch_on_device(sampling):
+    """Ragged clouds sampled without a host round trip: every cloud agrees with the oracle's fps() on its own points."""
+    rng = np.random.default_rng(5)
+    B, N, max_nobj, radius = 5, 600, 100, 0.35
+    n_pts = np.array([600, 431, 100, 57, 1])
+    pos = rng.normal(0, 0.8, size=(B, N, 3)).astype(np.float32)
+    s1 = np.array([rng.integers(0, n) for n in n_pts])
+    s2 = np.array([rng.integers(0, min(max_nobj, n)) for n in n_pts])
+    idx, cnt = sampling.fps_batch(torch.from_numpy(pos).cuda(), torch.from_numpy(n_pts).int().cuda(), max_nobj, radius,
+                                  torch.from_numpy(s1).int().cuda(), torch.from_numpy(s2).int().cuda())
+    idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+    for b in range(B):
+        ref = so.fps(pos[b, :n_pts[b]], max_nobj, radius, int(s1[b]), int(s2[b]))
+        assert cnt[b] == len(ref)
+        np.testing.assert_array_equal(idx[b, :cnt[b]], ref)
