@@ -36,7 +36,7 @@ EXPORTS = [
     "agx_forward_workspace_bytes", "agx_forward",
     "agx_rollout_workspace_bytes", "agx_rollout",
     "agx_profile_enable", "agx_profile_read", "agx_kind_name",
-    "agx_train_saved_bytes", "agx_train_scratch_bytes", "agx_forward_train", "agx_backward",
+    "agx_train_saved_bytes", "agx_train_scratch_bytes", "agx_forward_train", "agx_backward", "agx_adam_step",
 ]
 AGX_NUM_KINDS = 12
 
@@ -97,6 +97,7 @@ def _load() -> C.CDLL:
         "agx_train_scratch_bytes": (sz, [P(AgxModelDims), i32, i32, i64]),
         "agx_forward_train": (C.c_int, [P(AgxModelDims), vp, P(AgxGraphIn), vp, i64, vp, vp, sz, vp]),
         "agx_backward": (C.c_int, [P(AgxModelDims), vp, P(AgxGraphIn), vp, vp, vp, vp, vp, vp, P(AgxWeightGrads), vp, vp, sz, vp]),
+        "agx_adam_step": (C.c_int, [vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, vp, vp]),
         "agx_profile_enable": (C.c_int, [i32]),
         "agx_profile_read": (C.c_int, [P(C.c_double), P(i64)]),
         "agx_kind_name": (C.c_char_p, [i32]),

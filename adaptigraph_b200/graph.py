@@ -109,7 +109,7 @@ def edges_from_onehots(Rr: Tensor, Rs: Tensor) -> EdgeList:
     valid = (rid >= 0) & (sid >= 0)
     key = torch.where(valid, rid + torch.arange(B, device=dev)[:, None] * N, torch.full_like(rid, B * N)).reshape(-1)
     key_sorted, perm = torch.sort(key, stable=True)
-    deg = torch.bincount(key_sorted, minlength=B * N + 1)[: B * N]
+    deg = torch.zeros(B * N + 1, dtype=torch.int64, device=dev).index_add_(0, key_sorted, torch.ones_like(key_sorted))[: B * N]
     row_ptr = torch.zeros(B * N + 1, dtype=torch.int32, device=dev)
     row_ptr[1:] = torch.cumsum(deg, 0).to(torch.int32)
     send = sid.reshape(-1)[perm].clamp_(min=0).to(torch.int32).contiguous()

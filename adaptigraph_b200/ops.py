@@ -287,3 +287,17 @@ def backward(packed: Tensor, state: Tensor, attrs: Tensor, action: Tensor, p_ins
     L.check(lib.agx_backward(C.byref(dims), _ptr(packed), C.byref(g), _ptr(saved), _ptr(send_ptr), _ptr(send_perm), _ptr(pred_motion),
                              _ptr(d_pos) if d_pos is not None else nul, _ptr(d_motion) if d_motion is not None else nul, C.byref(wg),
                              _ptr(d_state) if d_state is not None else nul, _ptr(scratch), nsc, _stream()), "agx_backward")
+
+
+# --------------------------------------------------------------------------- optimiser
+def adam_step(params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, step: Tensor, lr: float, beta1: float, beta2: float,
+              eps: float, grad_scale: float = 1.0) -> None:
+    """In-place Adam over flat fp32 buckets (train.py:63 semantics); `step` is a device int32 counter, incremented on the stream."""
+    _need_cuda(params, grads, exp_avg, exp_avg_sq, step)
+    for t in (params, grads, exp_avg, exp_avg_sq):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != params.numel():
+            raise ValueError("adam_step: buckets must be contiguous float32 tensors of equal length")
+    if step.dtype != torch.int32 or step.numel() != 1:
+        raise ValueError("adam_step: step must be a one-element int32 tensor")
+    L.check(lib.agx_adam_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), lr, beta1, beta2, eps,
+                              grad_scale, _ptr(step), _stream()), "agx_adam_step")

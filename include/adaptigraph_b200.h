@@ -196,6 +196,14 @@ AGX_API int agx_backward(const AgxModelDims* dims, const void* packed_weights, c
                          const float* d_pred_motion, const AgxWeightGrads* grads, float* d_state, void* scratch,
                          size_t scratch_bytes, agx_stream_t stream);
 
+/* ---- optimiser step (replaces torch.optim.Adam of dynamics/train/train.py:63, :115): Adam over one flat
+ * fp32 bucket of n parameters (params, grads, exp_avg, exp_avg_sq: 16-byte aligned device arrays of n floats).  Gradients are
+ * multiplied by grad_scale first (1 / world size after a summing all-reduce).  `step` is a device int32 holding the number of
+ * steps taken so far; it is read for the bias corrections and incremented on the stream, so a captured CUDA graph can be replayed.
+ * The hyper-parameters are doubles because torch derives its scalars (1 - beta, lr / (1 - beta1^t), sqrt(1 - beta2^t)) in double. */
+AGX_API int agx_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, float grad_scale, int32_t* step, agx_stream_t stream);
+
 /* ---- per-kernel timing for bench.py's roofline block.  When enabled, every kernel launched by the
  * calling thread is bracketed by CUDA events on its launch stream; agx_profile_read synchronises on
  * those events and ADDS elapsed milliseconds / launch counts per kernel kind into ms[] / count[]

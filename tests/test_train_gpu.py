@@ -1,0 +1,137 @@
+"""Training glue: fused Adam against torch.optim.Adam (the reference's optimiser, train.py:63), the Trainer's
+unroll against the reference's loss (tests/golden/train_unroll_rope40.npz), CUDA-graph replay against eager stepping, and the
+optimizer state round trip through torch.optim.Adam's state_dict."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import agx_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def agx():
+    import adaptigraph_b200 as pkg
+    import adaptigraph_b200.ops  # noqa: F401  (loads the .so; raises if missing)
+    assert torch.cuda.is_available()
+    return pkg
+
+
+def _golden_batch():
+    g = H.load_npz("train_unroll_rope40.npz")
+    t = lambda k: torch.from_numpy(g[k]).cuda()  # noqa: E731
+    N = g["attrs"].shape[1]
+    Rr, Rs = H.onehots_from_lists(g["recv"], g["send"], N)
+    data = {"state": t("state"), "attrs": t("attrs"), "action": t("action"), "p_instance": t("p_instance"), "Rr": Rr.cuda(), "Rs": Rs.cuda(),
+            "rope_physics_param": t("physics_param"), "state_future": t("state_future"), "eef_future": t("eef_future"),
+            "action_future": t("action_future")}
+    return g, data
+
+
+def _model(agx, pstep):
+    from adaptigraph_b200 import synthetic as syn
+    m = agx.DynamicsPredictor(*syn.configs("rope", pstep), "cuda")
+    m.load_state_dict(H.golden_weights())
+    return m.cuda().train()
+
+
+def test_fused_adam_matches_torch_adam():
+    from adaptigraph_b200 import ops
+    torch.manual_seed(0)
+    n = 252903                                   # the model's parameter count: exercises the unaligned tail
+    p0 = torch.randn(n)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    p = p0.cuda()
+    m, v, step = torch.zeros_like(p), torch.zeros_like(p), torch.zeros(1, dtype=torch.int32, device="cuda")
+    for it in range(4):
+        g = torch.randn(n) * (10.0 ** (it - 2))
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, (g * 2).cuda(), m, v, step, 1e-3, 0.9, 0.999, 1e-8, grad_scale=0.5)
+        assert int(step.item()) == it + 1
+        assert (p.cpu() - ref.detach()).abs().max().item() <= 2e-7 * max(1.0, float(ref.detach().abs().max()))
+    st = opt.state[ref]
+    assert (m.cpu() - st["exp_avg"]).abs().max() <= 1e-6 * st["exp_avg"].abs().max()
+    assert (v.cpu() - st["exp_avg_sq"]).abs().max() <= 1e-6 * st["exp_avg_sq"].abs().max()
+    with pytest.raises(ValueError):
+        ops.adam_step(p, p[:10], m, v, step, 1e-3, 0.9, 0.999, 1e-8)
+    with pytest.raises(RuntimeError):
+        ops.adam_step(p.cpu(), p.cpu(), m.cpu(), v.cpu(), step.cpu(), 1e-3, 0.9, 0.999, 1e-8)
+
+
+def test_trainer_matches_reference_loss_and_torch_adam(agx):
+    """Same engine gradients, two optimisers: the fused flat-bucket Adam and torch.optim.Adam stepping the reference way."""
+    from adaptigraph_b200.train import Trainer, unroll_loss
+    g, data = _golden_batch()
+    a, b = _model(agx, int(g["pstep"])), _model(agx, int(g["pstep"]))
+    tr = Trainer(a, lr=1e-3, n_future=3)
+    opt = torch.optim.Adam(b.parameters(), lr=1e-3)
+    for it in range(3):
+        d = dict(data)
+        d["state"] = data["state"] + 0.01 * it
+        loss_a = tr.step(d)
+        opt.zero_grad()
+        loss_b = unroll_loss(b, d, 3)
+        loss_b.backward()
+        opt.step()
+        if it == 0:
+            assert abs(loss_a.item() - float(g["loss"])) <= 1e-6          # the reference's own loss on this batch
+        assert abs(loss_a.item() - loss_b.item()) <= 1e-6 * max(1.0, abs(loss_b.item()))
+        for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            assert (pa - pb).abs().max().item() <= 5e-6, (it, k)
+    assert int(tr.step_count.item()) == 3
+    # every parameter is a view of the flat bucket, in model.parameters() order
+    assert sum(p.numel() for p in a.parameters()) == tr.bucket.flat.numel() == 252903
+    assert next(a.parameters()).data_ptr() == tr.bucket.flat.data_ptr()
+
+
+def test_cuda_graph_replay_equals_eager_steps(agx):
+    from adaptigraph_b200.train import Trainer
+    g, data = _golden_batch()
+    a, b = _model(agx, int(g["pstep"])), _model(agx, int(g["pstep"]))
+    eager, graphed = Trainer(a, n_future=3), Trainer(b, n_future=3, cuda_graph=True)
+    edges = agx.edges_from_onehots(data["Rr"], data["Rs"])
+    for it in range(4):
+        d = dict(data)
+        d["state"] = data["state"] + 0.02 * it
+        d["state_future"] = data["state_future"] - 0.01 * it
+        la, lb = eager.step(d, edges), graphed.step(d, edges)
+        assert la.item() == lb.item(), it
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(pa, pb), k
+    assert int(graphed.step_count.item()) == 4
+    bad = dict(data)
+    bad["state"] = data["state"][:1]
+    with pytest.raises(RuntimeError):
+        graphed.step(bad, edges)
+
+
+def test_optimizer_state_round_trips_through_torch_adam(agx):
+    from adaptigraph_b200.train import Trainer, unroll_loss
+    g, data = _golden_batch()
+    a = _model(agx, int(g["pstep"]))
+    tr = Trainer(a, n_future=3)
+    assert tr.optimizer_state_dict()["state"] == {}
+    tr.step(data)
+    tr.step(data)
+    sd = tr.optimizer_state_dict()
+    b = _model(agx, int(g["pstep"]))
+    b.load_state_dict(copy.deepcopy(a.state_dict()))
+    opt = torch.optim.Adam(b.parameters(), lr=1e-3)
+    opt.load_state_dict(sd)                                   # the reference's latest_optim.pth format (train.py:121)
+    tr.step(data)
+    opt.zero_grad()
+    unroll_loss(b, data, 3).backward()
+    opt.step()
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert (pa - pb).abs().max().item() <= 5e-6, k
+    c = _model(agx, int(g["pstep"]))
+    tr2 = Trainer(c, n_future=3)
+    tr2.load_optimizer_state_dict(opt.state_dict())
+    assert int(tr2.step_count.item()) == 3
+    ref_m = opt.state_dict()["state"][0]["exp_avg"]
+    assert torch.equal(tr2.bucket.views(tr2.exp_avg)[0], ref_m.cuda())

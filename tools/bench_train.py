@@ -68,7 +68,39 @@ for _ in range(2):
     l_cpu, gs_cpu = cpu_step()
 cpu_ms = (time.perf_counter() - t0) / 2 * 1e3
 gerr = max(float((dict(m.named_parameters())[k].grad.cpu() - v.grad).abs().max() / max(1e-12, float(v.grad.abs().max()))) for k, v in p.items())
+# the reference's whole training iteration (train.py:84-115: zero_grad, n_future = 3 unroll, backward, Adam) through the Trainer,
+# eager and as one replayed CUDA graph
+from adaptigraph_b200.train import Trainer  # noqa: E402
+
+
+def trainer_ms(cuda_graph):
+    torch.manual_seed(0)
+    mm = agx.DynamicsPredictor(*syn.configs(c["material"], c["pstep"]), "cuda").cuda().train()
+    tr = Trainer(mm, n_future=3, cuda_graph=cuda_graph)
+    d = w.graph_dict()
+    n_p = w.p_instance.shape[1]
+    cur = w.state[:, -1]
+    d["state_future"] = torch.stack([cur[:, :n_p] + 0.01 * (i + 1) for i in range(3)], 1)
+    d["eef_future"] = torch.stack([cur, cur], 1)
+    d["action_future"] = torch.stack([w.action, w.action], 1)
+    for _ in range(4):
+        tr.step(d, el)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(K):
+        last = tr.step(d, el)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / K, float(last)
+
+
+tr_eager_ms, tr_eager_loss = trainer_ms(False)
+tr_graph_ms, tr_graph_loss = trainer_ms(True)
+
 print(json.dumps({
+    "trainer_n_future3_ms_per_iter_eager": tr_eager_ms, "trainer_n_future3_ms_per_iter_cuda_graph": tr_graph_ms,
+    "trainer_loss_after_24_iters": [tr_eager_loss, tr_graph_loss],
     "workload": "rope 300 particles, batch 32, pstep 4, forward+backward (BASELINE configs[1])", "relations": E,
     "gpu_ms_per_step": ms, "gpu_particle_steps_per_s": c["B"] * c["n_p"] / (ms * 1e-3),
     "cpu_ms_per_step": cpu_ms, "cpu_particle_steps_per_s": c["B"] * c["n_p"] / (cpu_ms * 1e-3), "cpu_cores": os.cpu_count(),
