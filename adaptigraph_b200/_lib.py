@@ -32,7 +32,7 @@ LAYER_NAMES = [
 EXPORTS = [
     "agx_version", "agx_last_error", "agx_launch_count",
     "agx_packed_weights_bytes", "agx_pack_weights",
-    "agx_graph_workspace_bytes", "agx_graph_build", "agx_onehot_to_ids", "agx_edges_to_onehot", "agx_fps",
+    "agx_graph_workspace_bytes", "agx_graph_build", "agx_onehot_to_ids", "agx_edges_to_onehot", "agx_fps", "agx_chamfer",
     "agx_forward_workspace_bytes", "agx_forward",
     "agx_rollout_workspace_bytes", "agx_rollout",
     "agx_profile_enable", "agx_profile_read", "agx_kind_name",
@@ -89,6 +89,7 @@ def _load() -> C.CDLL:
         "agx_onehot_to_ids": (C.c_int, [vp, i32, i32, i32, vp, vp]),
         "agx_edges_to_onehot": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "agx_fps": (C.c_int, [vp, vp, i32, i32, i32, vp, C.c_double, vp, vp, vp]),
+        "agx_chamfer": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
         "agx_forward_workspace_bytes": (sz, [P(AgxModelDims), i32, i32, i64]),
         "agx_forward": (C.c_int, [P(AgxModelDims), vp, P(AgxGraphIn), vp, i64, vp, i32, vp, sz, vp]),
         "agx_rollout_workspace_bytes": (sz, [P(AgxModelDims), i32, i32, i64, i32]),

@@ -114,3 +114,82 @@ int agx_fps(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ chamfer distance
+// planning/losses.py:4-10 — the MPC error term evaluated on the rollout's last frame (plan.py:36, :146): for every sample b
+//   mean_m min_n |x[b,n] - y[m]|  +  mean_n min_m |x[b,n] - y[m]|.
+// The reference materialises two (B, M, N, 3) tensors; here one CTA per sample keeps both point sets in shared memory, a thread
+// owns one point of one set and scans the other (min of squared distances, one sqrt per point: sqrt is monotone), then a fixed-order
+// block reduction gives the two means.
+namespace agx {
+
+constexpr int CH_THREADS = 256;
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < CH_THREADS / 32; ++w) t += red[w];   // same order in every thread
+  return t;
+}
+
+__global__ void __launch_bounds__(CH_THREADS) chamfer_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int M,
+                                                             int64_t y_stride_b, float* __restrict__ out) {
+  extern __shared__ float ch_smem[];
+  __shared__ float red[CH_THREADS / 32];
+  float* xs = ch_smem;            // [N][3]
+  float* ys = ch_smem + 3 * N;    // [M][3]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* xb = x + (size_t)b * N * 3;
+  const float* yb = y + (size_t)b * y_stride_b;
+  for (int i = tid; i < 3 * N; i += CH_THREADS) xs[i] = xb[i];
+  for (int i = tid; i < 3 * M; i += CH_THREADS) ys[i] = yb[i];
+  __syncthreads();
+  const float INF = __int_as_float(0x7f800000);
+  float sum_m = 0.f, sum_n = 0.f;
+  for (int m = tid; m < M; m += CH_THREADS) {
+    const float a0 = ys[3 * m], a1 = ys[3 * m + 1], a2 = ys[3 * m + 2];
+    float best = INF;
+    for (int n = 0; n < N; ++n) {
+      const float d0 = xs[3 * n] - a0, d1 = xs[3 * n + 1] - a1, d2 = xs[3 * n + 2] - a2;
+      best = fminf(best, __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+    }
+    sum_m += __fsqrt_rn(best);
+  }
+  for (int n = tid; n < N; n += CH_THREADS) {
+    const float a0 = xs[3 * n], a1 = xs[3 * n + 1], a2 = xs[3 * n + 2];
+    float best = INF;
+    for (int m = 0; m < M; ++m) {
+      const float d0 = a0 - ys[3 * m], d1 = a1 - ys[3 * m + 1], d2 = a2 - ys[3 * m + 2];
+      best = fminf(best, __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+    }
+    sum_n += __fsqrt_rn(best);
+  }
+  const float tm = block_sum_256(sum_m, red), tn = block_sum_256(sum_n, red);
+  if (tid == 0) out[b] = tm / (float)M + tn / (float)N;
+}
+
+}  // namespace agx
+
+extern "C" int agx_chamfer(const float* x, const float* y, int32_t B, int32_t N, int32_t M, int32_t y_batched, float* out,
+                           agx_stream_t stream) {
+  using namespace agx;
+  AGX_REQUIRE(x && y && out, AGX_ERR_ARG, "chamfer: null pointer argument");
+  AGX_REQUIRE(B > 0 && N > 0 && M > 0, AGX_ERR_ARG, "chamfer: B=%d N=%d M=%d must be positive", B, N, M);
+  const size_t smem = (size_t)(N + M) * 12;
+  AGX_REQUIRE(smem <= 200 * 1024, AGX_ERR_ARG, "chamfer: N + M = %d exceeds the shared-memory staging limit (17066 points)", N + M);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static thread_local size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    AGX_CUDA_OK(cudaFuncSetAttribute(chamfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  { ProfScope ps(AGX_KIND_OTHER, st);
+    chamfer_kernel<<<B, CH_THREADS, smem, st>>>(x, y, N, M, y_batched ? (int64_t)M * 3 : 0, out); }
+  AGX_LAUNCH_CHECK();
+  return AGX_OK;
+}

@@ -515,21 +515,24 @@ constexpr int AGG_CTAS_PER_SM = 2;
 // this kernel plus a bulk L2 prefetch of the next group's C / Qr rows 0.389 (the memory system is request-throughput bound on the
 // 64-byte pieces of the blocked layout, not latency bound: more requests in flight only queue).
 __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_split_kernel(
-    const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send, int64_t rows, int N, int64_t E_cap,
+    const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send, int rows, int N, int E_cap,
     const float4* __restrict__ C, const float4* __restrict__ Qr, const float4* __restrict__ Qs, uint32_t* __restrict__ agg_split,
     int32_t* __restrict__ agg_exp, float* __restrict__ agg_max) {
   __shared__ int smax[3][AGG_NODES];
   const int slot = threadIdx.x / (FP / 4), j = threadIdx.x - slot * (FP / 4);
   if (threadIdx.x < 3 * AGG_NODES) (&smax[0][0])[threadIdx.x] = 0;
   __syncthreads();
-  const int64_t n_groups = (rows + AGG_NODES - 1) / AGG_NODES, G = gridDim.x;
-  // float4 j of a row in the blocked layout (tc_chain.cuh: blk_off)
-  const int64_t joff = (int64_t)(j >> 2) * (TILE * BLK_W / 4) + (j & 3);
-  auto at = [joff](const float4* m, int64_t row) { return __ldg(m + (row >> 7) * (TILE * FP / 4) + (row & (TILE - 1)) * (BLK_W / 4) + joff); };
-  auto load_bounds = [&](int64_t grp, int& beg, int& end) {   // [beg, end) of this thread's row in group grp (empty past the last row)
-    const int64_t r = grp * AGG_NODES + slot;
+  const int n_groups = (rows + AGG_NODES - 1) / AGG_NODES, G = gridDim.x;
+  // float4 j of a row in the blocked layout (tc_chain.cuh: blk_off), as a 32-bit float4 index (the host checks that it fits):
+  // row * 4 + (row / 128) * (128 * 160 / 4 - 128 * 4) + piece offset
+  const uint32_t joff = (uint32_t)(j >> 2) * (TILE * BLK_W / 4) + (j & 3);
+  auto at = [joff](const float4* m, int row) {
+    return __ldg(m + ((uint32_t)row * (BLK_W / 4) + ((uint32_t)row >> 7) * (TILE * FP / 4 - TILE * BLK_W / 4) + joff));
+  };
+  auto load_bounds = [&](int grp, int& beg, int& end) {   // [beg, end) of this thread's row in group grp (empty past the last row)
+    const int r = grp * AGG_NODES + slot;
     beg = end = 0;
-    if (grp < n_groups && r < rows) { beg = (int)min((int64_t)__ldg(row_ptr + r), E_cap); end = (int)min((int64_t)__ldg(row_ptr + r + 1), E_cap); }
+    if (grp < n_groups && r < rows) { beg = min(__ldg(row_ptr + r), E_cap); end = min(__ldg(row_ptr + r + 1), E_cap); }
   };
   auto load_senders = [&](int beg, int end, int (&s)[AGG_BATCH]) {   // first AGG_BATCH sender ids of [beg, end); slots past the end repeat the last
     const int n = min(end - beg, AGG_BATCH);
@@ -537,15 +540,15 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
     for (int u = 0; u < AGG_BATCH; ++u) s[u] = n > 0 ? __ldg(send + beg + min(u, n - 1)) : 0;
   };
 
-  int64_t grp = blockIdx.x;
+  int grp = blockIdx.x;
   int beg, end, beg1, end1, s[AGG_BATCH];
   load_bounds(grp, beg, end);
   load_bounds(grp + G, beg1, end1);
   load_senders(beg, end, s);
   for (int it = 0; grp < n_groups; grp += G, ++it) {
-    const int64_t r = grp * AGG_NODES + slot;
+    const int r = grp * AGG_NODES + slot;
     const bool valid = r < rows;
-    const int64_t gb = valid ? (r / N) * N : 0;
+    const int gb = valid ? (r / N) * N : 0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 c[AGG_BATCH], q[AGG_BATCH];
     const int n0 = min(end - beg, AGG_BATCH);
@@ -702,10 +705,13 @@ int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
 int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st) {
   using namespace tc;
   const int64_t rows = (int64_t)g->B * g->N;
+  // the kernel indexes float4s with 32 bits: 40 per row (68 GB of features per buffer at the limit)
+  AGX_REQUIRE(blk_rows(rows) * (FP / 4) < (1ll << 32) && blk_rows(g->E_cap) * (FP / 4) < (1ll << 32) && g->E_cap < (1ll << 31), AGX_ERR_ARG,
+              "edge_aggregate: %lld rows / %lld relations exceed the 32-bit feature index", (long long)rows, (long long)g->E_cap);
   const int64_t groups = (rows + AGG_NODES - 1) / AGG_NODES, resident = (int64_t)num_sms() * AGG_CTAS_PER_SM;
   { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
     edge_aggregate_split_kernel<<<(unsigned)(groups < resident ? groups : resident), AGG_THREADS, 0, st>>>(
-        g->row_ptr, g->send, rows, g->N, g->E_cap, reinterpret_cast<const float4*>(w.C), reinterpret_cast<const float4*>(w.Qr),
+        g->row_ptr, g->send, (int)rows, g->N, (int)g->E_cap, reinterpret_cast<const float4*>(w.C), reinterpret_cast<const float4*>(w.Qr),
         reinterpret_cast<const float4*>(w.Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max); }
   AGX_LAUNCH_CHECK();
   return AGX_OK;

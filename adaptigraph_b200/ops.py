@@ -163,6 +163,25 @@ def _(pos, n_points, start_idx, max_samples, radius):
     return pos.new_empty((B, max_samples), dtype=torch.int32), pos.new_empty((B,), dtype=torch.int32)
 
 
+@torch.library.custom_op("agx::chamfer", mutates_args=())
+def chamfer(x: Tensor, y: Tensor) -> Tensor:
+    """planning/losses.py:4-10: x (B,N,3), y (1,M,3) or (B,M,3) -> (B) symmetric mean-of-min distances."""
+    _need_cuda(x, y)
+    x, y = _f32(x), _f32(y)
+    B, N, D = x.shape
+    By, M, Dy = y.shape
+    if D != 3 or Dy != 3 or By not in (1, B):
+        raise ValueError(f"chamfer: expected x (B,N,3) and y (1|B,M,3), got {tuple(x.shape)} and {tuple(y.shape)}")
+    out = torch.empty(B, dtype=torch.float32, device=x.device)
+    L.check(lib.agx_chamfer(_ptr(x), _ptr(y), B, N, M, int(By == B and B > 1), _ptr(out), _stream()), "agx_chamfer")
+    return out
+
+
+@chamfer.register_fake
+def _(x, y):
+    return x.new_empty((x.shape[0],))
+
+
 # --------------------------------------------------------------------------- forward / rollout
 @torch.library.custom_op("agx::forward", mutates_args=())
 def forward(packed: Tensor, state: Tensor, attrs: Tensor, action: Tensor, p_instance: Tensor, physics: Tensor,

@@ -145,6 +145,12 @@ AGX_API int agx_edges_to_onehot(const int32_t* row_ptr, const int32_t* send, int
 AGX_API int agx_fps(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int32_t max_samples,
             const int32_t* start_idx, double radius, int32_t* idx_out, int32_t* n_out, agx_stream_t stream);
 
+/* ---- chamfer distance of the MPC error term (planning/losses.py:4-10, used at plan.py:36 / :146 on the rollout's frames):
+ * out[b] = mean_m min_n |x[b,n] - y[m]| + mean_n min_m |x[b,n] - y[m]|.  x (B,N,3); y (M,3) shared by every sample
+ * (y_batched = 0, the planner's target) or (B,M,3) (y_batched = 1); out (B).  N + M <= 17066. */
+AGX_API int agx_chamfer(const float* x, const float* y, int32_t B, int32_t N, int32_t M, int32_t y_batched, float* out,
+                agx_stream_t stream);
+
 /* ---- model forward (replaces model.py:129-313) */
 AGX_API size_t agx_forward_workspace_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap);
 /* pred_pos, pred_motion: (B, n_p, 3).  pos_stride_b: floats between consecutive graphs in

@@ -92,3 +92,34 @@ def dynamics_masked(p, pstep, state, state_mask, action, cfg):
     raise_ = 0.01 * cfg["ratio"] if cfg["gripper"] else 0.0
     return _step_capture(p, pstep, states, attrs, p_inst, dfull, phys, mask, eef_mask, cfg["thr"], cfg["topk"], cfg["cta"], rep,
                          "masked_mean", raise_), dec
+
+
+# ---------------------------------------------------------------------------------------------- reward terms
+def chamfer(x, y):
+    """planning/losses.py:4-10, line by line (CPU torch).  Pinned: tests/golden/rewards.npz holds the reference's outputs."""
+    x = x[:, None].repeat(1, y.shape[1], 1, 1)
+    y = y[:, :, None].repeat(1, 1, x.shape[2], 1)
+    dis = torch.norm(x - y, 2, dim=-1)
+    return torch.mean(dis.min(dim=2).values, dim=1) + torch.mean(dis.min(dim=1).values, dim=1)
+
+
+def running_cost(state, action, state_cur, error_func, penalty_func, bbox):
+    """planning/plan.py:27-59 restated (plan.py itself cannot be imported here: pyflex / GroundingDINO / SAM are absent).
+    PARITY UNPINNED for this function; every term it calls is pinned through tests/golden/rewards.npz."""
+    bsz, n_look_forward = state.shape[0], state.shape[1]
+    state_flat = state.reshape(bsz * n_look_forward, state.shape[2], state.shape[3])
+    error = error_func(state_flat).reshape(bsz, n_look_forward)
+    error_weight = 2. / (error.max().item() + 1e-6)
+    collision_penalty = penalty_func(state, action, state_cur)
+    xmax = state.max(dim=2).values[:, :, 0]
+    xmin = state.min(dim=2).values[:, :, 0]
+    zmax = state.max(dim=2).values[:, :, 2]
+    zmin = state.min(dim=2).values[:, :, 2]
+    box_penalty = torch.stack([
+        torch.maximum(xmin - bbox[0, 0], torch.zeros_like(xmin)),
+        torch.maximum(bbox[0, 1] - xmax, torch.zeros_like(xmax)),
+        torch.maximum(zmin - bbox[1, 0], torch.zeros_like(zmin)),
+        torch.maximum(bbox[1, 1] - zmax, torch.zeros_like(zmax)),
+    ], dim=-1)
+    box_penalty = torch.exp(-box_penalty * 100.).max(dim=-1).values
+    return -error_weight * error[:, -1] - 5. * collision_penalty.mean(dim=1) - 5. * box_penalty.mean(dim=1)
