@@ -298,6 +298,14 @@ def main():
     else:
         roof = {"kernel": top, "bound": "hbm", "achieved": byts / per / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": byts / per / 1e6 / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"]}
+    # DRAM traffic of that kernel per launch from the committed ncu --set full capture of this same command (profiles/ncu_traffic.json,
+    # written by tools/ncu_summary.py); only valid for the default workload
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and B == WORKLOAD["B"] and n_p == WORKLOAD["n_p"]:
+        tk = json.load(open(tpath))["kernels"].get(top)
+        if tk:
+            roof["traffic"] = tk["traffic_gb_per_launch"]
+            roof["traffic_unit"] = "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum; algorithmic: %.3f GB)" % (byts / 1e9)
     # whole-step view: stage-granular algorithmic bytes of SURVEY §8d over the measured step time
     Eg, = (E / B,)
     bytes_step = B * (N * (80 + 14 + 4 * F + K * 24 * F) + Eg * (16 + 4 * F + K * (4 * F + 8)) + n_p * (4 * F + 36) + 4)
