@@ -5,7 +5,7 @@ Importing the compute API loads libadaptigraph_b200.so and fails loudly if it is
 """
 __all__ = ["DynamicsPredictor", "EdgeList", "build_edges", "construct_edges_from_states",
            "construct_edges_from_states_batch", "edges_from_onehots", "pad_torch", "truncate_graph",
-           "fps", "fps_rad_idx", "farthest_point_sampler", "fps_batch"]
+           "fps", "fps_rad_idx", "farthest_point_sampler", "fps_batch", "relation_lists", "collate_relation_lists"]
 
 
 def __getattr__(name):
@@ -13,7 +13,7 @@ def __getattr__(name):
         from .model import DynamicsPredictor
         return DynamicsPredictor
     if name in ("EdgeList", "build_edges", "construct_edges_from_states", "construct_edges_from_states_batch",
-                "edges_from_onehots"):
+                "edges_from_onehots", "relation_lists", "collate_relation_lists"):
         from . import graph
         return getattr(graph, name)
     if name in ("pad_torch", "truncate_graph"):

@@ -504,24 +504,26 @@ __device__ __forceinline__ float4 relu_add3(const float4 c, const float4 qr, con
 
 // Persistent: CTA b handles the row groups b, b + grid, b + 2 grid, ... (AGG_NODES consecutive receivers each, 40 threads = one
 // float4 column each per receiver), so the grid sweeps a contiguous window of rows and of the CSR-ordered C.  The index data is
-// software-pipelined: a group's sender ids are requested one group ahead and its row_ptr pair two groups ahead, so per group a
-// thread waits for exactly one round trip -- the 2 * AGG_BATCH feature-row loads it has in flight.  Summation is in CSR order per
+// software-pipelined: a group's sender ids are copied into shared memory one group ahead (cp.async, so no register is tied up while
+// they are in flight) and its row_ptr pair is loaded two groups ahead, so per group a thread waits for exactly one round trip -- the
+// 2 * AGG_BATCH feature-row loads it has in flight.  Summation is in CSR order per
 // column (deterministic, no atomics on data); the row maximum goes through a triple-buffered shared-memory slot.
 constexpr int AGG_BATCH = 8;   // relations in flight per thread
 constexpr int AGG_CTAS_PER_SM = 2;
-// Measured on cloth-2k x 128 (B200, ms per launch): one CTA per 8 rows with 2 relations in flight 0.392; this kernel with
-// (batch, CTAs/SM) = (8, 2) 0.349, (4, 3) 0.386, (2, 4) 0.370, (6, 2) 0.436; visiting runs of 16 consecutive groups per CTA 0.387;
+// Measured on cloth-2k x 128 (B200, ms per launch): one CTA per 8 rows with 2 relations in flight 0.392; this kernel with the sender
+// ids prefetched into registers and 64-bit indexing, (batch, CTAs/SM) = (8, 2) 0.349 [32-bit indexing 0.332, ids through cp.async 0.308], (4, 3) 0.386, (2, 4) 0.370, (6, 2) 0.436; visiting runs of 16 consecutive groups per CTA 0.387;
 // a warp-per-row variant staging C through per-warp TMA rings 0.658 (150 instructions per relation: issue-latency bound);
 // this kernel plus a bulk L2 prefetch of the next group's C / Qr rows 0.389 (the memory system is request-throughput bound on the
-// 64-byte pieces of the blocked layout, not latency bound: more requests in flight only queue).
+// 64-byte pieces of the blocked layout, not latency bound: more requests in flight only queue); sweeping the rows in reverse so that
+// the most recently written C / Qr / Qs tiles are read first: no change (0.308 both ways).
 __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_split_kernel(
     const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send, int rows, int N, int E_cap,
     const float4* __restrict__ C, const float4* __restrict__ Qr, const float4* __restrict__ Qs, uint32_t* __restrict__ agg_split,
     int32_t* __restrict__ agg_exp, float* __restrict__ agg_max) {
   __shared__ int smax[3][AGG_NODES];
+  __shared__ __align__(16) int32_t ids[2][AGG_NODES][AGG_BATCH];   // first AGG_BATCH sender ids of every row of this / the next group
   const int slot = threadIdx.x / (FP / 4), j = threadIdx.x - slot * (FP / 4);
   if (threadIdx.x < 3 * AGG_NODES) (&smax[0][0])[threadIdx.x] = 0;
-  __syncthreads();
   const int n_groups = (rows + AGG_NODES - 1) / AGG_NODES, G = gridDim.x;
   // float4 j of a row in the blocked layout (tc_chain.cuh: blk_off), as a 32-bit float4 index (the host checks that it fits):
   // row * 4 + (row / 128) * (128 * 160 / 4 - 128 * 4) + piece offset
@@ -529,24 +531,27 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
   auto at = [joff](const float4* m, int row) {
     return __ldg(m + ((uint32_t)row * (BLK_W / 4) + ((uint32_t)row >> 7) * (TILE * FP / 4 - TILE * BLK_W / 4) + joff));
   };
-  auto load_bounds = [&](int grp, int& beg, int& end) {   // [beg, end) of this thread's row in group grp (empty past the last row)
-    const int r = grp * AGG_NODES + slot;
+  auto load_bounds = [&](int v, int& beg, int& end) {   // [beg, end) of this thread's row in group v (empty past the end)
+    const int r = v * AGG_NODES + slot;
     beg = end = 0;
-    if (grp < n_groups && r < rows) { beg = min(__ldg(row_ptr + r), E_cap); end = min(__ldg(row_ptr + r + 1), E_cap); }
+    if (v < n_groups && r < rows) { beg = min(__ldg(row_ptr + r), E_cap); end = min(__ldg(row_ptr + r + 1), E_cap); }
   };
-  auto load_senders = [&](int beg, int end, int (&s)[AGG_BATCH]) {   // first AGG_BATCH sender ids of [beg, end); slots past the end repeat the last
-    const int n = min(end - beg, AGG_BATCH);
-#pragma unroll
-    for (int u = 0; u < AGG_BATCH; ++u) s[u] = n > 0 ? __ldg(send + beg + min(u, n - 1)) : 0;
+  // threads j < AGG_BATCH of every row copy sender id j of [beg, end) straight into shared memory (cp.async: no register is tied up
+  // while the id is in flight); slots past the end are never read
+  auto stage_senders = [&](int buf, int beg, int end) {
+    if (j < AGG_BATCH && beg + j < end)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&ids[buf][slot][j])), "l"(send + beg + j) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  int grp = blockIdx.x;
-  int beg, end, beg1, end1, s[AGG_BATCH];
-  load_bounds(grp, beg, end);
-  load_bounds(grp + G, beg1, end1);
-  load_senders(beg, end, s);
-  for (int it = 0; grp < n_groups; grp += G, ++it) {
-    const int r = grp * AGG_NODES + slot;
+  int beg, end, beg1, end1;
+  load_bounds(blockIdx.x, beg, end);
+  load_bounds(blockIdx.x + G, beg1, end1);
+  stage_senders(0, beg, end);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  for (int it = 0, v = blockIdx.x; v < n_groups; v += G, ++it) {
+    const int r = v * AGG_NODES + slot;
     const bool valid = r < rows;
     const int gb = valid ? (r / N) * N : 0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -555,46 +560,48 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
     float4 qr = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) qr = at(Qr, r);
     if (n0 > 0) {
+      const int32_t* my = ids[it & 1][slot];
 #pragma unroll
       for (int u = 0; u < AGG_BATCH; ++u) {
-        c[u] = at(C, beg + min(u, n0 - 1));
-        q[u] = at(Qs, gb + s[u]);
+        const int uu = min(u, n0 - 1);                    // past-the-end slots repeat the last relation (masked below)
+        c[u] = at(C, beg + uu);
+        q[u] = at(Qs, gb + my[uu]);
       }
     }
     // index data of the groups to come (their latency hides behind this group's feature rows)
-    int s1[AGG_BATCH], beg2, end2;
-    load_senders(beg1, end1, s1);
-    load_bounds(grp + 2 * G, beg2, end2);
+    int beg2, end2;
+    stage_senders((it + 1) & 1, beg1, end1);
+    load_bounds(v + 2 * G, beg2, end2);
     if (n0 > 0) {
 #pragma unroll
       for (int u = 0; u < AGG_BATCH; ++u) {
         if (u < n0) {
-          const float4 v = relu_add3(c[u], qr, q[u]);
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          const float4 w = relu_add3(c[u], qr, q[u]);
+          acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
         }
       }
     }
     for (int e0 = beg + AGG_BATCH; e0 < end; e0 += AGG_BATCH) {   // rows with more than AGG_BATCH relations: further (unpipelined) batches
       const int n = min(end - e0, AGG_BATCH);
-      int sx[AGG_BATCH];
-      load_senders(e0, end, sx);
 #pragma unroll
       for (int u = 0; u < AGG_BATCH; ++u) {
-        c[u] = at(C, e0 + min(u, n - 1));
-        q[u] = at(Qs, gb + sx[u]);
+        const int uu = min(u, n - 1);
+        c[u] = at(C, e0 + uu);
+        q[u] = at(Qs, gb + __ldg(send + e0 + uu));
       }
 #pragma unroll
       for (int u = 0; u < AGG_BATCH; ++u) {
         if (u < n) {
-          const float4 v = relu_add3(c[u], qr, q[u]);
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          const float4 w = relu_add3(c[u], qr, q[u]);
+          acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
         }
       }
     }
     // agg >= 0 (sum of ReLUs): the int view of the floats orders like the floats
     int* mxs = smax[it % 3];
     if (valid) atomicMax(&mxs[slot], __float_as_int(fmaxf(fmaxf(acc.x, acc.y), fmaxf(acc.z, acc.w))));
-    __syncthreads();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // the next group's sender ids have landed ...
+    __syncthreads();                                       // ... and are visible to the whole CTA; row maxima complete
     if (threadIdx.x < AGG_NODES) smax[(it + 2) % 3][threadIdx.x] = 0;   // free since the previous barrier; next used after the next one
     if (valid) {
       const float mx = __int_as_float(mxs[slot]);
@@ -611,8 +618,6 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
       if (j == 0) { agg_exp[r] = e; agg_max[r] = mx; }
     }
     beg = beg1; end = end1; beg1 = beg2; end1 = end2;
-#pragma unroll
-    for (int u = 0; u < AGG_BATCH; ++u) s[u] = s1[u];
   }
 }
 

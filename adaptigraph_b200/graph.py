@@ -102,17 +102,34 @@ def edges_from_onehots(Rr: Tensor, Rs: Tensor) -> EdgeList:
     (agx_onehot_to_ids); ordering rows by receiver is a stable device sort, so relations of one
     receiver keep the caller's relative order.  No host synchronisation.
     """
-    B, n_rel, N = Rr.shape
-    dev = Rr.device
-    rid = ops.onehot_to_ids(Rr).long()
-    sid = ops.onehot_to_ids(Rs).long()
+    N = Rr.shape[2]
+    return collate_relation_lists(ops.onehot_to_ids(Rr), ops.onehot_to_ids(Rs), N, Rr.device)
+
+
+# ------------------------------------------------------------------------------------------ sparse sample format (data loading)
+def relation_lists(Rr, Rs):
+    """One sample's dense (n_rel, N) one-hots (CPU or CUDA, zero rows = padding, dataset.py:215-219) -> two int32 vectors
+    (receiver id, sender id per relation row, -1 on padding rows).  A pure format conversion (arg-max of one-hot rows): what a
+    DataLoader worker ships instead of 2 x max_nR x N floats (~0.8 MB -> ~4 kB per sample for the shipped configs)."""
+    def one(R):
+        idx = R.argmax(-1).to(torch.int32)
+        idx[R.sum(-1) == 0] = -1
+        return idx
+    return one(Rr), one(Rs)
+
+
+def collate_relation_lists(recv: Tensor, send: Tensor, N: int, device=None) -> EdgeList:
+    """Batched (B, n_rel) receiver / sender id lists (-1 = padding, any row order) -> EdgeList on `device` (default: current CUDA
+    device).  Same stable receiver sort as `edges_from_onehots`, so relations of one receiver keep the sample's order."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    rid, sid = recv.to(dev).long(), send.to(dev).long()
+    B = rid.shape[0]
     valid = (rid >= 0) & (sid >= 0)
     key = torch.where(valid, rid + torch.arange(B, device=dev)[:, None] * N, torch.full_like(rid, B * N)).reshape(-1)
     key_sorted, perm = torch.sort(key, stable=True)
     deg = torch.zeros(B * N + 1, dtype=torch.int64, device=dev).index_add_(0, key_sorted, torch.ones_like(key_sorted))[: B * N]
     row_ptr = torch.zeros(B * N + 1, dtype=torch.int32, device=dev)
     row_ptr[1:] = torch.cumsum(deg, 0).to(torch.int32)
-    send = sid.reshape(-1)[perm].clamp_(min=0).to(torch.int32).contiguous()
-    recv = key_sorted.clamp_(max=B * N - 1).to(torch.int32).contiguous()
-    n_edges = valid.sum(1).to(torch.int32)
-    return EdgeList(row_ptr, send, recv, n_edges, torch.zeros(1, dtype=torch.int32, device=dev), B, N)
+    send_out = sid.reshape(-1)[perm].clamp_(min=0).to(torch.int32).contiguous()
+    recv_out = key_sorted.clamp_(max=B * N - 1).to(torch.int32).contiguous()
+    return EdgeList(row_ptr, send_out, recv_out, valid.sum(1).to(torch.int32), torch.zeros(1, dtype=torch.int32, device=dev), B, N)

@@ -319,3 +319,17 @@ def test_mpc_drivers_match_reference(agx, name, precision):
     assert np.abs(out["state_seqs"].cpu().numpy() - c["state_seqs"]).max() <= 5e-5
     out = planning.dynamics_masked(torch.from_numpy(c["m_state"]), torch.from_numpy(c["m_mask"]), torch.from_numpy(c["action"][:, 0]), m, "cuda", ppm)
     assert np.abs(out["state_seqs"].cpu().numpy() - c["m_state_seqs"]).max() <= 5e-5
+
+
+def test_sparse_sample_format_equals_dense_path(agx):
+    """dataset.py:215-219 emits dense padded one-hots per sample; the list format a DataLoader can ship instead gives the same EdgeList."""
+    from adaptigraph_b200 import synthetic as syn
+    w = syn.make_workload("granular", 90, 4, seed=12, n_pad=7)
+    Rr, Rs = agx.build_edges(w.state[:, -1].cuda(), w.adj_thresh, w.state_mask.cuda(), w.eef_mask.cuda(), w.topk, w.connect_tools_all).to_dense(1500)
+    lists = [agx.relation_lists(Rr[b].cpu(), Rs[b].cpu()) for b in range(4)]        # what each worker would emit (CPU, per sample)
+    assert all(r.dtype == torch.int32 and r.shape == (1500,) for r, _ in lists)
+    el = agx.collate_relation_lists(torch.stack([r for r, _ in lists]), torch.stack([s for _, s in lists]), w.N)
+    ref = agx.edges_from_onehots(Rr, Rs)
+    E = int(ref.row_ptr[-1])
+    assert torch.equal(el.row_ptr, ref.row_ptr) and torch.equal(el.send[:E], ref.send[:E]) and torch.equal(el.recv[:E], ref.recv[:E])
+    assert torch.equal(el.n_edges, ref.n_edges)
