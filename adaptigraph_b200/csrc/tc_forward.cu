@@ -508,8 +508,12 @@ __device__ __forceinline__ float4 relu_add3(const float4 c, const float4 qr, con
 // they are in flight) and its row_ptr pair is loaded two groups ahead, so per group a thread waits for exactly one round trip -- the
 // 2 * AGG_BATCH feature-row loads it has in flight.  Summation is in CSR order per
 // column (deterministic, no atomics on data); the row maximum goes through a triple-buffered shared-memory slot.
-constexpr int AGG_BATCH = 8;   // relations in flight per thread
-constexpr int AGG_CTAS_PER_SM = 2;
+#ifndef AGX_AGG_BATCH
+#define AGX_AGG_BATCH 8
+#define AGX_AGG_CTAS 2
+#endif
+constexpr int AGG_BATCH = AGX_AGG_BATCH;   // relations in flight per thread
+constexpr int AGG_CTAS_PER_SM = AGX_AGG_CTAS;
 // Measured on cloth-2k x 128 (B200, ms per launch): one CTA per 8 rows with 2 relations in flight 0.392; this kernel with the sender
 // ids prefetched into registers and 64-bit indexing, (batch, CTAs/SM) = (8, 2) 0.349 [32-bit indexing 0.332, ids through cp.async 0.308], (4, 3) 0.386, (2, 4) 0.370, (6, 2) 0.436; visiting runs of 16 consecutive groups per CTA 0.387;
 // a warp-per-row variant staging C through per-warp TMA rings 0.658 (150 instructions per relation: issue-latency bound);

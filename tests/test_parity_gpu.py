@@ -333,3 +333,54 @@ def test_sparse_sample_format_equals_dense_path(agx):
     E = int(ref.row_ptr[-1])
     assert torch.equal(el.row_ptr, ref.row_ptr) and torch.equal(el.send[:E], ref.send[:E]) and torch.equal(el.recv[:E], ref.recv[:E])
     assert torch.equal(el.n_edges, ref.n_edges)
+
+
+def _cloud_cases():
+    """Geometries that stress the builder's cell grid: clamped grids (extent >> 64 radii), zero extent, one-axis clouds along each
+    axis, exact distance ties, a far outlier, masked particles with non-finite coordinates, more cells than particles."""
+    rng = np.random.default_rng(99)
+    cases = {}
+    cases["cube_sparse"] = (rng.uniform(-50, 50, (2, 3000, 3)), 1.5, 8)                    # 100 / 1.5 > 64 cells: widened cells
+    cases["cube_dense"] = (rng.uniform(0, 2, (2, 1500, 3)), 0.35, 20)
+    cases["coincident"] = (np.zeros((1, 60, 3)), 0.1, 10)                                   # zero extent, all distances tie at 0
+    for ax in range(3):
+        p = np.zeros((1, 400, 3))
+        p[0, :, ax] = np.sort(rng.uniform(0, 30, 400))
+        cases[f"line_axis{ax}"] = (p, 0.4, 6)
+    lattice = np.stack(np.meshgrid(np.arange(30.0), [0.0], np.arange(30.0), indexing="ij"), -1).reshape(1, -1, 3)
+    cases["lattice_ties"] = (lattice, 1.0001, 5)                                            # four equidistant neighbours each
+    far = rng.normal(0, 0.3, (2, 300, 3))
+    far[:, 7] = [1e4, -2e4, 3e4]
+    cases["far_outlier"] = (far, 0.25, 10)
+    cases["tiny_radius"] = (rng.uniform(0, 1, (1, 200, 3)), 1e-3, 4)                        # 64 x 64 cells for 200 particles
+    return cases
+
+
+@pytest.mark.parametrize("name", sorted(_cloud_cases()))
+@pytest.mark.parametrize("cta,sem", [(False, 0), (True, 0), (True, 1)])
+def test_graph_build_cell_grid_stress_matches_c_oracle(agx, name, cta, sem):
+    from adaptigraph_b200 import _lib as L
+    from adaptigraph_b200 import ops
+    from oracle import build_oracle
+    pos, thr, topk = _cloud_cases()[name]
+    pos = torch.from_numpy(pos.astype(np.float32))
+    B, N, _ = pos.shape
+    rng = np.random.default_rng(5)
+    mask = torch.ones(B, N, dtype=torch.bool)
+    mask[:, rng.choice(N, max(1, N // 10), replace=False)] = False                          # padded / invalid particles ...
+    tool = torch.zeros(B, N, dtype=torch.bool)
+    tool[:, -3:] = True
+    mask[:, -3:] = True
+    pos_dev = pos.clone()
+    pos_dev[~mask] = float("nan")                                                           # ... whose coordinates must never matter
+    pos[~mask] = 0.0
+    thr2 = np.float32(thr) * np.float32(thr)
+    recv, send, n_edges = build_oracle.edges(pos.numpy(), mask.numpy(), tool.numpy(), thr2, topk, cta, sem)
+    cap = B * N * (min(topk, N) + 3)
+    row_ptr, s, r, ne, status = ops.graph_build(pos_dev.cuda(), mask.cuda(), tool.cuda(), torch.full((B,), float(thr2)).cuda(), topk, cta,
+                                                L.AGX_SEM_SINGLE if sem else L.AGX_SEM_BATCH, cap)
+    assert int(status.item()) == 0
+    E = int(row_ptr[-1])
+    assert E == recv.shape[0] and np.array_equal(ne.cpu().numpy(), n_edges)
+    assert np.array_equal(s[:E].cpu().numpy(), send)
+    assert np.array_equal(r[:E].cpu().numpy() % N, recv)
