@@ -56,7 +56,10 @@ constexpr int TARGET_EXP = 14;                          // scaled operands satis
 // tensor-core layer ids (order of the fp16 images in the packed blob)
 enum TcLayer {
   T_PENC0 = 0, T_PENC2, T_PENC4, T_RENC0, T_RENC2, T_RENC4, T_RP_REL, T_RP_RECV, T_RP_SEND, T_PP_ENC, T_PP_AGG,
-  T_PRED0, T_PRED1, T_NUM
+  T_PRED0, T_PRED1,
+  // transposed images (element (j, n) = W[n][j], no bias column): the B operands of the backward's dX = dY * W products
+  TT_PENC2, TT_PENC4, TT_RENC0, TT_RENC2, TT_RENC4, TT_RP_REL, TT_RP_RECV, TT_RP_SEND, TT_PP_ENC, TT_PP_AGG, TT_PRED0, TT_PRED1,
+  T_NUM
 };
 __host__ __device__ constexpr int tc_kpad(int t) { return t == T_PENC0 ? 16 : (t == T_RENC0 ? 32 : FP); }
 

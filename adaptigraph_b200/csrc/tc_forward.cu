@@ -12,6 +12,7 @@ constexpr float MOTION_CLAMP = 100.f;  // model.py:85
 // ------------------------------------------------------------------------------------ weight images
 struct PackSpec {
   const float* W; const float* bias; int ld, col0, K, F;   // source: W[n*ld + col0 + k], n < F, k < K
+  int transpose;                                            // 1: source W[k*ld + col0 + n] instead (image of the transposed matrix)
 };
 struct PackArgs {
   PackSpec spec[T_NUM];
@@ -27,10 +28,11 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
   const int kpad = tc_kpad(t);
   // the bias occupies the first padding column (k = K): it is multiplied by the constant 1 every A row carries there
   float wmax = 0.f, smax = 0.f;
+  auto src = [&](int n, int k) { return s.transpose ? s.W[(size_t)k * s.ld + s.col0 + n] : s.W[(size_t)n * s.ld + s.col0 + k]; };
   for (int n = tid; n < s.F; n += 256) {
     float rs = 0.f;
     for (int k = 0; k < s.K; ++k) {
-      const float w = fabsf(s.W[(size_t)n * s.ld + s.col0 + k]);
+      const float w = fabsf(src(n, k));
       wmax = fmaxf(wmax, w);
       rs += w;
     }
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const PackArgs a) {
     const int n = i / kpad, k = i - n * kpad;
     float v = 0.f;
     if (n < s.F) {
-      if (k < s.K) v = s.W[(size_t)n * s.ld + s.col0 + k] * sc;
+      if (k < s.K) v = src(n, k) * sc;
       else if (k == s.K && s.bias) v = s.bias[n] * sc;
     }
     const __half h = __float2half_rn(v);
@@ -490,6 +492,107 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
   chain_teardown(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------ single dense layer (training path)
+// Y[m][0:160] (+)= [relu]( (X[m][0:160] (*) [mask[m][k] > 0]) * W + bias + add1[m] + add2[m] )  — the contract of train.cu's
+// lin_kernel<160>, with the product on the tensor cores (same split-fp16 scheme, same 128-row tiles and two slots per CTA as the
+// chains above; rows are plain row-major fp32 here because that is what the backward kernels read).  `layer` selects the weight
+// image: a T_* image for a forward product (its bias column is switched off: the fp32 bias is added in the epilogue) or a TT_*
+// image (transposed matrix) for the backward's dX = dY * W.
+struct LinTcArgs {
+  const float* X; int ldx;
+  const float* mask; int ldm;
+  const float* bias; const float* add1; const float* add2;
+  float* Y; int ldy;
+  int64_t M;
+  int relu, accumulate, n_store, layer;
+  const uint8_t* blob; TcLayout L;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) tc_lin_kernel(const LinTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const LayerStep prog[1] = {{a.layer, 10, IN_PRODUCER}};
+  Shared sh;
+  float4 meta[1];
+  const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, meta);
+  const int n_tiles = (int)((a.M + TILE - 1) / TILE);
+  const int warp = threadIdx.x >> 5;
+  if (warp >= EPI_WARPS) {
+    reg_dealloc_other();
+    if (warp == LOAD_WARP) loader_role(sh, prog, a.blob, a.L, n_tiles, 20);
+    else if (warp < LOAD_WARP) mma_role(sh, prog, warp - MMA_WARP0, tmem_base, n_tiles, 20);
+  } else {
+    reg_alloc_epilogue();
+    EpiCtx cx = make_ctx(tmem_base);
+    int tile = slot_tile(0, cx.slot, n_tiles);
+    for (int k = 0; tile >= 0; ++k) {
+      const int64_t r = (int64_t)tile * TILE + cx.row;
+      const bool valid = r < a.M;
+      const float* xrow = a.X + r * a.ldx;
+      const float* mrow = a.mask ? a.mask + r * a.ldm : nullptr;
+      // this thread's 16 columns of chunk c, masked; columns >= 150 (padding, and the image's bias column) are forced to zero
+      auto load_piece = [&](int c, float (&v)[HW]) {
+        const int col0 = 32 * c + HW * cx.half;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) {
+            x = *reinterpret_cast<const float4*>(xrow + col0 + 4 * q);
+            if (mrow) {
+              const float4 m = *reinterpret_cast<const float4*>(mrow + col0 + 4 * q);
+              x.x = m.x > 0.f ? x.x : 0.f; x.y = m.y > 0.f ? x.y : 0.f; x.z = m.z > 0.f ? x.z : 0.f; x.w = m.w > 0.f ? x.w : 0.f;
+            }
+          }
+          v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        }
+        if (c == NCHUNK - 1 && cx.half == 1) {
+#pragma unroll
+          for (int i = ONE_COL % HW; i < HW; ++i) v[i] = 0.f;
+        }
+      };
+      // ---- producer, pass 1: row maximum -> exact power-of-two scale; pass 2: split into the slot's A (second read hits L1 / L2)
+      float mx = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        float v[HW];
+        load_piece(c, v);
+        mx = max16(v, mx);
+      }
+      mx = epi_exchange<true>(sh, cx, mx);
+      cx.e_in = scale_exp(mx);
+      cx.bound_in = mx;
+      const float sc = exp2i(cx.e_in);
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        float v[HW];
+        load_piece(c, v);
+        epi_store_a(cx, c, v, sc);
+      }
+      epi_signal(cx, &sh.bar_in[cx.slot]);
+      // ---- epilogue
+      const float unscale = exp2i(-cx.e_in) * meta[0].x;
+      float* yrow = a.Y + r * a.ldy;
+      epi_layer_out<false>(sh, cx, unscale, [&](int, int col0, float (&v)[HW]) {
+        if (!valid) return;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col = col0 + 4 * q;
+          if (col >= a.n_store) continue;                     // n_store is a multiple of 4
+          float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          if (a.bias) { const float4 b = *reinterpret_cast<const float4*>(a.bias + col); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+          if (a.add1) { const float4 b = *reinterpret_cast<const float4*>(a.add1 + r * FP + col); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+          if (a.add2) { const float4 b = *reinterpret_cast<const float4*>(a.add2 + r * FP + col); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+          if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          float4* y = reinterpret_cast<float4*>(yrow + col);
+          if (a.accumulate) { const float4 p = *y; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+          *y = o;
+        }
+      });
+      tile = slot_tile(k + 1, cx.slot, n_tiles);
+    }
+  }
+  chain_teardown(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------ edge aggregate (split output)
 // Same reduction as forward.cu's edge_aggregate_kernel, but the row leaves the kernel the way the update chain's
 // tensor-memory A wants it: scaled by an exact per-row power of two and split into packed fp16 hi / lo columns.
@@ -638,7 +741,11 @@ int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_
   AGX_REQUIRE(d_node == 6 && d_rel == 17 && F == ONE_COL, AGX_ERR_ARG, "tc_pack: the tensor-core path is built for 6/17/150 input dims");
   PackArgs a;
   auto set = [&](int t, int layer, int ld, int col0, int K, bool bias) {
-    a.spec[t] = PackSpec{raw->weight[layer], bias ? raw->bias[layer] : nullptr, ld, col0, K, F};
+    a.spec[t] = PackSpec{raw->weight[layer], bias ? raw->bias[layer] : nullptr, ld, col0, K, F, 0};
+  };
+  // transposed: n_out = columns of the original block (the layer's inputs), K = its F rows
+  auto set_t = [&](int t, int layer, int ld, int col0, int n_out) {
+    a.spec[t] = PackSpec{raw->weight[layer], nullptr, ld, col0, F, n_out, 1};
   };
   set(T_PENC0, AGX_W_PENC0, d_node, 0, d_node, true);
   set(T_PENC2, AGX_W_PENC2, F, 0, F, true);
@@ -653,6 +760,18 @@ int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_
   set(T_PP_AGG, AGX_W_PPROP, 2 * F, F, F, false);
   set(T_PRED0, AGX_W_PRED0, F, 0, F, true);
   set(T_PRED1, AGX_W_PRED1, F, 0, F, true);
+  set_t(TT_PENC2, AGX_W_PENC2, F, 0, F);
+  set_t(TT_PENC4, AGX_W_PENC4, F, 0, F);
+  set_t(TT_RENC0, AGX_W_RENC0, d_rel, 0, d_rel);
+  set_t(TT_RENC2, AGX_W_RENC2, F, 0, F);
+  set_t(TT_RENC4, AGX_W_RENC4, F, 0, F);
+  set_t(TT_RP_REL, AGX_W_RPROP, 3 * F, 0, F);
+  set_t(TT_RP_RECV, AGX_W_RPROP, 3 * F, F, F);
+  set_t(TT_RP_SEND, AGX_W_RPROP, 3 * F, 2 * F, F);
+  set_t(TT_PP_ENC, AGX_W_PPROP, 2 * F, 0, F);
+  set_t(TT_PP_AGG, AGX_W_PPROP, 2 * F, F, F);
+  set_t(TT_PRED0, AGX_W_PRED0, F, 0, F);
+  set_t(TT_PRED1, AGX_W_PRED1, F, 0, F);
   a.blob = static_cast<uint8_t*>(packed);
   a.L = tc_layout(base_bytes);
   { ProfScope ps(AGX_KIND_OTHER, st);
@@ -680,6 +799,7 @@ static int tc_ensure_attrs() {
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute(tc_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   done = true;
   return AGX_OK;
 }
@@ -707,6 +827,23 @@ int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
              w.C};
   { ProfScope ps(AGX_KIND_EDGE_ENCODER, st);
     tc_edge_encoder_kernel<<<(int)(tiles < num_sms() ? tiles : num_sms()), THREADS, SMEM_BYTES, st>>>(a); }
+  AGX_LAUNCH_CHECK();
+  return AGX_OK;
+}
+
+// Tensor-core replacement of train.cu's lin<160> (see tc_lin_kernel); `packed` is the blob written by agx_pack_weights.
+int tc_lin(cudaStream_t st, const void* packed, size_t base_bytes, int layer, const float* X, int ldx, const float* mask, int ldm,
+           const float* bias, const float* add1, const float* add2, float* Y, int ldy, int64_t M, bool relu, bool accumulate, int n_store) {
+  using namespace tc;
+  if (M <= 0) return AGX_OK;
+  if (int rc = tc_ensure_attrs()) return rc;
+  AGX_REQUIRE(layer >= 0 && layer < T_NUM && tc_kpad(layer) == FP && n_store % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (!mask || ldm % 4 == 0),
+              AGX_ERR_ARG, "tc_lin: unsupported layer / strides");
+  LinTcArgs a{X, ldx, mask, ldm, bias, add1, add2, Y, ldy, M, relu ? 1 : 0, accumulate ? 1 : 0, n_store, layer,
+              reinterpret_cast<const uint8_t*>(packed), tc_layout(base_bytes)};
+  const int64_t tiles = (M + TILE - 1) / TILE;
+  { ProfScope ps(AGX_KIND_OTHER, st);
+    tc_lin_kernel<<<(int)(tiles < num_sms() ? tiles : num_sms()), THREADS, SMEM_BYTES, st>>>(a); }
   AGX_LAUNCH_CHECK();
   return AGX_OK;
 }

@@ -16,6 +16,7 @@
 // with respect to `state` (BPTT through the history features and pred_pos = state[:, -1] + ...).
 #include "common.cuh"
 #include "mlp_simt.cuh"
+#include "tc_chain.cuh"
 
 namespace agx {
 
@@ -496,6 +497,22 @@ static int lin(cudaStream_t st, const float* X, int ldx, const float* mask, int 
   return AGX_OK;
 }
 
+// 160 -> 160 layers: tensor-core tiles (tc_forward.cu: tc_lin_kernel, split-fp16 products at fp32 accuracy) unless
+// AGX_TRAIN_PRECISION=fp32 asks for the exact FFMA tiles above.  `layer` names the fp16 image of the same matrix inside `packed`.
+int tc_lin(cudaStream_t st, const void* packed, size_t base_bytes, int layer, const float* X, int ldx, const float* mask, int ldm,
+           const float* bias, const float* add1, const float* add2, float* Y, int ldy, int64_t M, bool relu, bool accumulate, int n_store);
+static bool train_use_tc() {
+  static const bool v = [] { const char* e = getenv("AGX_TRAIN_PRECISION"); return !(e && !strcmp(e, "fp32")); }();
+  return v;
+}
+static int lin160(cudaStream_t st, const float* packed, int layer, const float* X, int ldx, const float* mask, int ldm, const float* Wt,
+                  const float* bias, const float* add1, const float* add2, float* Y, int ldy, int64_t M, bool relu, bool accumulate,
+                  int n_store = FP) {
+  if (train_use_tc())
+    return tc_lin(st, packed, packed_layout().total * sizeof(float), layer, X, ldx, mask, ldm, bias, add1, add2, Y, ldy, M, relu, accumulate, n_store);
+  return lin<FP>(st, X, ldx, mask, ldm, Wt, bias, add1, add2, Y, ldy, M, relu, accumulate, n_store);
+}
+
 // dW (reference layout, += ) and optional db from dY (masked by act > 0) and the layer input X
 static int wgrad(cudaStream_t st, const float* dY, const float* mask, const float* X, int ldx, int kx, int64_t M, float* part, int F, int K,
                  int ld, int col0, float* dW, float* db) {
@@ -567,28 +584,28 @@ int agx_forward_train(const AgxModelDims* dims, const void* packed_weights, cons
                                                                    s.nfeat, s.p_in);
   AGX_LAUNCH_CHECK();
   AGX_TRY(lin<D_NODE_IN>(st, s.p_in, D_NODE_IN, nullptr, 0, W + L.penc0_w, W + L.penc0_b, nullptr, nullptr, s.h1, FP, rows, true, false));
-  AGX_TRY(lin<FP>(st, s.h1, FP, nullptr, 0, W + L.penc2_w, W + L.penc2_b, nullptr, nullptr, s.h2, FP, rows, true, false));
-  AGX_TRY(lin<FP>(st, s.h2, FP, nullptr, 0, W + L.penc4_w, W + L.penc4_b, nullptr, nullptr, s.penc, FP, rows, true, false));
-  AGX_TRY(lin<FP>(st, s.penc, FP, nullptr, 0, W + L.pp_enc_w, W + L.pp_b, nullptr, nullptr, s.A, FP, rows, false, false));
+  AGX_TRY(lin160(st, W, tc::T_PENC2, s.h1, FP, nullptr, 0, W + L.penc2_w, W + L.penc2_b, nullptr, nullptr, s.h2, FP, rows, true, false));
+  AGX_TRY(lin160(st, W, tc::T_PENC4, s.h2, FP, nullptr, 0, W + L.penc4_w, W + L.penc4_b, nullptr, nullptr, s.penc, FP, rows, true, false));
+  AGX_TRY(lin160(st, W, tc::T_PP_ENC, s.penc, FP, nullptr, 0, W + L.pp_enc_w, W + L.pp_b, nullptr, nullptr, s.A, FP, rows, false, false));
   if (g->E_cap > 0) {
     edge_prep_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(g->row_ptr, g->send, g->recv, rows, g->N, g->E_cap, s.nfeat, s.rel_in);
     AGX_LAUNCH_CHECK();
     AGX_TRY(lin<D_REL_IN>(st, s.rel_in, D_REL_IN, nullptr, 0, W + L.renc0_w, W + L.renc0_b, nullptr, nullptr, s.g1, FP, E, true, false));
-    AGX_TRY(lin<FP>(st, s.g1, FP, nullptr, 0, W + L.renc2_w, W + L.renc2_b, nullptr, nullptr, s.g2, FP, E, true, false));
-    AGX_TRY(lin<FP>(st, s.g2, FP, nullptr, 0, W + L.renc4_w, W + L.renc4_b, nullptr, nullptr, s.renc, FP, E, true, false));
-    AGX_TRY(lin<FP>(st, s.renc, FP, nullptr, 0, W + L.rp_rel_w, W + L.rp_b, nullptr, nullptr, s.C, FP, E, false, false));
+    AGX_TRY(lin160(st, W, tc::T_RENC2, s.g1, FP, nullptr, 0, W + L.renc2_w, W + L.renc2_b, nullptr, nullptr, s.g2, FP, E, true, false));
+    AGX_TRY(lin160(st, W, tc::T_RENC4, s.g2, FP, nullptr, 0, W + L.renc4_w, W + L.renc4_b, nullptr, nullptr, s.renc, FP, E, true, false));
+    AGX_TRY(lin160(st, W, tc::T_RP_REL, s.renc, FP, nullptr, 0, W + L.rp_rel_w, W + L.rp_b, nullptr, nullptr, s.C, FP, E, false, false));
   }
   for (int k = 0; k < K; ++k) {
-    AGX_TRY(lin<FP>(st, s.P[k], FP, nullptr, 0, W + L.rp_recv_w, nullptr, nullptr, nullptr, s.Qr[k], FP, rows, false, false));
-    AGX_TRY(lin<FP>(st, s.P[k], FP, nullptr, 0, W + L.rp_send_w, nullptr, nullptr, nullptr, s.Qs[k], FP, rows, false, false));
+    AGX_TRY(lin160(st, W, tc::T_RP_RECV, s.P[k], FP, nullptr, 0, W + L.rp_recv_w, nullptr, nullptr, nullptr, s.Qr[k], FP, rows, false, false));
+    AGX_TRY(lin160(st, W, tc::T_RP_SEND, s.P[k], FP, nullptr, 0, W + L.rp_send_w, nullptr, nullptr, nullptr, s.Qs[k], FP, rows, false, false));
     train_aggregate_kernel<<<(unsigned)((rows + TA_NODES - 1) / TA_NODES), TA_THREADS, 0, st>>>(
         g->row_ptr, g->send, rows, g->N, g->E_cap, reinterpret_cast<const float4*>(s.C), reinterpret_cast<const float4*>(s.Qr[k]),
         reinterpret_cast<const float4*>(s.Qs[k]), reinterpret_cast<float4*>(s.agg[k]));
     AGX_LAUNCH_CHECK();
-    AGX_TRY(lin<FP>(st, s.agg[k], FP, nullptr, 0, W + L.pp_agg_w, nullptr, s.A, s.P[k], s.P[k + 1], FP, rows, true, false));
+    AGX_TRY(lin160(st, W, tc::T_PP_AGG, s.agg[k], FP, nullptr, 0, W + L.pp_agg_w, nullptr, s.A, s.P[k], s.P[k + 1], FP, rows, true, false));
   }
-  AGX_TRY(lin<FP>(st, s.P[K], FP, nullptr, 0, W + L.pred0_w, W + L.pred0_b, nullptr, nullptr, s.u1, FP, rows, true, false));
-  AGX_TRY(lin<FP>(st, s.u1, FP, nullptr, 0, W + L.pred1_w, W + L.pred1_b, nullptr, nullptr, s.u2, FP, rows, true, false));
+  AGX_TRY(lin160(st, W, tc::T_PRED0, s.P[K], FP, nullptr, 0, W + L.pred0_w, W + L.pred0_b, nullptr, nullptr, s.u1, FP, rows, true, false));
+  AGX_TRY(lin160(st, W, tc::T_PRED1, s.u1, FP, nullptr, 0, W + L.pred1_w, W + L.pred1_b, nullptr, nullptr, s.u2, FP, rows, true, false));
   head_out_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(s.u2, W + L.pred2_w, g->state, g->B, g->N, g->n_p, pred_pos, pos_stride_b, pred_motion);
   AGX_LAUNCH_CHECK();
   return AGX_OK;
@@ -626,9 +643,9 @@ int agx_backward(const AgxModelDims* dims, const void* packed_weights, const Agx
     AGX_LAUNCH_CHECK();
   }
   AGX_TRY(wgrad(st, t.dU, s.u2, s.u1, FP, FP, rows, t.part, F, F, F, 0, gw[AGX_W_PRED1], gb[AGX_W_PRED1]));
-  AGX_TRY(lin<FP>(st, t.dU, FP, s.u2, FP, W + T.pred1, nullptr, nullptr, nullptr, t.dV, FP, rows, false, false));          // dU1
+  AGX_TRY(lin160(st, W, tc::TT_PRED1, t.dU, FP, s.u2, FP, W + T.pred1, nullptr, nullptr, nullptr, t.dV, FP, rows, false, false));          // dU1
   AGX_TRY(wgrad(st, t.dV, s.u1, s.P[K], FP, FP, rows, t.part, F, F, F, 0, gw[AGX_W_PRED0], gb[AGX_W_PRED0]));
-  AGX_TRY(lin<FP>(st, t.dV, FP, s.u1, FP, W + T.pred0, nullptr, nullptr, nullptr, t.dP, FP, rows, false, false));          // dP_K
+  AGX_TRY(lin160(st, W, tc::TT_PRED0, t.dV, FP, s.u1, FP, W + T.pred0, nullptr, nullptr, nullptr, t.dP, FP, rows, false, false));          // dP_K
 
   // ---- propagation steps, last to first
   for (int k = K - 1; k >= 0; --k) {
@@ -638,7 +655,7 @@ int agx_backward(const AgxModelDims* dims, const void* packed_weights, const Agx
     AGX_LAUNCH_CHECK();
     add_rows_kernel<<<(unsigned)((rows * FP + 255) / 256), 256, 0, st>>>(t.dA, t.dP, rows * FP);
     AGX_LAUNCH_CHECK();
-    AGX_TRY(lin<FP>(st, t.dP, FP, nullptr, 0, W + T.pp_agg, nullptr, nullptr, nullptr, t.dAgg, FP, rows, false, false));
+    AGX_TRY(lin160(st, W, tc::TT_PP_AGG, t.dP, FP, nullptr, 0, W + T.pp_agg, nullptr, nullptr, nullptr, t.dAgg, FP, rows, false, false));
     if (g->E_cap > 0) {
       effect_bwd_recv_kernel<<<(unsigned)((rows + TA_NODES - 1) / TA_NODES), TA_THREADS, 0, st>>>(
           g->row_ptr, g->send, rows, g->N, g->E_cap, reinterpret_cast<const float4*>(s.C), reinterpret_cast<const float4*>(s.Qr[k]),
@@ -652,28 +669,28 @@ int agx_backward(const AgxModelDims* dims, const void* packed_weights, const Agx
       AGX_TRY(wgrad(st, t.dQr, nullptr, s.P[k], FP, FP, rows, t.part, F, F, 3 * F, F, gw[AGX_W_RPROP], nullptr));
       AGX_TRY(wgrad(st, t.dQs, nullptr, s.P[k], FP, FP, rows, t.part, F, F, 3 * F, 2 * F, gw[AGX_W_RPROP], nullptr));
       // dP_k = d pre_n (residual) + dQr*W_recv + dQs*W_send   (accumulated in place: dP already holds d pre_n)
-      AGX_TRY(lin<FP>(st, t.dQr, FP, nullptr, 0, W + T.rp_recv, nullptr, nullptr, nullptr, t.dP, FP, rows, false, true));
-      AGX_TRY(lin<FP>(st, t.dQs, FP, nullptr, 0, W + T.rp_send, nullptr, nullptr, nullptr, t.dP, FP, rows, false, true));
+      AGX_TRY(lin160(st, W, tc::TT_RP_RECV, t.dQr, FP, nullptr, 0, W + T.rp_recv, nullptr, nullptr, nullptr, t.dP, FP, rows, false, true));
+      AGX_TRY(lin160(st, W, tc::TT_RP_SEND, t.dQs, FP, nullptr, 0, W + T.rp_send, nullptr, nullptr, nullptr, t.dP, FP, rows, false, true));
     }
   }
   // ---- encoders: d penc = dP_0 + dA * W_enc
   AGX_TRY(wgrad(st, t.dA, nullptr, s.penc, FP, FP, rows, t.part, F, F, 2 * F, 0, gw[AGX_W_PPROP], gb[AGX_W_PPROP]));
-  AGX_TRY(lin<FP>(st, t.dA, FP, nullptr, 0, W + T.pp_enc, nullptr, nullptr, nullptr, t.dP, FP, rows, false, true));
+  AGX_TRY(lin160(st, W, tc::TT_PP_ENC, t.dA, FP, nullptr, 0, W + T.pp_enc, nullptr, nullptr, nullptr, t.dP, FP, rows, false, true));
   AGX_TRY(wgrad(st, t.dP, s.penc, s.h2, FP, FP, rows, t.part, F, F, F, 0, gw[AGX_W_PENC4], gb[AGX_W_PENC4]));
-  AGX_TRY(lin<FP>(st, t.dP, FP, s.penc, FP, W + T.penc4, nullptr, nullptr, nullptr, t.dU, FP, rows, false, false));        // dH2
+  AGX_TRY(lin160(st, W, tc::TT_PENC4, t.dP, FP, s.penc, FP, W + T.penc4, nullptr, nullptr, nullptr, t.dU, FP, rows, false, false));        // dH2
   AGX_TRY(wgrad(st, t.dU, s.h2, s.h1, FP, FP, rows, t.part, F, F, F, 0, gw[AGX_W_PENC2], gb[AGX_W_PENC2]));
-  AGX_TRY(lin<FP>(st, t.dU, FP, s.h2, FP, W + T.penc2, nullptr, nullptr, nullptr, t.dV, FP, rows, false, false));          // dH1
+  AGX_TRY(lin160(st, W, tc::TT_PENC2, t.dU, FP, s.h2, FP, W + T.penc2, nullptr, nullptr, nullptr, t.dV, FP, rows, false, false));          // dH1
   AGX_TRY(wgrad(st, t.dV, s.h1, s.p_in, D_NODE_IN, D_NODE_IN, rows, t.part, F, d_node, d_node, 0, gw[AGX_W_PENC0], gb[AGX_W_PENC0]));
   if (g->E_cap > 0) {
     AGX_TRY(wgrad(st, t.dC, nullptr, s.renc, FP, FP, E, t.part, F, F, 3 * F, 0, gw[AGX_W_RPROP], gb[AGX_W_RPROP]));
-    AGX_TRY(lin<FP>(st, t.dC, FP, nullptr, 0, W + T.rp_rel, nullptr, nullptr, nullptr, t.dE, FP, E, false, false));         // dRenc
+    AGX_TRY(lin160(st, W, tc::TT_RP_REL, t.dC, FP, nullptr, 0, W + T.rp_rel, nullptr, nullptr, nullptr, t.dE, FP, E, false, false));         // dRenc
     AGX_TRY(wgrad(st, t.dE, s.renc, s.g2, FP, FP, E, t.part, F, F, F, 0, gw[AGX_W_RENC4], gb[AGX_W_RENC4]));
-    AGX_TRY(lin<FP>(st, t.dE, FP, s.renc, FP, W + T.renc4, nullptr, nullptr, nullptr, t.dC, FP, E, false, false));          // dG2 (dC is free now)
+    AGX_TRY(lin160(st, W, tc::TT_RENC4, t.dE, FP, s.renc, FP, W + T.renc4, nullptr, nullptr, nullptr, t.dC, FP, E, false, false));          // dG2 (dC is free now)
     AGX_TRY(wgrad(st, t.dC, s.g2, s.g1, FP, FP, E, t.part, F, F, F, 0, gw[AGX_W_RENC2], gb[AGX_W_RENC2]));
-    AGX_TRY(lin<FP>(st, t.dC, FP, s.g2, FP, W + T.renc2, nullptr, nullptr, nullptr, t.dE, FP, E, false, false));            // dG1
+    AGX_TRY(lin160(st, W, tc::TT_RENC2, t.dC, FP, s.g2, FP, W + T.renc2, nullptr, nullptr, nullptr, t.dE, FP, E, false, false));            // dG1
     AGX_TRY(wgrad(st, t.dE, s.g1, s.rel_in, D_REL_IN, D_REL_IN, E, t.part, F, d_rel, d_rel, 0, gw[AGX_W_RENC0], gb[AGX_W_RENC0]));
     if (d_state)
-      AGX_TRY(lin<FP>(st, t.dE, FP, s.g1, FP, W + T.renc0, nullptr, nullptr, nullptr, t.dRel, D_REL_IN, E, false, false, D_REL_IN));   // d rel_in
+      AGX_TRY(lin160(st, W, tc::TT_RENC0, t.dE, FP, s.g1, FP, W + T.renc0, nullptr, nullptr, nullptr, t.dRel, D_REL_IN, E, false, false, D_REL_IN));   // d rel_in
   }
   if (d_state) {
     if (g->E_cap == 0) AGX_CUDA_OK(cudaMemsetAsync(t.dRel, 0, sizeof(float), st));
