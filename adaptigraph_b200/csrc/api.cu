@@ -3,6 +3,7 @@
 
 #include <vector>
 
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace agx {
@@ -25,6 +26,9 @@ int64_t& launch_counter() {
   return n;
 }
 
+static thread_local int g_sm_share = 0;   // > 0: persistent grids are sized for this many SMs (two half-batches side by side)
+void set_sm_share(int n) { g_sm_share = n; }
+
 int num_sms() {
   static thread_local int cached = 0;
   if (cached == 0) {
@@ -32,8 +36,10 @@ int num_sms() {
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || cached <= 0)
       cached = 148;
+    // experiment knob (tools only): cap the persistent grids, e.g. to measure a half batch on half the SMs
+    if (const char* e = getenv("AGX_SM_CAP")) { const int v = atoi(e); if (v > 0 && v < cached) cached = v; }
   }
-  return cached;
+  return g_sm_share > 0 && g_sm_share < cached ? g_sm_share : cached;
 }
 
 struct ProfRec { int kind; cudaEvent_t e0, e1; };

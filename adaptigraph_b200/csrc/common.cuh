@@ -57,6 +57,7 @@ struct Carver {
 };
 
 int num_sms();
+void set_sm_share(int n);   // thread-local: size persistent grids for n SMs (0 = all)
 
 // ---- optional per-kernel timing (agx_profile_*): CUDA events recorded on the launch stream
 // around every kernel, summed per kernel kind when read.  Off by default.

@@ -456,7 +456,7 @@ static int ensure_smem_attrs() {
 
 static int forward_impl(const AgxModelDims* dims, const float* wts, const AgxGraphIn* g, float* pred_pos,
                         int64_t pos_stride_b, float* pred_motion, int precision, void* workspace, size_t workspace_bytes,
-                        cudaStream_t st) {
+                        cudaStream_t st, cudaEvent_t after_encoders = nullptr) {
   AGX_REQUIRE(precision == AGX_PREC_FP32 || precision == AGX_PREC_TC_F16X3, AGX_ERR_ARG, "unknown precision %d", precision);
   const int64_t rows = (int64_t)g->B * g->N;
   FwdWs ws;
@@ -471,6 +471,7 @@ static int forward_impl(const AgxModelDims* dims, const float* wts, const AgxGra
     if (int rc = tc_node_encoder(g, wts, L, base, tb, st)) return rc;
     if (g->E_cap > 0)
       if (int rc = tc_edge_encoder(g, wts, L, base, tb, st)) return rc;
+    if (after_encoders) AGX_CUDA_OK(cudaEventRecord(after_encoders, st));   // the tensor-bound phase of this step is enqueued
     for (int k = 0; k < dims->pstep; ++k) {
       if (int rc = tc_edge_aggregate(g, tb, st)) return rc;
       if (int rc = tc_node_update(g, wts, L, base, tb, k + 1 == dims->pstep, pred_pos, pos_stride_b, pred_motion, st)) return rc;
@@ -534,6 +535,39 @@ static size_t rollout_ws_carve(void* base, int B, int N, int64_t E_cap, int topk
   w.fwd_ws = c.take<char>(w.fwd_ws_bytes);
   if (out) *out = w;
   return align_up(c.off, 256);
+}
+
+// ---- side-by-side half batches (agx_rollout)
+struct SplitPlan { int B0; int64_t E0, E1; int sms; };
+struct SplitStreams { cudaStream_t side; cudaEvent_t fork, offset, join; };
+static SplitStreams* split_streams() {   // per host thread, created on first use, never destroyed (process lifetime)
+  static thread_local SplitStreams ss{};
+  static thread_local bool ok = false;
+  if (!ok) {
+    if (cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.offset, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ok = true;
+  }
+  return &ss;
+}
+// Opt-in (AGX_ROLLOUT_SPLIT=1), tensor-core path only.  Measured on cloth-2k x 128 (B200): 29.3 ms per 10-step rollout against
+// 27.9 ms unsplit — run alone on 74 SMs a half batch needs 0.241 / 0.647 ms for edge_aggregate / edge_encoder, but side by side each
+// half's kernels take as long as the full-batch kernels on the whole GPU (0.315 / 0.72 ms): two thirds of a step is HBM bound, so the
+// two halves mostly compete for HBM instead of interleaving with each other's tensor-bound phase.  Kept for workloads with a
+// larger tensor-bound share (more propagation-free encoder work per relation); results are bit-identical either way.
+static bool rollout_split_plan(int B, int N, int64_t E_cap, int topk, int precision, SplitPlan* p) {
+  (void)topk; (void)N;
+  const char* e = getenv("AGX_ROLLOUT_SPLIT");
+  if (!e || atoi(e) != 1) return false;
+  if (precision != AGX_PREC_TC_F16X3 || B < 2) return false;
+  const int sms = num_sms() / 2;
+  p->B0 = B / 2;
+  p->E0 = E_cap / B * p->B0;          // E_cap is per-graph capacity x B for every caller of the Python layer
+  p->E1 = E_cap - p->E0;
+  p->sms = sms;
+  return sms > 0;
 }
 
 }  // namespace agx
@@ -620,7 +654,15 @@ int agx_forward(const AgxModelDims* dims, const void* packed_weights, const AgxG
 size_t agx_rollout_workspace_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap, int32_t topk) {
   (void)dims;
   if (B <= 0 || N <= 0 || E_cap <= 0 || topk <= 0) return 0;
-  return agx::rollout_ws_carve(nullptr, B, N, E_cap, topk < N ? topk : N, nullptr);
+  const int k = topk < N ? topk : N;
+  size_t need = agx::rollout_ws_carve(nullptr, B, N, E_cap, k, nullptr);
+  if (B >= 2) {   // the side-by-side plan carves two half-batch workspaces
+    const int B0 = B / 2;
+    const int64_t E0 = E_cap / B * B0;
+    const size_t split = agx::rollout_ws_carve(nullptr, B0, N, E0, k, nullptr) + agx::rollout_ws_carve(nullptr, B - B0, N, E_cap - E0, k, nullptr);
+    if (split > need) need = split;
+  }
+  return need;
 }
 
 int agx_rollout(const AgxModelDims* dims, const void* packed_weights, const AgxRolloutIn* r, float* pred_seq,
@@ -637,26 +679,61 @@ int agx_rollout(const AgxModelDims* dims, const void* packed_weights, const AgxR
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int topk = r->topk < r->N ? r->topk : r->N;
   RolloutWs ws;
-  const size_t need = rollout_ws_carve(workspace, r->B, r->N, r->E_cap, topk, &ws);
+  rollout_ws_carve(workspace, r->B, r->N, r->E_cap, topk, &ws);
+  const size_t need = agx_rollout_workspace_bytes(dims, r->B, r->N, r->E_cap, r->topk);   // covers the side-by-side plan too
   AGX_REQUIRE(workspace && workspace_bytes >= need, AGX_ERR_CAPACITY, "rollout: workspace %zu < %zu bytes", workspace_bytes, need);
   const int T = r->n_steps;
   const int64_t frame = (int64_t)r->N * 3;
-  for (int t = 0; t < T; ++t) {
+  // one model step of the graphs [b0, b0 + Bh) on stream s with workspace w
+  auto step = [&](int t, int b0, int Bh, int64_t E_cap_h, const RolloutWs& w, cudaStream_t s, cudaEvent_t after_encoders) -> int {
+    float* state = r->state + (size_t)b0 * H_FIX * frame;
+    const float* action = r->action + (size_t)b0 * frame;
+    const uint8_t* mask = r->mask + (size_t)b0 * r->N;
     // relations on the current positions (forward_dynamics.py:125 for t = 0, :171 afterwards)
-    int rc = graph_build_impl(r->state + (H_FIX - 1) * frame, H_FIX * frame, r->mask, r->tool_mask, r->thr2, r->B, r->N, topk,
-                              r->connect_tools_all != 0, AGX_SEM_BATCH, ws.row_ptr, ws.send, ws.recv, r->E_cap,
-                              n_edges_seq ? n_edges_seq + (size_t)t * r->B : ws.n_edges, status, ws.graph_ws, ws.graph_ws_bytes, st);
+    int rc = graph_build_impl(state + (H_FIX - 1) * frame, H_FIX * frame, mask, r->tool_mask + (size_t)b0 * r->N, r->thr2 + b0, Bh, r->N, topk,
+                              r->connect_tools_all != 0, AGX_SEM_BATCH, w.row_ptr, w.send, w.recv, E_cap_h,
+                              n_edges_seq ? n_edges_seq + (size_t)t * r->B + b0 : w.n_edges, status, w.graph_ws, w.graph_ws_bytes, s);
     if (rc) return rc;
-    AgxGraphIn g{r->B, r->N, r->n_p, r->state, r->attrs, r->action, r->p_instance, r->physics, ws.row_ptr, ws.send, ws.recv, r->E_cap};
-    float* pred_t = pred_seq + (size_t)t * r->n_p * 3;
+    AgxGraphIn g{Bh, r->N, r->n_p, state, r->attrs + (size_t)b0 * r->N * dims->d_attr, action, r->p_instance + (size_t)b0 * r->n_p,
+                 r->physics + (size_t)b0 * dims->d_phys, w.row_ptr, w.send, w.recv, E_cap_h};
     const int64_t stride = (int64_t)T * r->n_p * 3;
-    rc = forward_impl(dims, static_cast<const float*>(packed_weights), &g, pred_t, stride, ws.motion, precision, ws.fwd_ws,
-                      ws.fwd_ws_bytes, st);
+    float* pred_t = pred_seq + (size_t)b0 * stride + (size_t)t * r->n_p * 3;
+    rc = forward_impl(dims, static_cast<const float*>(packed_weights), &g, pred_t, stride, w.motion, precision, w.fwd_ws, w.fwd_ws_bytes, s,
+                      after_encoders);
     if (rc) return rc;
-    { ProfScope ps(AGX_KIND_ROLLOUT_ADVANCE, st);
-      rollout_advance_kernel<<<r->B, 256, 0, st>>>(r->state, r->action, r->mask, pred_t, stride, r->N, r->n_p, r->y_mode, r->gripper_raise); }
+    { ProfScope ps(AGX_KIND_ROLLOUT_ADVANCE, s);
+      rollout_advance_kernel<<<Bh, 256, 0, s>>>(state, action, mask, pred_t, stride, r->N, r->n_p, r->y_mode, r->gripper_raise); }
     AGX_LAUNCH_CHECK();
+    return AGX_OK;
+  };
+
+  SplitPlan plan;
+  if (rollout_split_plan(r->B, r->N, r->E_cap, topk, precision, &plan)) {
+    // Two half-batches side by side (graphs are independent): each on its own stream with the persistent grids sized for half
+    // the SMs, the second half started once the first has enqueued its encoder chains, so that one half's tensor-bound phase
+    // (node / edge encoders) runs under the other half's HBM-bound phase (aggregate / update) instead of after it.
+    SplitStreams* ss = split_streams();
+    AGX_REQUIRE(ss, AGX_ERR_CUDA, "rollout: could not create the second stream");
+    RolloutWs w0, w1;
+    const size_t n0 = rollout_ws_carve(workspace, plan.B0, r->N, plan.E0, topk, &w0);
+    rollout_ws_carve(static_cast<char*>(workspace) + n0, r->B - plan.B0, r->N, plan.E1, topk, &w1);
+    AGX_CUDA_OK(cudaEventRecord(ss->fork, st));
+    AGX_CUDA_OK(cudaStreamWaitEvent(ss->side, ss->fork, 0));
+    set_sm_share(plan.sms);
+    int rc = AGX_OK;
+    for (int t = 0; t < T && !rc; ++t) {
+      rc = step(t, 0, plan.B0, plan.E0, w0, st, t == 0 ? ss->offset : nullptr);
+      if (!rc && t == 0) rc = cudaStreamWaitEvent(ss->side, ss->offset, 0) == cudaSuccess ? AGX_OK : AGX_ERR_CUDA;
+      if (!rc) rc = step(t, plan.B0, r->B - plan.B0, plan.E1, w1, ss->side, nullptr);
+    }
+    set_sm_share(0);
+    if (rc) return rc;
+    AGX_CUDA_OK(cudaEventRecord(ss->join, ss->side));
+    AGX_CUDA_OK(cudaStreamWaitEvent(st, ss->join, 0));
+    return AGX_OK;
   }
+  for (int t = 0; t < T; ++t)
+    if (int rc = step(t, 0, r->B, r->E_cap, ws, st, nullptr)) return rc;
   return AGX_OK;
 }
 

@@ -384,3 +384,18 @@ def test_graph_build_cell_grid_stress_matches_c_oracle(agx, name, cta, sem):
     assert E == recv.shape[0] and np.array_equal(ne.cpu().numpy(), n_edges)
     assert np.array_equal(s[:E].cpu().numpy(), send)
     assert np.array_equal(r[:E].cpu().numpy() % N, recv)
+
+
+def test_side_by_side_half_batches_are_bit_identical(agx, monkeypatch):
+    """AGX_ROLLOUT_SPLIT=1 runs the two halves of the batch on two streams with half-sized persistent grids: same bits."""
+    from adaptigraph_b200 import synthetic as syn
+    w = syn.make_workload("cloth", 300, 7, seed=31).to("cuda")          # odd batch: halves of 3 and 4 graphs
+    m = _model(agx, "cloth", 3, "tc")
+    run = lambda: m.rollout(w.state, w.attrs, w.action, w.p_instance, w.physics_param, w.state_mask, w.eef_mask, w.adj_thresh, w.topk,  # noqa: E731
+                            w.connect_tools_all, 4, max_nR=3000)
+    monkeypatch.delenv("AGX_ROLLOUT_SPLIT", raising=False)
+    a = run()
+    monkeypatch.setenv("AGX_ROLLOUT_SPLIT", "1")
+    b = run()
+    torch.cuda.synchronize()
+    assert torch.equal(a["state_seqs"], b["state_seqs"]) and torch.equal(a["n_edges"], b["n_edges"]) and torch.equal(a["state"], b["state"])
