@@ -324,9 +324,9 @@ def main():
     # ---- CPU baseline + parity on rank 0 at N=1 only
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         Bc = 1
-        cpu_value, cpu_dt, cpu_preds, _ = time_cpu_baseline(params_cpu, Bc, steps=2, warmup=1, w=w_host.take(slice(0, Bc)))
+        cpu_value, cpu_dt, cpu_preds, _ = time_cpu_baseline(params_cpu, Bc, steps=12, warmup=1, w=w_host.take(slice(0, Bc)))
         line["cpu_baseline"] = {"value": cpu_value, "unit": "particle-steps/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"B={Bc} graph of the same workload (graph 0), T={T} rollout, 2 timed passes of {cpu_dt:.1f} s",
+                                "sample": f"B={Bc} graph of the same workload (graph 0), T={T} rollout, 12 timed passes of {cpu_dt:.1f} s each",
                                 "cpu": cpu_model_name()}
         err = out["state_seqs"][:Bc].cpu() - cpu_preds
         line["parity"] = {"rollout_rmse_vs_cpu": float(err.pow(2).mean().sqrt()), "rollout_max_abs": float(err.abs().max()),
