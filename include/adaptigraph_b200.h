@@ -141,7 +141,9 @@ AGX_API int agx_edges_to_onehot(const int32_t* row_ptr, const int32_t* send, int
  * radius >= 0 : fps_rad_idx(pcd, radius), utils.py:10-24 — picks until every point is within `radius` of a pick
  *               (fp32 norms, compared with the double `radius`), at most max_samples.
  * pos (B,N,3); n_points (B) valid prefix length of every cloud or NULL (= N); start_idx (B) first pick;
- * idx_out (B, max_samples) picks in selection order; n_out (B) number of picks.  N <= 12800. */
+ * idx_out (B, max_samples) picks in selection order; n_out (B) number of picks.  Clouds of up to 12800 points run in one CTA's
+ * shared memory; larger ones (N <= 204800) on a thread-block cluster of 2..16 CTAs exchanging their arg-max through distributed
+ * shared memory, with identical picks. */
 AGX_API int agx_fps(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int32_t max_samples,
             const int32_t* start_idx, double radius, int32_t* idx_out, int32_t* n_out, agx_stream_t stream);
 

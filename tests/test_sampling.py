@@ -86,7 +86,7 @@ def test_gpu_fps_wrapper_matches_reference(sampling, name):
 @pytest.mark.gpu
 def test_gpu_sampler_matches_oracle_batched(sampling):
     rng = np.random.default_rng(3)
-    for B, N, k in [(4, 257, 64), (2, 2025, 300), (3, 33, 33), (1, 12800, 40)]:
+    for B, N, k in [(4, 257, 64), (2, 2025, 300), (3, 33, 33), (1, 12800, 40)]:   # 12800 = the largest single-CTA cloud
         pos = rng.normal(size=(B, N, 3)).astype(np.float32)
         start = rng.integers(0, N, B)
         ref = so.farthest_point_sampler(pos, k, start)
@@ -99,8 +99,30 @@ def test_gpu_sampler_matches_oracle_batched(sampling):
     np.testing.assert_array_equal(got.numpy(), so.farthest_point_sampler(pos, 100, [17]))
     with pytest.raises(ValueError):
         sampling.farthest_point_sampler(torch.from_numpy(pos), 10, start_idx=500)
-    with pytest.raises(ValueError):   # beyond the shared-memory staging limit: an error, not a fallback
-        sampling.farthest_point_sampler(torch.zeros(1, 12801, 3), 4, start_idx=0)
+    with pytest.raises(ValueError):   # beyond the cluster staging limit: an error, not a fallback
+        sampling.farthest_point_sampler(torch.zeros(1, 204801, 3), 4, start_idx=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,k", [(12801, 40), (20000, 64), (60000, 48), (150000, 32), (204800, 8)])
+def test_gpu_cluster_sampler_matches_oracle(sampling, N, k):
+    """Clouds beyond one CTA's shared memory run on a thread-block cluster (2, 2, 8, 16, 16 CTAs): same picks as the oracle,
+    in both modes, for ragged lengths too."""
+    rng = np.random.default_rng(N)
+    B = 2
+    pos = rng.normal(size=(B, N, 3)).astype(np.float32)
+    start = rng.integers(0, N // 2, B)
+    got = sampling.farthest_point_sampler(torch.from_numpy(pos).cuda(), k, torch.from_numpy(start).cuda())
+    np.testing.assert_array_equal(got.cpu().numpy(), so.farthest_point_sampler(pos, k, start))
+    # radius mode on a ragged prefix (second cloud uses 60 % of its points)
+    from adaptigraph_b200 import ops
+    n_pts = np.array([N, int(0.6 * N)])
+    radius = 2.2
+    idx, cnt = ops.fps(torch.from_numpy(pos).cuda(), torch.from_numpy(n_pts).int().cuda(), torch.from_numpy(start).int().cuda(), 4096, radius)
+    for b in range(B):
+        _, ref = so.fps_rad_idx(pos[b, :n_pts[b]], radius, int(start[b]))
+        assert int(cnt[b]) == len(ref)
+        np.testing.assert_array_equal(idx[b, :len(ref)].cpu().numpy(), ref)
 
 
 @pytest.mark.gpu
