@@ -11,9 +11,9 @@
 //                    the permuted SoA copy of the graph and the first slot of every cell
 //   G1 knn_rows      one thread per receiver: a sender in range lies in the receiver's cell or one of its 8
 //                    neighbours, i.e. in three contiguous slot runs (cells b-1..b+1 of grid rows a-1..a+1), which
-//                    the thread walks in shared memory (each CTA stages just the grid rows its 128 receivers
-//                    can reach); the k nearest in-radius senders live in a per-thread sorted list in shared
-//                    memory, finally re-sorted by sender id -> <= k candidates
+//                    the thread walks in the sorted SoA copy (L1-resident: the threads of a CTA are a few
+//                    neighbouring cells); the k nearest in-radius senders live in a per-thread sorted list in
+//                    shared memory, finally re-sorted by sender id -> <= k candidates
 //   G2 degrees_scan  per-row relation count after the tool rules (:134-144 / :77-80) + block scan
 //   G2b scan_blocks  scan of the block sums -> row offsets, total
 //   G3 fill_rows     one thread per receiver merges candidates and tool senders in ascending sender order
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restric
 
 // ------------------------------------------------------------------------------------ G1
 // One THREAD per receiver (a CTA = G1_THREADS consecutive sorted slots, i.e. a few neighbouring cells): the thread walks its
-// three slot runs in shared memory — threads of the same cell read the same addresses (broadcast) — and keeps the k nearest
+// three slot runs — threads of the same cell read the same addresses (broadcast) — and keeps the k nearest
 // in-radius senders in a private sorted list (distance, then sender id) that lives in shared memory, interleaved by thread so
 // that list accesses are conflict free.  An insertion only happens when a sender beats the current k-th best, so after the
 // first few candidates the loop is pure distance arithmetic.  The list is finally re-sorted by sender id (<= k entries).
@@ -235,23 +235,20 @@ __global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
   const int na = grid_dims[2 * b], nb = grid_dims[2 * b + 1];
   const int32_t* cs = cell_start + (size_t)b * (GRID_MAX_CELLS + 1);
   const int s_beg = blockIdx.x * G1_ROWS_PER_CTA, s_end = min(N, s_beg + G1_ROWS_PER_CTA);
-  // slot range this CTA's receivers can reach: whole grid rows a_first - 1 .. a_last + 1
-  const int a_first = scell[gb + s_beg] / nb, a_last = scell[gb + s_end - 1] / nb;
-  const int r_lo = cs[max(a_first - 1, 0) * nb], r_hi = cs[(min(a_last + 1, na - 1) + 1) * nb], M = r_hi - r_lo;
-  if (M > smem_cap) __trap();   // host sizes shared memory for the whole graph, so this cannot happen
-  // per-thread lists first (fixed size), then the staged slots
+  // r_lo: a slot at or before everything this CTA's receivers can reach (start of grid row a_first - 1); keeps the offsets small
+  const int a_first = scell[gb + s_beg] / nb;
+  const int r_lo = cs[max(a_first - 1, 0) * nb];
+  (void)smem_cap;
   float* ld = smem;                                                   // [topk][G1_THREADS]
   int32_t* lj = reinterpret_cast<int32_t*>(ld + topk * G1_THREADS);   // [topk][G1_THREADS]  (sender id << 1) | tool bit
-  float* px = reinterpret_cast<float*>(lj + topk * G1_THREADS);
-  float* py = px + M;
-  float* pz = py + M;
-  int32_t* pj = reinterpret_cast<int32_t*>(pz + M);
-  uint8_t* fl = reinterpret_cast<uint8_t*>(pj + M);
-  for (int s = tid; s < M; s += G1_THREADS) {
-    const size_t o = gb + r_lo + s;
-    px[s] = sx[o]; py[s] = sy[o]; pz[s] = sz[o]; pj[s] = sidx[o]; fl[s] = sflag[o];
-  }
-  __syncthreads();
+  // candidates straight from global memory (read-only and shared by the neighbouring threads, so they are L1 hits); staging the
+  // CTA's reachable slot range in shared memory first was measured slower everywhere but on tiny graphs, and 4x slower at 8192
+  // particles per graph (the worst-case allocation leaves one CTA per SM): 0.437 -> 0.106 ms for cloth-8192 x 32
+  const float* px = sx + gb + r_lo;
+  const float* py = sy + gb + r_lo;
+  const float* pz = sz + gb + r_lo;
+  const int32_t* pj = sidx + gb + r_lo;
+  const uint8_t* fl = sflag + gb + r_lo;
 
   const int slot = s_beg + tid;
   if (slot >= s_end) return;
@@ -501,7 +498,7 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
   int NP2 = 1;
   while (NP2 < N) NP2 <<= 1;
   const size_t sort_smem = (size_t)NP2 * 8;
-  const size_t smem = (size_t)N * 17 + 32 + (size_t)topk * G1_THREADS * 8;   // worst case: a CTA's window spans the whole graph; + per-thread lists
+  const size_t smem = (size_t)topk * G1_THREADS * 8;   // the per-thread candidate lists
   AGX_REQUIRE(smem <= 227 * 1024 && sort_smem <= 227 * 1024, AGX_ERR_ARG, "graph_build: N=%d exceeds the shared-memory staging limit", N);
   static thread_local size_t smem_set = 0, sort_smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
