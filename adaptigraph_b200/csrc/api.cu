@@ -128,7 +128,7 @@ int agx_profile_read(double* ms, int64_t* count) {
 const char* agx_kind_name(int32_t kind) {
   static const char* names[AGX_NUM_KINDS] = {"graph_tool_list", "graph_knn_rows", "graph_scan", "graph_fill_rows",
                                              "node_encoder", "edge_encoder", "edge_aggregate", "node_update",
-                                             "node_update_head", "rollout_advance", "other", "graph_sort_axis"};
+                                             "node_update_head", "rollout_advance", "other", "graph_sort_cells"};
   return (kind >= 0 && kind < AGX_NUM_KINDS) ? names[kind] : "?";
 }
 

@@ -7,8 +7,8 @@
 //
 //   G0 tool_list     (only with connect_tools_all) ascending list of tool particles per graph
 //   G0b sort_cells   per graph: lay a uniform grid of cells no narrower than the radius over the two coordinate
-//                    axes of largest extent, sort the particles by cell id (bitonic sort in shared memory), emit
-//                    the permuted SoA copy of the graph and the first slot of every cell
+//                    axes of largest extent, counting-sort the particles by cell id (shared-memory histogram +
+//                    block scan), emit the permuted SoA copy of the graph and the first slot of every cell
 //   G1 knn_rows      one thread per receiver: a sender in range lies in the receiver's cell or one of its 8
 //                    neighbours, i.e. in three contiguous slot runs (cells b-1..b+1 of grid rows a-1..a+1), which
 //                    the thread walks in the sorted SoA copy (L1-resident: the threads of a CTA are a few
@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) tool_list_kernel(const uint8_t* __restric
 // ------------------------------------------------------------------------------------ G0b
 // One CTA per graph.  Grid over the two axes of largest extent of the valid particles; cell width >= the radius (with slack
 // for the fp32 rounding of the reference's distance and of the cell coordinate itself), so that two particles within the
-// radius differ by at most one cell along each axis.  Sort key = cell id (a * nb + b), ties by particle id.
+// radius differ by at most one cell along each axis.  Particles are counting-sorted by cell id (a * nb + b): histogram with
+// shared-memory atomics, block scan (= the first slot of every cell), scatter.
 __device__ __forceinline__ int cell_coord(float x, float lo, float w, int n) {
   const float u = __fdiv_rn(__fsub_rn(x, lo), w);
   return min(max((int)fminf(fmaxf(u, 0.f), (float)GRID_MAX_AXIS), 0), n - 1);   // NaN -> 0
@@ -115,13 +116,12 @@ __device__ __forceinline__ int cell_coord(float x, float lo, float w, int n) {
 
 __global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restrict__ pos, int64_t pos_stride_b,
                                                            const uint8_t* __restrict__ mask, const uint8_t* __restrict__ tool_mask,
-                                                           const float* __restrict__ thr2, int N, int NP2, float* __restrict__ sx,
+                                                           const float* __restrict__ thr2, int N, float* __restrict__ sx,
                                                            float* __restrict__ sy, float* __restrict__ sz, int32_t* __restrict__ scell,
                                                            int32_t* __restrict__ sidx, uint8_t* __restrict__ sflag,
                                                            int32_t* __restrict__ cell_start, int32_t* __restrict__ grid_dims) {
-  extern __shared__ int32_t smem_i[];
-  int32_t* key = smem_i;
-  int32_t* val = smem_i + NP2;
+  __shared__ int cnt[GRID_MAX_CELLS + 1];
+  __shared__ int wsum[32];
   __shared__ float red[6][32];
   __shared__ float lo_s[2], w_s[2];
   __shared__ int axis_s[2], n_s[2];
@@ -178,40 +178,58 @@ __global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restric
   __syncthreads();
   const int axa = axis_s[0], axb = axis_s[1], na = n_s[0], nb = n_s[1];
   const float loa = lo_s[0], lob = lo_s[1], wa = w_s[0], wb = w_s[1];
-  for (int j = tid; j < NP2; j += 1024) {
-    key[j] = j < N ? cell_coord(p[3 * j + axa], loa, wa, na) * nb + cell_coord(p[3 * j + axb], lob, wb, nb) : 0x7fffffff;
-    val[j] = j;
+  const int n_cells = na * nb;
+  auto cell_of = [&](int j) { return cell_coord(p[3 * j + axa], loa, wa, na) * nb + cell_coord(p[3 * j + axb], lob, wb, nb); };
+  // counting sort by cell id.  The order INSIDE a cell is whatever the atomics give: nothing downstream depends on it (knn_rows
+  // ranks candidates by (distance, particle id), a strict total order, and emits them sorted by id).
+  for (int c = tid; c <= n_cells; c += 1024) cnt[c] = 0;
+  __syncthreads();
+  for (int j = tid; j < N; j += 1024) atomicAdd(&cnt[cell_of(j)], 1);
+  __syncthreads();
+  // exclusive scan of cnt[0 .. n_cells] (<= 4097 entries): each thread owns up to 5 consecutive entries
+  constexpr int PER = (GRID_MAX_CELLS + 1 + 1023) / 1024;
+  int local[PER], sum = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = tid * PER + i;
+    local[i] = c <= n_cells ? cnt[c] : 0;
+    sum += local[i];
+  }
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, w, o);
+      if (lane >= o) w += v;
+    }
+    wsum[lane] = w;
   }
   __syncthreads();
-  for (int size = 2; size <= NP2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < (NP2 >> 1); t += 1024) {
-        const int lo = 2 * t - (t & (stride - 1));   // index with the `stride` bit clear
-        const int hi = lo + stride;
-        const bool up = (lo & size) == 0;
-        const int ka = key[lo], kb = key[hi];
-        const int va = val[lo], vb = val[hi];
-        const bool a_gt_b = (ka > kb) || (ka == kb && va > vb);
-        if (a_gt_b == up) { key[lo] = kb; key[hi] = ka; val[lo] = vb; val[hi] = va; }
-      }
-      __syncthreads();
-    }
-  }
+  int run = (warp ? wsum[warp - 1] : 0) + incl - sum;
   int32_t* cs = cell_start + (size_t)b * (GRID_MAX_CELLS + 1);
-  const int n_cells = na * nb;
-  for (int s = tid; s <= N; s += 1024) {
-    // cells (key[s-1], key[s]] start at slot s; slot N closes every remaining cell
-    const int c_prev = s > 0 ? key[s - 1] : -1;
-    const int c_here = s < N ? key[s] : n_cells;
-    for (int c = c_prev + 1; c <= c_here; ++c) cs[c] = s;
-    if (s < N) {
-      const int j = val[s];
-      const size_t o = (size_t)b * N + s;
-      sx[o] = p[3 * j + 0]; sy[o] = p[3 * j + 1]; sz[o] = p[3 * j + 2];
-      scell[o] = c_here;
-      sidx[o] = j;
-      sflag[o] = (mk[j] ? 1 : 0) | (tool_mask[(size_t)b * N + j] ? 2 : 0);
-    }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = tid * PER + i;
+    if (c <= n_cells) { cnt[c] = run; cs[c] = run; }   // cnt becomes the cell's write cursor; cs[n_cells] = N
+    run += local[i];
+  }
+  __syncthreads();
+  for (int j = tid; j < N; j += 1024) {
+    const int c = cell_of(j);
+    const int s = atomicAdd(&cnt[c], 1);
+    const size_t o = (size_t)b * N + s;
+    sx[o] = p[3 * j + 0]; sy[o] = p[3 * j + 1]; sz[o] = p[3 * j + 2];
+    scell[o] = c;
+    sidx[o] = j;
+    sflag[o] = (mk[j] ? 1 : 0) | (tool_mask[(size_t)b * N + j] ? 2 : 0);
   }
 }
 
@@ -495,19 +513,11 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
   const size_t need = graph_ws_carve(workspace, B, N, topk, &ws);
   AGX_REQUIRE(workspace && workspace_bytes >= need, AGX_ERR_CAPACITY, "graph_build: workspace %zu < %zu bytes",
               workspace_bytes, need);
-  int NP2 = 1;
-  while (NP2 < N) NP2 <<= 1;
-  const size_t sort_smem = (size_t)NP2 * 8;
-  const size_t smem = (size_t)topk * G1_THREADS * 8;   // the per-thread candidate lists
-  AGX_REQUIRE(smem <= 227 * 1024 && sort_smem <= 227 * 1024, AGX_ERR_ARG, "graph_build: N=%d exceeds the shared-memory staging limit", N);
-  static thread_local size_t smem_set = 0, sort_smem_set = 0;
+  const size_t smem = (size_t)topk * G1_THREADS * 8;   // the per-thread candidate lists of knn_rows
+  static thread_local size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     AGX_CUDA_OK(cudaFuncSetAttribute(knn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
-  }
-  if (sort_smem > 48 * 1024 && sort_smem > sort_smem_set) {
-    AGX_CUDA_OK(cudaFuncSetAttribute(sort_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-    sort_smem_set = sort_smem;
   }
   const int rows = B * N;
   const int nblk = (rows + SCAN_BLOCK - 1) / SCAN_BLOCK;
@@ -517,7 +527,7 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
     AGX_LAUNCH_CHECK();
   }
   { ProfScope ps(AGX_KIND_GRAPH_SORT, st);
-    sort_cells_kernel<<<B, 1024, sort_smem, st>>>(pos, pos_stride_b, mask, tool_mask, thr2, N, NP2, ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx,
+    sort_cells_kernel<<<B, 1024, 0, st>>>(pos, pos_stride_b, mask, tool_mask, thr2, N, ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx,
                                                   ws.sflag, ws.cell_start, ws.grid_dims); }
   AGX_LAUNCH_CHECK();
   dim3 g1((N + G1_ROWS_PER_CTA - 1) / G1_ROWS_PER_CTA, B);
