@@ -3,15 +3,15 @@
 Importing the compute API loads libadaptigraph_b200.so and fails loudly if it is missing.
 `adaptigraph_b200.synthetic` (workload generators) is importable without it.
 """
-__all__ = ["DynamicsPredictor", "EdgeList", "build_edges", "construct_edges_from_states",
+__all__ = ["DynamicsPredictor", "GraphedRollout", "EdgeList", "build_edges", "construct_edges_from_states",
            "construct_edges_from_states_batch", "edges_from_onehots", "pad_torch", "truncate_graph",
            "fps", "fps_rad_idx", "farthest_point_sampler", "fps_batch", "relation_lists", "collate_relation_lists"]
 
 
 def __getattr__(name):
-    if name == "DynamicsPredictor":
-        from .model import DynamicsPredictor
-        return DynamicsPredictor
+    if name in ("DynamicsPredictor", "GraphedRollout"):
+        from . import model
+        return getattr(model, name)
     if name in ("EdgeList", "build_edges", "construct_edges_from_states", "construct_edges_from_states_batch",
                 "edges_from_onehots", "relation_lists", "collate_relation_lists"):
         from . import graph

@@ -180,3 +180,72 @@ class DynamicsPredictor(nn.Module):
             if int(status.item()) & 1 or worst > max_nR:
                 raise RuntimeError(f"rollout: a graph reached {worst} relations, capacity max_nR={max_nR}")
         return {"state_seqs": pred_seq, "n_edges": n_edges, "state": hist}
+
+
+class GraphedRollout:
+    """`DynamicsPredictor.rollout` captured once as a CUDA graph and replayed: one launch instead of ~17 per model step, which is
+    what an MPC loop with small sample batches is bound by.  Shapes, relation capacity, step count and the scalar arguments are
+    frozen at construction; every call copies the new tensors into the captured buffers and replays.
+
+        roll = GraphedRollout(model, state, attrs, action, p_instance, physics_param, state_mask, eef_mask,
+                              adj_thresh, topk, connect_tools_all, n_steps, max_nR)
+        out = roll(state=new_state, action=new_action)      # any subset of the tensor arguments; returns the captured outputs
+
+    The returned tensors are overwritten by the next call.  Capacity overflow is reported by `out["status"]` / `check()`
+    (no host synchronisation inside a replay)."""
+
+    _TENSORS = ("state", "attrs", "action", "p_instance", "physics_param", "state_mask", "eef_mask")
+
+    def __init__(self, model, state, attrs, action, p_instance, physics_param, state_mask, eef_mask, adj_thresh, topk,
+                 connect_tools_all, n_steps, max_nR, y_mode="min", gripper_raise=0.0):
+        if not state.is_cuda:
+            raise RuntimeError("GraphedRollout needs CUDA tensors (no CPU path)")
+        self.model, self.max_nR = model, max_nR
+        self.static = {k: v.detach().clone() for k, v in zip(self._TENSORS, (state, attrs, action, p_instance,
+                                                                            physics_param.to(state.device), state_mask, eef_mask))}
+        self.static["state"] = self.static["state"].to(torch.float32).contiguous()
+        B, dev = state.shape[0], state.device
+        thr2 = _thr2_batch(adj_thresh, B, dev)
+        mode = {"min": L.AGX_Y_MIN, "masked_mean": L.AGX_Y_MASKED_MEAN}[y_mode]
+        packed = model.packed_weights()
+
+        hist = torch.empty_like(self.static["state"])      # the history the rollout advances in place
+
+        def run():
+            hist.copy_(self.static["state"])
+            pred_seq, n_edges, status = ops.rollout(
+                packed, hist, self.static["attrs"], self.static["action"], self.static["p_instance"], self.static["physics_param"],
+                self.static["state_mask"], self.static["eef_mask"], thr2, model.nf_effect, model.model_config["pstep"], topk,
+                connect_tools_all, n_steps, mode, float(gripper_raise), B * max_nR, model.precision)
+            return {"state_seqs": pred_seq, "n_edges": n_edges, "state": hist, "status": status}
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out = run()
+        self._packed_key = model._packed_key
+        self._keep = (thr2, packed, hist)      # the graph holds raw addresses: everything it reads must outlive __init__
+
+    def __call__(self, **tensors):
+        if self.model._packed_key != self._packed_key or self.model.packed_weights() is None:
+            raise RuntimeError("the model's parameters changed since capture: build a new GraphedRollout")
+        for k, v in tensors.items():
+            if k not in self.static:
+                raise KeyError(f"{k} is not a tensor argument of the captured rollout ({', '.join(self._TENSORS)})")
+            if v.shape != self.static[k].shape:
+                raise RuntimeError(f"GraphedRollout was captured for {k} of shape {tuple(self.static[k].shape)}, got {tuple(v.shape)}")
+            self.static[k].copy_(v)
+        self.graph.replay()
+        return self.out
+
+    def check(self):
+        """Synchronises; raises like pad_torch (utils.py:37-46) if a graph exceeded max_nR in the last replay."""
+        worst = int(self.out["n_edges"].max().item())
+        if int(self.out["status"].item()) & 1 or worst > self.max_nR:
+            raise RuntimeError(f"rollout: a graph reached {worst} relations, capacity max_nR={self.max_nR}")
+        return self.out

@@ -399,3 +399,25 @@ def test_side_by_side_half_batches_are_bit_identical(agx, monkeypatch):
     b = run()
     torch.cuda.synchronize()
     assert torch.equal(a["state_seqs"], b["state_seqs"]) and torch.equal(a["n_edges"], b["n_edges"]) and torch.equal(a["state"], b["state"])
+
+
+def test_graphed_rollout_replays_the_eager_rollout(agx):
+    """CUDA-graph replay of the device-resident rollout: same bits as the eager call, follows new inputs, refuses new shapes."""
+    from adaptigraph_b200 import synthetic as syn
+    w = syn.make_workload("granular", 200, 6, seed=41).to("cuda")
+    m = _model(agx, "granular", 3, "tc")
+    args = (w.state, w.attrs, w.action, w.p_instance, w.physics_param, w.state_mask, w.eef_mask, w.adj_thresh, w.topk, w.connect_tools_all)
+    roll = agx.GraphedRollout(m, *args, 5, 5000)
+    for shift in (0.0, 0.03):
+        st = w.state + shift
+        act = w.action * (1.0 + shift)
+        ref = m.rollout(st, w.attrs, act, w.p_instance, w.physics_param, w.state_mask, w.eef_mask, w.adj_thresh, w.topk,
+                        w.connect_tools_all, 5, max_nR=5000)
+        got = roll(state=st, action=act)
+        roll.check()
+        assert torch.equal(got["state_seqs"], ref["state_seqs"]) and torch.equal(got["n_edges"], ref["n_edges"])
+        assert torch.equal(got["state"], ref["state"])
+    with pytest.raises(RuntimeError):
+        roll(state=w.state[:3])
+    with pytest.raises(KeyError):
+        roll(Rr=w.state)
