@@ -5,7 +5,7 @@
 // difference tensors, a B x N x N distance matrix, a top-k index tensor and two dense
 // B x n_rel x N one-hots; here nothing quadratic ever reaches HBM:
 //
-//   G0 tool_list     (only with connect_tools_all) ascending list of tool particles per graph
+//   (G0 tool list    with connect_tools_all: ascending list of tool particles per graph, built by sort_cells' CTA)
 //   G0b sort_cells   per graph: lay a uniform grid of cells no narrower than the radius over the two coordinate
 //                    axes of largest extent, counting-sort the particles by cell id (shared-memory histogram +
 //                    block scan), emit the permuted SoA copy of the graph and the first slot of every cell
@@ -14,8 +14,8 @@
 //                    the thread walks in the sorted SoA copy (L1-resident: the threads of a CTA are a few
 //                    neighbouring cells); the k nearest in-radius senders live in a per-thread sorted list in
 //                    shared memory, finally re-sorted by sender id -> <= k candidates
-//   G2 degrees_scan  per-row relation count after the tool rules (:134-144 / :77-80) + block scan
-//   G2b scan_blocks  scan of the block sums -> row offsets, total
+//   G2 degrees_scan  per-row relation count after the tool rules (:134-144 / :77-80) + block scan; the last block to
+//                    finish scans the block sums -> row offsets, total
 //   G3 fill_rows     one thread per receiver merges candidates and tool senders in ascending sender order
 //
 // Arithmetic follows the reference exactly: dis = (dx*dx + dy*dy) + dz*dz in fp32 without FMA
@@ -40,6 +40,7 @@ struct GraphWs {
   int32_t* lpre;       // [B*N]   block-local exclusive prefix
   int32_t* blk;        // [nblk]  block sums -> exclusive block offsets
   int32_t* total;      // [1]
+  int32_t* ticket;     // [1]     last-block-done counter of degrees_scan (zeroed by sort_cells)
   int32_t* flags;      // [B]     probe: some tool receiver kept a non-tool sender (graph.py:135)
   int32_t* n_tools;    // [B]
   int32_t* tools;      // [B*N]
@@ -62,6 +63,7 @@ static size_t graph_ws_carve(void* base, int B, int N, int topk, GraphWs* ws) {
   w.lpre = c.take<int32_t>(rows);
   w.blk = c.take<int32_t>(nblk + 1);
   w.total = c.take<int32_t>(1);
+  w.ticket = c.take<int32_t>(1);
   w.flags = c.take<int32_t>(B);
   w.n_tools = c.take<int32_t>(B);
   w.tools = c.take<int32_t>(rows);
@@ -76,32 +78,30 @@ static size_t graph_ws_carve(void* base, int B, int N, int topk, GraphWs* ws) {
 }
 
 // ------------------------------------------------------------------------------------ G0
-__global__ void __launch_bounds__(256) tool_list_kernel(const uint8_t* __restrict__ tool_mask, int N,
-                                                         int32_t* __restrict__ tools, int32_t* __restrict__ n_tools,
-                                                         int32_t* __restrict__ flags) {
-  __shared__ int warp_tot[8];
-  __shared__ int base_s;
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { base_s = 0; flags[b] = 0; }
+// Ascending list of the graph's tool particles (ordered compaction), by the graph's CTA of 1024 threads.
+__device__ __forceinline__ void tool_list_block(const uint8_t* __restrict__ tm, int N, int32_t* __restrict__ tools,
+                                                int32_t* __restrict__ n_tools_b, int* warp_tot /*[32] shared*/, int* base_s /*shared*/) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) *base_s = 0;
   __syncthreads();
-  for (int j0 = 0; j0 < N; j0 += 256) {
-    int j = j0 + tid;
-    bool f = (j < N) && tool_mask[(size_t)b * N + j];
-    unsigned m = __ballot_sync(FULL, f);
+  for (int j0 = 0; j0 < N; j0 += 1024) {
+    const int j = j0 + tid;
+    const bool f = (j < N) && tm[j];
+    const unsigned m = __ballot_sync(FULL, f);
     if (lane == 0) warp_tot[warp] = __popc(m);
     __syncthreads();
-    int off = base_s;
+    int off = *base_s;
     for (int w = 0; w < warp; ++w) off += warp_tot[w];
-    if (f) tools[(size_t)b * N + off + __popc(m & ((1u << lane) - 1))] = j;
+    if (f) tools[off + __popc(m & ((1u << lane) - 1))] = j;
     __syncthreads();
     if (tid == 0) {
       int t = 0;
-      for (int w = 0; w < 8; ++w) t += warp_tot[w];
-      base_s += t;
+      for (int w = 0; w < 32; ++w) t += warp_tot[w];
+      *base_s += t;
     }
     __syncthreads();
   }
-  if (tid == 0) n_tools[b] = base_s;
+  if (tid == 0) *n_tools_b = *base_s;
 }
 
 // ------------------------------------------------------------------------------------ G0b
@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restric
                                                            const float* __restrict__ thr2, int N, float* __restrict__ sx,
                                                            float* __restrict__ sy, float* __restrict__ sz, int32_t* __restrict__ scell,
                                                            int32_t* __restrict__ sidx, uint8_t* __restrict__ sflag,
-                                                           int32_t* __restrict__ cell_start, int32_t* __restrict__ grid_dims) {
+                                                           int32_t* __restrict__ cell_start, int32_t* __restrict__ grid_dims,
+                                                           int32_t* __restrict__ tools, int32_t* __restrict__ n_tools,
+                                                           int32_t* __restrict__ flags, int32_t* __restrict__ scan_ticket) {
   __shared__ int cnt[GRID_MAX_CELLS + 1];
   __shared__ int wsum[32];
   __shared__ float red[6][32];
@@ -230,6 +232,12 @@ __global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restric
     scell[o] = c;
     sidx[o] = j;
     sflag[o] = (mk[j] ? 1 : 0) | (tool_mask[(size_t)b * N + j] ? 2 : 0);
+  }
+  if (b == 0 && tid == 0) *scan_ticket = 0;     // degrees_scan's last-block-done counter (same stream, earlier kernel)
+  if (tools) {                                   // connect_tools_all
+    if (tid == 0) flags[b] = 0;
+    __syncthreads();                             // wsum / cnt are free again
+    tool_list_block(tool_mask + (size_t)b * N, N, tools + (size_t)b * N, n_tools + b, wsum, &cnt[0]);
   }
 }
 
@@ -344,7 +352,8 @@ __device__ __forceinline__ int row_degree(int packed, bool valid, bool tool_i, i
 __global__ void __launch_bounds__(SCAN_BLOCK) degrees_scan_kernel(
     const int32_t* __restrict__ cnt, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ tool_mask,
     const int32_t* __restrict__ flags, const int32_t* __restrict__ n_tools, int rows, int N, int cta, int sem,
-    int32_t* __restrict__ deg, int32_t* __restrict__ lpre, int32_t* __restrict__ blk) {
+    int32_t* __restrict__ deg, int32_t* __restrict__ lpre, int32_t* __restrict__ blk, int32_t* __restrict__ ticket,
+    int32_t* __restrict__ total, int32_t* __restrict__ row_ptr_end) {
   __shared__ int warp_sum[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = blockIdx.x * SCAN_BLOCK + tid;
@@ -376,25 +385,29 @@ __global__ void __launch_bounds__(SCAN_BLOCK) degrees_scan_kernel(
   const int warp_off = warp ? warp_sum[warp - 1] : 0;
   if (r < rows) lpre[r] = warp_off + incl - d;
   if (tid == SCAN_BLOCK - 1) blk[blockIdx.x] = warp_off + incl;
-}
-
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(int32_t* __restrict__ blk, int nblk, int32_t* __restrict__ total,
-                                                            int32_t* __restrict__ row_ptr_end) {
-  __shared__ int warp_sum[32];
+  // ---- the last block to finish turns the block sums into exclusive block offsets (what scan_blocks_kernel used to do)
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int nblk = gridDim.x;
   __shared__ int carry_s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) carry_s = 0;
   __syncthreads();
-  for (int i0 = 0; i0 < nblk; i0 += 1024) {
+  for (int i0 = 0; i0 < nblk; i0 += SCAN_BLOCK) {
     const int i = i0 + tid;
-    const int v = i < nblk ? blk[i] : 0;
-    int incl = v;
+    const int v = i < nblk ? __ldcg(blk + i) : 0;
+    int inc2 = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += u;
+      const int u = __shfl_up_sync(FULL, inc2, o);
+      if (lane >= o) inc2 += u;
     }
-    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (lane == 31) warp_sum[warp] = inc2;
     __syncthreads();
     if (warp == 0) {
       int w = warp_sum[lane];
@@ -407,10 +420,10 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(int32_t* __restrict__
     }
     __syncthreads();
     const int carry = carry_s;
-    const int excl = carry + (warp ? warp_sum[warp - 1] : 0) + incl - v;
+    const int excl = carry + (warp ? warp_sum[warp - 1] : 0) + inc2 - v;
     if (i < nblk) blk[i] = excl;
     __syncthreads();
-    if (tid == 1023) carry_s = excl + v;
+    if (tid == SCAN_BLOCK - 1) carry_s = excl + v;
     __syncthreads();
   }
   if (tid == 0) { *total = carry_s; *row_ptr_end = carry_s; }
@@ -521,14 +534,9 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
   }
   const int rows = B * N;
   const int nblk = (rows + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  if (cta) {
-    { ProfScope ps(AGX_KIND_GRAPH_TOOLS, st);
-      tool_list_kernel<<<B, 256, 0, st>>>(tool_mask, N, ws.tools, ws.n_tools, ws.flags); }
-    AGX_LAUNCH_CHECK();
-  }
   { ProfScope ps(AGX_KIND_GRAPH_SORT, st);
     sort_cells_kernel<<<B, 1024, 0, st>>>(pos, pos_stride_b, mask, tool_mask, thr2, N, ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx,
-                                                  ws.sflag, ws.cell_start, ws.grid_dims); }
+                                                  ws.sflag, ws.cell_start, ws.grid_dims, cta ? ws.tools : nullptr, ws.n_tools, ws.flags, ws.ticket); }
   AGX_LAUNCH_CHECK();
   dim3 g1((N + G1_ROWS_PER_CTA - 1) / G1_ROWS_PER_CTA, B);
   { ProfScope ps(AGX_KIND_GRAPH_KNN, st);
@@ -537,10 +545,7 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
   AGX_LAUNCH_CHECK();
   { ProfScope ps(AGX_KIND_GRAPH_SCAN, st);
     degrees_scan_kernel<<<nblk, SCAN_BLOCK, 0, st>>>(ws.cnt, mask, tool_mask, ws.flags, ws.n_tools, rows, N, cta, sem,
-                                                      ws.deg, ws.lpre, ws.blk); }
-  AGX_LAUNCH_CHECK();
-  { ProfScope ps(AGX_KIND_GRAPH_SCAN, st);
-    scan_blocks_kernel<<<1, 1024, 0, st>>>(ws.blk, nblk, ws.total, row_ptr + rows); }
+                                                      ws.deg, ws.lpre, ws.blk, ws.ticket, ws.total, row_ptr + rows); }
   AGX_LAUNCH_CHECK();
   { ProfScope ps(AGX_KIND_GRAPH_FILL, st);
     fill_rows_kernel<<<(rows + 255) / 256, 256, 0, st>>>(ws.cand, ws.cnt, ws.lpre, ws.blk, ws.total, mask, tool_mask, ws.flags,
