@@ -85,3 +85,24 @@ def test_module_keeps_reference_state_dict_and_init(L):
     mc["state_dim"] = 3
     with pytest.raises(NotImplementedError):
         DynamicsPredictor(mc, matc, dc, "cpu")
+
+
+def test_widened_entry_points_validate_arguments_without_a_device(L):
+    """agx_fps / agx_chamfer / agx_adam_step / the training entries return AGX_ERR_ARG before any launch."""
+    lib = L.lib
+    assert lib.agx_fps(None, None, 1, 10, 4, None, -1.0, None, None, None) == L.AGX_ERR_ARG
+    buf = (C.c_float * 64)()
+    ibuf = (C.c_int32 * 16)()
+    p, ip = C.cast(buf, C.c_void_p), C.cast(ibuf, C.c_void_p)
+    assert lib.agx_fps(p, None, 0, 10, 4, ip, -1.0, ip, ip, None) == L.AGX_ERR_ARG           # B = 0
+    assert lib.agx_fps(p, None, 1, 300000, 4, ip, -1.0, ip, ip, None) == L.AGX_ERR_ARG      # beyond the cluster staging limit
+    assert b"staging limit" in lib.agx_last_error()
+    assert lib.agx_chamfer(None, p, 1, 4, 4, 0, p, None) == L.AGX_ERR_ARG
+    assert lib.agx_chamfer(p, p, 1, 20000, 4, 0, p, None) == L.AGX_ERR_ARG                   # N + M beyond shared memory
+    assert lib.agx_adam_step(None, p, p, p, 16, 1e-3, 0.9, 0.999, 1e-8, 1.0, ip, None) == L.AGX_ERR_ARG
+    assert lib.agx_adam_step(p, p, p, p, 0, 1e-3, 0.9, 0.999, 1e-8, 1.0, ip, None) == L.AGX_ERR_ARG
+    off = C.c_void_p(p.value + 4)                                                            # misaligned bucket
+    assert lib.agx_adam_step(off, p, p, p, 8, 1e-3, 0.9, 0.999, 1e-8, 1.0, ip, None) == L.AGX_ERR_ARG
+    dims = L.AgxModelDims(150, 4, 2, 1, 3, 3)
+    assert lib.agx_train_saved_bytes(C.byref(dims), 2, 50, 400) > 0
+    assert lib.agx_train_scratch_bytes(C.byref(dims), 2, 50, 400) > 0
