@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--graphs", type=int, default=WORKLOAD["B"], help="graphs per GPU (default: the BASELINE batch)")
+    ap.add_argument("--total-graphs", type=int, default=0,
+                    help="strong scaling: this many graphs in total, split evenly over the GPUs (overrides --graphs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rollout-steps", type=int, default=WORKLOAD["T"], help="T (default: the BASELINE 10-step rollout)")
     args = ap.parse_args()
@@ -196,6 +198,11 @@ def main():
     import adaptigraph_b200 as agx
     from adaptigraph_b200 import ops, synthetic as syn
 
+    strong = args.total_graphs > 0
+    if strong:
+        from adaptigraph_b200.shard import shard_slice
+        sl = shard_slice(args.total_graphs, world, rank)
+        args.graphs = sl.stop - sl.start
     B, n_p, K, T = args.graphs, WORKLOAD["n_p"], WORKLOAD["pstep"], WORKLOAD["T"]
     torch.manual_seed(0)
     model = agx.DynamicsPredictor(*syn.configs(WORKLOAD["material"], K), dev).to(dev).eval()
@@ -244,7 +251,8 @@ def main():
     assert not overflow, "relation capacity exceeded in the bench workload"
     ms_per_step = ms_total / args.steps
     particle_steps = B * n_p * T
-    value = world * particle_steps / (ms_per_step * 1e-3)
+    job_particle_steps = (args.total_graphs if strong else world * B) * n_p * T      # all ranks together
+    value = job_particle_steps / (ms_per_step * 1e-3)
 
     # ---- end to end from pinned host buffers (H2D of the step's inputs + D2H of the predictions each step)
     host = {k: v.pin_memory() for k, v in dict(state=w_host.state, attrs=w_host.attrs, action=w_host.action, p_instance=w_host.p_instance,
@@ -270,7 +278,7 @@ def main():
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    e2e_value = world * particle_steps / (e2e_ms * 1e-3)
+    e2e_value = job_particle_steps / (e2e_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (live CUDA-event timings of the timed region above)
     E = float(out["n_edges"].float().sum(1).mean().item())      # relations per model step over the batch
@@ -314,7 +322,7 @@ def main():
 
     line = {
         "metric": "particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": dict(config_block(B), arithmetic=os.environ.get("AGX_PRECISION", "tc")),
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "roofline": roof, "kernels": kernels, "relations_per_graph": Eg,
