@@ -179,7 +179,7 @@ class DynamicsPredictor(nn.Module):
             worst = int(n_edges.max().item())
             if int(status.item()) & 1 or worst > max_nR:
                 raise RuntimeError(f"rollout: a graph reached {worst} relations, capacity max_nR={max_nR}")
-        return {"state_seqs": pred_seq, "n_edges": n_edges, "state": hist}
+        return {"state_seqs": pred_seq, "n_edges": n_edges, "state": hist, "status": status}
 
 
 class GraphedRollout:
