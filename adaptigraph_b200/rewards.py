@@ -18,11 +18,19 @@ import torch
 from . import ops
 
 
+def _on_device(*ts):
+    for t in ts:
+        if not t.is_cuda:
+            raise RuntimeError("adaptigraph_b200.rewards evaluates on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor of shape {tuple(t.shape)}")
+
+
 def chamfer(x, y):  # x: (B, N, D), y: (1|B, M, D)
     return ops.chamfer(x, y)
 
 
 def box_loss(state, target):
+    _on_device(state, target)
     xmin, xmax, zmin, zmax = target[0, 0], target[0, 1], target[1, 0], target[1, 1]
     zero = torch.zeros_like(state[:, :, 0])
     x_diff = torch.maximum(xmin - state[:, :, 0], zero) + torch.maximum(state[:, :, 0] - xmax, zero)
@@ -36,6 +44,7 @@ def _min_point_distance(action_point_2d, state_2d):
 
 
 def rope_penalty(state_pred, action, state_init, sim_real_ratio=10.0):
+    _on_device(state_pred, action, state_init)
     bsz = action.shape[0]
     action_point_2d = torch.stack([action[:, :, 0], action[:, :, 1]], dim=-1)
     state_2d = torch.cat([state_init[:, [0, 2]][None, None].expand(bsz, 1, -1, -1), state_pred[:, :-1, :, [0, 2]]], dim=1)
@@ -45,6 +54,7 @@ def rope_penalty(state_pred, action, state_init, sim_real_ratio=10.0):
 
 
 def cloth_penalty(state_pred, action, state_init, sim_real_ratio=10.0):
+    _on_device(state_pred, action, state_init)
     action_point_2d = torch.stack([action[:, :, 0], action[:, :, 1]], dim=-1)
     dist = torch.norm(action_point_2d[:, :, None] - state_init[:, [0, 2]][None, None], dim=-1)
     dmin = dist.min(dim=-1).values
@@ -55,6 +65,7 @@ def cloth_penalty(state_pred, action, state_init, sim_real_ratio=10.0):
 
 
 def granular_penalty(state_pred, action, state_init, sim_real_ratio=10.0):
+    _on_device(state_pred, action, state_init)
     bsz, n_look_forward, _ = action.shape
     x_start, z_start, theta = action[:, :, 0], action[:, :, 1], action[:, :, 2]
     pusher_radius = 0.05 * sim_real_ratio
@@ -73,6 +84,7 @@ def granular_penalty(state_pred, action, state_init, sim_real_ratio=10.0):
 def running_cost(state, action, state_cur, error_func, penalty_func, bbox, verbose=False, **kwargs):
     """plan.py:27-59.  state (bsz, n_look_forward, max_nobj, 3), action (bsz, n_look_forward, action_dim), state_cur
     (max_nobj, 3), bbox (2, 2) -> {'reward_seqs': (bsz,)}."""
+    _on_device(state, action, state_cur, bbox)
     bsz, n_look_forward = state.shape[0], state.shape[1]
     state_flat = state.reshape(bsz * n_look_forward, state.shape[2], state.shape[3])
     error = error_func(state_flat).reshape(bsz, n_look_forward)

@@ -123,3 +123,16 @@ def running_cost(state, action, state_cur, error_func, penalty_func, bbox):
     ], dim=-1)
     box_penalty = torch.exp(-box_penalty * 100.).max(dim=-1).values
     return -error_weight * error[:, -1] - 5. * collision_penalty.mean(dim=1) - 5. * box_penalty.mean(dim=1)
+
+
+def rope_penalty(state_pred, action, state_init, sim_real_ratio=10.0):
+    """planning/losses.py:37-48, line by line (CPU torch).  Pinned: tests/golden/rewards.npz holds the reference's output."""
+    bsz, n_look_forward, _ = action.shape
+    x_start = action[:, :, 0]
+    z_start = action[:, :, 1]
+    action_point_2d = torch.stack([x_start, z_start], dim=-1)
+    state_2d = torch.cat([state_init[:, [0, 2]][None, None].repeat(bsz, 1, 1, 1), state_pred[:, :-1, :, [0, 2]]], dim=1)
+    action_state_distance = torch.norm(action_point_2d[:, :, None] - state_2d, dim=-1).min(dim=-1).values
+    pusher_size = 0.02 * sim_real_ratio
+    action_state_distance = torch.maximum(action_state_distance - pusher_size, torch.zeros_like(action_state_distance))
+    return torch.exp(-action_state_distance * 100.)

@@ -82,7 +82,7 @@ po.dynamics(params, 3, state, a_cpu[:8], cfg)
 t0 = time.perf_counter()
 ref, dec_cpu = po.dynamics(params, 3, state, a_cpu, cfg)
 r_cpu = po.running_cost(ref, dec_cpu, state, partial(po.chamfer, y=target),
-                        lambda s, a, c: rewards.rope_penalty(s, a, c), bbox)
+                        po.rope_penalty, bbox)
 cpu_s = time.perf_counter() - t0
 out = planning.dynamics(state.cuda(), a_cpu.cuda(), model, "cuda", ppm)
 err = float((out["state_seqs"].cpu() - ref).abs().max())

@@ -14,6 +14,11 @@ CH = sorted({k.split("/")[1] for k in G if k.startswith("chamfer/")})
 TOL = 2e-6
 
 
+def test_oracle_rope_penalty_matches_reference():
+    t = lambda k: torch.from_numpy(G[k])  # noqa: E731
+    np.testing.assert_allclose(po.rope_penalty(t("state"), t("action"), t("state_cur")).numpy(), G["rope_penalty"], rtol=0, atol=1e-7)
+
+
 @pytest.mark.parametrize("name", CH)
 def test_oracle_chamfer_matches_reference(name):
     out = po.chamfer(torch.from_numpy(G[f"chamfer/{name}/x"]), torch.from_numpy(G[f"chamfer/{name}/y"]))
@@ -41,6 +46,8 @@ def test_gpu_chamfer_matches_reference(rw, name):
 def test_gpu_chamfer_rejects_bad_input(rw):
     with pytest.raises(RuntimeError):
         rw.chamfer(torch.zeros(2, 4, 3), torch.zeros(1, 4, 3))                       # CPU tensors: no fallback
+    with pytest.raises(RuntimeError):
+        rw.rope_penalty(torch.zeros(2, 3, 4, 3), torch.zeros(2, 3, 4), torch.zeros(4, 3))
     with pytest.raises(ValueError):
         rw.chamfer(torch.zeros(2, 4, 3).cuda(), torch.zeros(3, 4, 3).cuda())         # target batch neither 1 nor B
     with pytest.raises(ValueError):
