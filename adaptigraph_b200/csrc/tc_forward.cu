@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
   const int warp = threadIdx.x >> 5;
   if (warp >= EPI_WARPS) {
     reg_dealloc_other();
-    if (warp == LOAD_WARP) loader_role(sh, prog, a.blob, a.L, n_tiles, LAST ? 13 : 3);
+    if (warp == LOAD_WARP) loader_role(sh, prog, a.blob, a.L, n_tiles, LAST ? 13 : 3, !LAST);
     else if (warp < LOAD_WARP) mma_role(sh, prog, warp - MMA_WARP0, tmem_base, n_tiles, LAST ? 13 : 3);
   } else {
     reg_alloc_epilogue();
