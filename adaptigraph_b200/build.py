@@ -30,16 +30,33 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """Compiles every translation unit for sm_100a (in parallel, one nvcc per source) and links the shared object."""
     if not force and not _stale() and out == LIB:
         return LIB
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines] + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode:
-        raise RuntimeError("nvcc failed building " + os.path.basename(out))
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines]
+    with tempfile.TemporaryDirectory(prefix="agx_build_") as tmp:
+        def compile_one(src):
+            obj = os.path.join(tmp, src.replace(".cu", ".o"))
+            res = subprocess.run([nvcc] + compile_flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+            return src, obj, res
+        with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+            results = list(pool.map(compile_one, SOURCES))
+        failed = False
+        for src, _, res in results:
+            if verbose or res.returncode:
+                sys.stderr.write(res.stdout + res.stderr)
+            failed = failed or res.returncode != 0
+        if failed:
+            raise RuntimeError("nvcc failed building " + os.path.basename(out))
+        link = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] +
+                              [obj for _, obj, _ in results] + ["-o", out], capture_output=True, text=True)
+        if verbose or link.returncode:
+            sys.stderr.write(link.stdout + link.stderr)
+        if link.returncode:
+            raise RuntimeError("nvcc failed linking " + os.path.basename(out))
     return out
 
 
