@@ -141,10 +141,27 @@ __device__ __forceinline__ float max16(const float (&v)[HW], float m) {   // max
   for (int i = 0; i < HW; ++i) m = fmaxf(m, fabsf(v[i]));
   return m;
 }
-__device__ __forceinline__ void stg16(float* p, const float (&v)[HW]) {
-  const float a[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]}, b[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+// this thread's 16 columns [col0, col0 + 16) of blocked row `row`: the narrow last piece holds only columns 144..151
+__device__ __forceinline__ void blk_store16(float* base, int64_t row, int col0, const float (&v)[HW]) {
+  float* p = base + blk_off(row, col0);
+  const float a[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
   stg256(p, a);
-  stg256(p + 8, b);
+  if (col0 < BLK_LAST) {
+    const float b[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+    stg256(p + 8, b);
+  }
+}
+__device__ __forceinline__ void blk_add16(const float* base, int64_t row, int col0, float (&v)[HW]) {   // v += stored columns
+  const float* p = base + blk_off(row, col0);
+  float t[8];
+  ldg256(p, t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] += t[i];
+  if (col0 < BLK_LAST) {
+    ldg256(p + 8, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[8 + i] += t[i];
+  }
 }
 struct NoExtra { __device__ void operator()(int, int, float (&)[HW]) const {} };
 struct NoSide { __device__ void operator()(int, int, const float (&)[HW]) const {} };
@@ -166,7 +183,7 @@ __device__ __forceinline__ float epi_store_rows(const Shared& sh, EpiCtx& cx, co
   float mx = 0.f;
   epi_layer_out<false>(sh, cx, unscale, [&](int, int col0, float (&v)[HW]) {
     mx = max16(v, mx);
-    if (valid) stg16(out + blk_off(grow, col0), v);
+    if (valid) blk_store16(out, grow, col0, v);
   }, all_read);
   return mx;
 }
@@ -336,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
         const float bound_next = fmaxf(cx.bound_in * m.y, 1.f);
         const int e_next = scale_exp(bound_next);
         float pm = epi_layer_to_a(sh, cx, exp2i(-cx.e_in) * m.x, exp2i(e_next), NoExtra{}, [&](int, int col0, const float (&v)[HW]) {
-          if (valid) stg16(a.P + blk_off(r, col0), v);
+          if (valid) blk_store16(a.P, r, col0, v);
         });
         pm = epi_exchange<true>(sh, cx, pm);
         cx.bound_in = bound_next;
@@ -398,18 +415,26 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
       AGX_STAMP_EPI(cx, 30);
       if (cx.warp % SLOT_WARPS == 0 && cx.lane == 0) {
         // the residual rows of this tile are read by the first layer's epilogue: start them towards L2 now
-        bulk_prefetch_l2(a.A + (int64_t)tile * TILE * FP, TILE * FP * 4);   // (buffers are padded to whole tiles)
-        bulk_prefetch_l2(a.P + (int64_t)tile * TILE * FP, TILE * FP * 4);
+        bulk_prefetch_l2(a.A + (int64_t)tile * BLK_TILE, BLK_TILE * 4);   // (buffers are padded to whole tiles)
+        bulk_prefetch_l2(a.P + (int64_t)tile * BLK_TILE, BLK_TILE * 4);
       }
       // ---- producer: the aggregated relation effects arrive already scaled and split (edge_aggregate): copy to A
       {
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
           uint32_t hi[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lo[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          if (valid) {   // 16 words per (row, piece): 8 hi then 8 lo
-            const uint32_t* piece = a.agg_split + blk_off(r, 32 * c + HW * cx.half);
-            ldg256(reinterpret_cast<const float*>(piece), reinterpret_cast<float(&)[8]>(hi));
-            ldg256(reinterpret_cast<const float*>(piece + 8), reinterpret_cast<float(&)[8]>(lo));
+          if (valid) {   // 16 words per (row, piece): 8 hi then 8 lo; the narrow last piece: 4 hi then 4 lo
+            const int col0 = 32 * c + HW * cx.half;
+            const uint32_t* piece = a.agg_split + blk_off(r, col0);
+            if (col0 < BLK_LAST) {
+              ldg256(reinterpret_cast<const float*>(piece), reinterpret_cast<float(&)[8]>(hi));
+              ldg256(reinterpret_cast<const float*>(piece + 8), reinterpret_cast<float(&)[8]>(lo));
+            } else {
+              uint32_t w[8];
+              ldg256(reinterpret_cast<const float*>(piece), reinterpret_cast<float(&)[8]>(w));
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { hi[i] = w[i]; lo[i] = w[4 + i]; }
+            }
           }
           epi_store_packed(cx, c, hi, lo);
         }
@@ -424,25 +449,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
         const float bound_next = fmaxf(cx.bound_in * m.y + extra_bound, 1.f);
         const int e_next = scale_exp(bound_next);
         const float unscale = exp2i(-cx.e_in) * m.x;
-        const float* a_row = a.A + blk_off(r, 0);      // + (col0 / 16) * TILE * 16 selects the piece
-        float* p_row = a.P + blk_off(r, 0);
         float pm = epi_layer_to_a(sh, cx, unscale, exp2i(e_next),
                                   [&](int, int col0, float (&v)[HW]) {
                                     if (valid) {
-                                      float t[8];
-#pragma unroll
-                                      for (int h = 0; h < 2; ++h) {
-                                        ldg256(a_row + (col0 >> 4) * (TILE * BLK_W) + 8 * h, t);
-#pragma unroll
-                                        for (int i = 0; i < 8; ++i) v[8 * h + i] += t[i];
-                                        ldg256(p_row + (col0 >> 4) * (TILE * BLK_W) + 8 * h, t);
-#pragma unroll
-                                        for (int i = 0; i < 8; ++i) v[8 * h + i] += t[i];
-                                      }
+                                      blk_add16(a.A, r, col0, v);
+                                      blk_add16(a.P, r, col0, v);
                                     }
                                   },
                                   [&](int, int col0, const float (&v)[HW]) {
-                                    if (!LAST && valid) stg16(p_row + (col0 >> 4) * (TILE * BLK_W), v);
+                                    if (!LAST && valid) blk_store16(a.P, r, col0, v);
                                   });
         pm = epi_exchange<true>(sh, cx, pm);
         cx.bound_in = fmaxf(pm, 1.f);                  // actual maximum of the new P row (tighter than the propagated bound)
@@ -450,7 +465,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
         if (!LAST && valid && cx.half == 0) a.rowmaxP[r] = pm;
       }
       if (next >= 0 && cx.warp % SLOT_WARPS == 0 && cx.lane == 0)   // the next tile's input rows: two layers of lead time
-        bulk_prefetch_l2(a.agg_split + (int64_t)next * TILE * FP, TILE * FP * 4);
+        bulk_prefetch_l2(a.agg_split + (int64_t)next * BLK_TILE, BLK_TILE * 4);
       if (!LAST) {
         epi_store_rows(sh, cx, meta[1], a.Qr, r, valid);
         epi_store_rows(sh, cx, meta[2], a.Qs, r, valid);
@@ -633,11 +648,16 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
   if (threadIdx.x < 3 * AGG_NODES) (&smax[0][0])[threadIdx.x] = 0;
   const int n_groups = (rows + AGG_NODES - 1) / AGG_NODES, G = gridDim.x;
   // float4 j of a row in the blocked layout (tc_chain.cuh: blk_off), as a 32-bit float4 index (the host checks that it fits):
-  // row * 4 + (row / 128) * (128 * 160 / 4 - 128 * 4) + piece offset
-  const uint32_t joff = (uint32_t)(j >> 2) * (TILE * BLK_W / 4) + (j & 3);
-  auto at = [joff](const float4* m, int row) {
-    return __ldg(m + ((uint32_t)row * (BLK_W / 4) + ((uint32_t)row >> 7) * (TILE * FP / 4 - TILE * BLK_W / 4) + joff));
-  };
+  // (row / 128) * tile + piece * 128 * 4 + (row % 128) * (floats4 per piece row) + j % 4; the narrow last piece has two float4 per
+  // row, so the threads j = 38, 39 of a row have nothing to load (their columns 152..159 are padding: they keep zeros)
+  const bool has_cols = j < BLK_COLS / 4;
+  const int jj = has_cols ? j : BLK_COLS / 4 - 1;      // the two idle threads shadow the row's last float4 (same address: no traffic)
+  const bool narrow = jj >= BLK_LAST / 4;
+  // index = row * jrow + (row / 128) * jtile + joff, all per-thread constants
+  const uint32_t jrow = narrow ? (BLK_COLS - BLK_LAST) / 4 : BLK_W / 4;
+  const uint32_t jtile = BLK_TILE / 4 - TILE * jrow;
+  const uint32_t joff = (uint32_t)(jj >> 2) * (TILE * BLK_W / 4) + (jj & 3);
+  auto at = [=](const float4* m, int row) { return __ldg(m + ((uint32_t)row * jrow + ((uint32_t)row >> 7) * jtile + joff)); };
   auto load_bounds = [&](int v, int& beg, int& end) {   // [beg, end) of this thread's row in group v (empty past the end)
     const int r = v * AGG_NODES + slot;
     beg = end = 0;
@@ -718,10 +738,13 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
       const __half2 h0 = __float22half2_rn(s0), h1 = __float22half2_rn(s1f);
       const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
       const __half2 l0 = __float22half2_rn(make_float2(s0.x - f0.x, s0.y - f0.y)), l1 = __float22half2_rn(make_float2(s1f.x - f1.x, s1f.y - f1.y));
-      // the 16 words of (row, piece = 16 columns): 8 packed hi pairs then 8 packed lo pairs
-      uint32_t* piece = agg_split + blk_off(r, 16 * (j >> 2));
-      *reinterpret_cast<uint2*>(piece + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-      *reinterpret_cast<uint2*>(piece + 8 + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      // the 16 words of (row, piece = 16 columns): 8 packed hi pairs then 8 packed lo pairs (narrow last piece: 4 then 4)
+      if (has_cols) {
+        uint32_t* piece = agg_split + blk_off(r, 16 * (j >> 2));
+        const int lo_at = narrow ? (BLK_COLS - BLK_LAST) / 2 : BLK_W / 2;
+        *reinterpret_cast<uint2*>(piece + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(piece + lo_at + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      }
       if (j == 0) { agg_exp[r] = e; agg_max[r] = mx; }
     }
     beg = beg1; end = end1; beg1 = beg2; end1 = end2;
@@ -852,7 +875,7 @@ int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t s
   using namespace tc;
   const int64_t rows = (int64_t)g->B * g->N;
   // the kernel indexes float4s with 32 bits: 40 per row (68 GB of features per buffer at the limit)
-  AGX_REQUIRE(blk_rows(rows) * (FP / 4) < (1ll << 32) && blk_rows(g->E_cap) * (FP / 4) < (1ll << 32) && g->E_cap < (1ll << 31), AGX_ERR_ARG,
+  AGX_REQUIRE(blk_rows(rows) * (BLK_COLS / 4) < (1ll << 32) && blk_rows(g->E_cap) * (BLK_COLS / 4) < (1ll << 32) && g->E_cap < (1ll << 31), AGX_ERR_ARG,
               "edge_aggregate: %lld rows / %lld relations exceed the 32-bit feature index", (long long)rows, (long long)g->E_cap);
   const int64_t groups = (rows + AGG_NODES - 1) / AGG_NODES, resident = (int64_t)num_sms() * AGG_CTAS_PER_SM;
   { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
