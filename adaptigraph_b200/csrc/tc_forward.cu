@@ -637,7 +637,8 @@ constexpr int AGG_CTAS_PER_SM = AGX_AGG_CTAS;
 // a warp-per-row variant staging C through per-warp TMA rings 0.658 (150 instructions per relation: issue-latency bound);
 // this kernel plus a bulk L2 prefetch of the next group's C / Qr rows 0.389 (the memory system is request-throughput bound on the
 // 64-byte pieces of the blocked layout, not latency bound: more requests in flight only queue); sweeping the rows in reverse so that
-// the most recently written C / Qr / Qs tiles are read first: no change (0.308 both ways).
+// the most recently written C / Qr / Qs tiles are read first: no change (0.308 both ways); 8 columns per thread with 256-bit loads
+// (19 threads per row, 4 relations in flight, half the load instructions per byte): 0.328-0.335 against 0.310-0.313 on the same box.
 __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_split_kernel(
     const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send, int rows, int N, int E_cap,
     const float4* __restrict__ C, const float4* __restrict__ Qr, const float4* __restrict__ Qs, uint32_t* __restrict__ agg_split,
