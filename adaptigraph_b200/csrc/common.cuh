@@ -57,6 +57,17 @@ struct Carver {
 };
 
 int num_sms();
+// cudaFuncSetAttribute / stream caches are per device: a host thread that switches devices must redo them
+struct DeviceOnce {
+  int dev = -1;
+  bool need() {   // true the first time it is asked on the calling thread's current device
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) return true;
+    if (d == dev) return false;
+    dev = d;
+    return true;
+  }
+};
 void set_sm_share(int n);   // thread-local: size persistent grids for n SMs (0 = all)
 
 // ---- optional per-kernel timing (agx_profile_*): CUDA events recorded on the launch stream

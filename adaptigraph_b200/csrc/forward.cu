@@ -444,13 +444,12 @@ static int check_dims(const AgxModelDims* d) {
 }
 
 static int ensure_smem_attrs() {
-  static thread_local bool done = false;
-  if (done) return AGX_OK;
+  static thread_local DeviceOnce once;
+  if (!once.need()) return AGX_OK;
   AGX_CUDA_OK(cudaFuncSetAttribute(node_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(edge_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(node_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(node_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
-  done = true;
   return AGX_OK;
 }
 
@@ -542,13 +541,12 @@ struct SplitPlan { int B0; int64_t E0, E1; int sms; };
 struct SplitStreams { cudaStream_t side; cudaEvent_t fork, offset, join; };
 static SplitStreams* split_streams() {   // per host thread, created on first use, never destroyed (process lifetime)
   static thread_local SplitStreams ss{};
-  static thread_local bool ok = false;
-  if (!ok) {
+  static thread_local DeviceOnce once;
+  if (once.need()) {
     if (cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ss.offset, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    ok = true;
   }
   return &ss;
 }

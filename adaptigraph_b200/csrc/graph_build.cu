@@ -528,6 +528,8 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
               workspace_bytes, need);
   const size_t smem = (size_t)topk * G1_THREADS * 8;   // the per-thread candidate lists of knn_rows
   static thread_local size_t smem_set = 0;
+  static thread_local DeviceOnce once;
+  if (once.need()) smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     AGX_CUDA_OK(cudaFuncSetAttribute(knn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;

@@ -206,6 +206,8 @@ int agx_fps(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int
   const size_t smem = (size_t)N * 16;
   cudaStream_t st = st0;
   static thread_local size_t set_count = 0, set_radius = 0;
+  static thread_local DeviceOnce once;
+  if (once.need()) set_count = set_radius = 0;
   if (radius < 0.0) {
     if (smem > 48 * 1024 && smem > set_count) {
       AGX_CUDA_OK(cudaFuncSetAttribute(fps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -296,6 +298,8 @@ extern "C" int agx_chamfer(const float* x, const float* y, int32_t B, int32_t N,
   AGX_REQUIRE(smem <= 200 * 1024, AGX_ERR_ARG, "chamfer: N + M = %d exceeds the shared-memory staging limit (17066 points)", N + M);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static thread_local size_t smem_set = 0;
+  static thread_local DeviceOnce once;
+  if (once.need()) smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     AGX_CUDA_OK(cudaFuncSetAttribute(chamfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;

@@ -810,8 +810,8 @@ struct TcFwdBuffers {
 };
 
 static int tc_ensure_attrs() {
-  static thread_local bool done = false;
-  if (done) return AGX_OK;
+  static thread_local DeviceOnce once;
+  if (!once.need()) return AGX_OK;
   using namespace tc;
 #ifdef AGX_TC_STAGGER
   if (const char* e = getenv("AGX_TC_STAGGER")) {
@@ -824,7 +824,6 @@ static int tc_ensure_attrs() {
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  done = true;
   return AGX_OK;
 }
 

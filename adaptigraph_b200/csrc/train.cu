@@ -474,13 +474,12 @@ static size_t scratch_carve(void* base, int64_t rows, int64_t E, TrainScratch* o
 static size_t train_base_floats() { return tc_blob_bytes(packed_layout().total * sizeof(float)) / sizeof(float); }
 
 static int train_attrs() {
-  static thread_local bool done = false;
-  if (done) return AGX_OK;
+  static thread_local DeviceOnce once;
+  if (!once.need()) return AGX_OK;
   AGX_CUDA_OK(cudaFuncSetAttribute(lin_kernel<D_NODE_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(lin_kernel<D_REL_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(lin_kernel<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
-  done = true;
   return AGX_OK;
 }
 
