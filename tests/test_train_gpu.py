@@ -135,3 +135,37 @@ def test_optimizer_state_round_trips_through_torch_adam(agx):
     assert int(tr2.step_count.item()) == 3
     ref_m = opt.state_dict()["state"][0]["exp_avg"]
     assert torch.equal(tr2.bucket.views(tr2.exp_avg)[0], ref_m.cuda())
+
+
+@pytest.mark.parametrize("material,n_p,B,pstep", [("granular", 150, 3, 2), ("cloth", 200, 2, 3)])
+def test_gradients_match_oracle_autograd_on_seeded_graphs(agx, material, n_p, B, pstep):
+    """Beyond the golden unroll (rope, 40 particles): loss and every gradient of one forward against torch autograd over the oracle's
+    dense restatement, on graphs with hundreds of particles, tool senders and padded particles (tensor-core training layers)."""
+    from adaptigraph_b200 import synthetic as syn
+    from oracle import dynamics_oracle as orc
+    w = syn.make_workload(material, n_p, B, seed=77, n_pad=6)
+    torch.manual_seed(3)
+    m = agx.DynamicsPredictor(*syn.configs(material, pstep), "cuda").cuda().train()
+    wd = w.to("cuda")
+    el = agx.build_edges(wd.state[:, -1], w.adj_thresh, wd.state_mask, wd.eef_mask, w.topk, w.connect_tools_all).check()
+    st = wd.state.clone().requires_grad_(True)
+    d = wd.graph_dict()
+    d["state"] = st
+    pos, motion = m(**d, edges=el)
+    tgt = torch.randn(pos.shape, generator=torch.Generator().manual_seed(5)).cuda() * 0.05
+    loss = torch.nn.functional.mse_loss(pos, wd.state[:, -1, :pos.shape[1]] + tgt) + 0.1 * motion.square().mean()
+    loss.backward()
+    # oracle: dense one-hots + autograd on the CPU
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    Rr, Rs = orc.edges_dense_batch(w.state[:, -1], w.adj_thresh, w.state_mask, w.eef_mask, w.topk, w.connect_tools_all)
+    st_c = w.state.clone().requires_grad_(True)
+    pos_c, motion_c = orc.forward_dense(p, pstep, st_c, w.attrs, Rr, Rs, w.p_instance, w.action, w.physics_param)
+    loss_c = torch.nn.functional.mse_loss(pos_c, w.state[:, -1, :pos_c.shape[1]] + tgt.cpu()) + 0.1 * motion_c.square().mean()
+    loss_c.backward()
+    assert abs(loss.item() - loss_c.item()) <= 1e-6 * max(1.0, abs(loss_c.item()))
+    # the default (fp32 FFMA) training layers measure <= 8e-7 here; AGX_TRAIN_PRECISION=tc would reach 1.4e-4 and fail
+    ref = st_c.grad
+    assert (st.grad.cpu() - ref).abs().max() <= 1e-5 * max(1e-3, float(ref.abs().max()))
+    for k, v in m.named_parameters():
+        ref = p[k].grad
+        assert (v.grad.cpu() - ref).abs().max() <= 1e-5 * max(1e-3, float(ref.abs().max())), k
