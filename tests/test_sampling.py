@@ -141,3 +141,36 @@ def test_gpu_fps_batch_on_device(sampling):
         ref = so.fps(pos[b, :n_pts[b]], max_nobj, radius, int(s1[b]), int(s2[b]))
         assert cnt[b] == len(ref)
         np.testing.assert_array_equal(idx[b, :cnt[b]], ref)
+
+
+def test_wrapper_host_logic_without_a_gpu(monkeypatch):
+    """The reference-signature wrappers (random draws, index composition, numpy in / out) around a stand-in for the CUDA op: with the
+    oracle behind `ops.fps`, seeded calls must reproduce the reference's own outputs — the draws happen in the reference's order."""
+    from adaptigraph_b200 import sampling
+
+    def fake_fps(pos, n_points, start_idx, max_samples, radius):
+        pos, n_points, start_idx = pos.cpu().numpy(), n_points.cpu().numpy(), start_idx.cpu().numpy()
+        B = pos.shape[0]
+        idx = np.zeros((B, max_samples), np.int32)
+        cnt = np.zeros(B, np.int32)
+        for b in range(B):
+            pts = pos[b, :n_points[b]]
+            if radius < 0:
+                sel = so.farthest_point_sampler(pts[None], max_samples, [start_idx[b]])[0]
+            else:
+                sel = so.fps_rad_idx(pts, radius, int(start_idx[b]))[1][:max_samples]
+            idx[b, :len(sel)], cnt[b] = sel, len(sel)
+        return torch.from_numpy(idx), torch.from_numpy(cnt)
+
+    monkeypatch.setattr(sampling.ops, "fps", fake_fps)
+    monkeypatch.setattr(sampling, "_device", lambda device=None: torch.device("cpu"))
+    for name in ("blob300", "dup64", "single"):
+        pcd = FPS[f"{name}/pcd"]
+        for k in range(3):
+            np.random.seed(int(FPS[f"{name}/rad{k}/seed"]))
+            pts, idx = sampling.fps_rad_idx(pcd, float(FPS[f"{name}/rad{k}/radius"]))
+            np.testing.assert_array_equal(idx, FPS[f"{name}/rad{k}/idx"])
+            rr = FPS[f"{name}/fps{k}/range"]
+            np.random.seed(int(FPS[f"{name}/fps{k}/seed"]))
+            got = sampling.fps(pcd, int(FPS[f"{name}/fps{k}/max_nobj"]), float(rr[0]) if len(rr) == 1 else list(rr))
+            np.testing.assert_array_equal(got, FPS[f"{name}/fps{k}/idx"])
