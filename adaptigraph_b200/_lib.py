@@ -16,7 +16,7 @@ AGX_FP = 160
 AGX_MAX_TOPK = 32
 AGX_SEM_BATCH, AGX_SEM_SINGLE = 0, 1
 AGX_Y_MIN, AGX_Y_MASKED_MEAN = 0, 1
-AGX_PREC_FP32, AGX_PREC_TC_F16X3 = 0, 1
+AGX_PREC_FP32, AGX_PREC_TC_F16X3, AGX_PREC_TC_MIXED = 0, 1, 2
 AGX_NUM_LAYERS = 11
 AGX_ERR_ARG, AGX_ERR_CAPACITY, AGX_ERR_CUDA = -1, -2, -3
 

@@ -34,13 +34,14 @@ struct TcFwdBuffers {
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
   int32_t* agg_exp; float* agg_max;
 };
-int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st);
+int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, cudaStream_t st);
 size_t tc_blob_bytes(size_t base_bytes);
 size_t train_blob_bytes();
 int train_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, cudaStream_t st);
 int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_t base_bytes, cudaStream_t st);
 int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, cudaStream_t st);
-int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, cudaStream_t st);
+int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool mixed,
+                    cudaStream_t st);
 int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool last,
                    float* pred_pos, int64_t pos_stride_b, float* pred_motion, cudaStream_t st);
 
@@ -456,23 +457,25 @@ static int ensure_smem_attrs() {
 static int forward_impl(const AgxModelDims* dims, const float* wts, const AgxGraphIn* g, float* pred_pos,
                         int64_t pos_stride_b, float* pred_motion, int precision, void* workspace, size_t workspace_bytes,
                         cudaStream_t st, cudaEvent_t after_encoders = nullptr) {
-  AGX_REQUIRE(precision == AGX_PREC_FP32 || precision == AGX_PREC_TC_F16X3, AGX_ERR_ARG, "unknown precision %d", precision);
+  AGX_REQUIRE(precision == AGX_PREC_FP32 || precision == AGX_PREC_TC_F16X3 || precision == AGX_PREC_TC_MIXED, AGX_ERR_ARG,
+              "unknown precision %d", precision);
   const int64_t rows = (int64_t)g->B * g->N;
   FwdWs ws;
   const size_t need = fwd_ws_carve(workspace, rows, g->E_cap, &ws);
   AGX_REQUIRE(workspace && workspace_bytes >= need, AGX_ERR_CAPACITY, "forward: workspace %zu < %zu bytes", workspace_bytes, need);
   if (int rc = ensure_smem_attrs()) return rc;
   const PackedLayout L = packed_layout();
-  if (precision == AGX_PREC_TC_F16X3) {
-    // same stages, dense layers on the tcgen05 tensor cores (tc_forward.cu)
+  if (precision != AGX_PREC_FP32) {
+    // same stages, dense layers on the tcgen05 tensor cores (tc_forward.cu); MIXED: relation chain at 2 MMAs per K step, C as C16
+    const bool mixed = precision == AGX_PREC_TC_MIXED;
     const size_t base = L.total * sizeof(float);
     const TcFwdBuffers tb{ws.nfeat, ws.P, ws.A, ws.Qr, ws.Qs, ws.agg, ws.C, ws.rowmaxP, ws.rowmaxA, ws.agg_exp, ws.agg_max};
     if (int rc = tc_node_encoder(g, wts, L, base, tb, st)) return rc;
     if (g->E_cap > 0)
-      if (int rc = tc_edge_encoder(g, wts, L, base, tb, st)) return rc;
+      if (int rc = tc_edge_encoder(g, wts, L, base, tb, mixed, st)) return rc;
     if (after_encoders) AGX_CUDA_OK(cudaEventRecord(after_encoders, st));   // the tensor-bound phase of this step is enqueued
     for (int k = 0; k < dims->pstep; ++k) {
-      if (int rc = tc_edge_aggregate(g, tb, st)) return rc;
+      if (int rc = tc_edge_aggregate(g, tb, mixed, st)) return rc;
       if (int rc = tc_node_update(g, wts, L, base, tb, k + 1 == dims->pstep, pred_pos, pos_stride_b, pred_motion, st)) return rc;
     }
     return AGX_OK;
@@ -559,7 +562,7 @@ static bool rollout_split_plan(int B, int N, int64_t E_cap, int topk, int precis
   (void)topk; (void)N;
   const char* e = getenv("AGX_ROLLOUT_SPLIT");
   if (!e || atoi(e) != 1) return false;
-  if (precision != AGX_PREC_TC_F16X3 || B < 2) return false;
+  if (precision == AGX_PREC_FP32 || B < 2) return false;
   const int sms = num_sms() / 2;
   p->B0 = B / 2;
   p->E0 = E_cap / B * p->B0;          // E_cap is per-graph capacity x B for every caller of the Python layer

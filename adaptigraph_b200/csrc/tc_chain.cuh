@@ -134,6 +134,19 @@ __device__ __forceinline__ void split16_relu(const float (&s)[HW], uint32_t (&hi
     lo[i] = cvt_rn_relu_f16x2(l.x, l.y);
   }
 }
+// hi-only variants (the consuming layer issues 2 MMAs per K step): round to nearest
+__device__ __forceinline__ void round16_relu(const float (&s)[HW], uint32_t (&hi)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) hi[i] = cvt_rn_relu_f16x2(s[2 * i], s[2 * i + 1]);
+}
+__device__ __forceinline__ void round16(const float (&v)[HW], float scale, uint32_t (&hi)[8]) {
+  const float2 sc2 = make_float2(scale, scale);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const __half2 h = __float22half2_rn(__fmul2_rn(make_float2(v[2 * i], v[2 * i + 1]), sc2));
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+}
 // signed variant for layer inputs that may be negative (hi = round-to-nearest, lo = residual)
 __device__ __forceinline__ void split16(const float (&v)[HW], float scale, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
   const float2 sc2 = make_float2(scale, scale);
@@ -188,7 +201,18 @@ __device__ __forceinline__ Shared carve_shared(uint8_t* raw) {
 //   IN_EPILOGUE  written by the previous layer's epilogue  (wait bar_a)
 //   IN_SAME      the previous layer's A is reused          (no wait)
 enum { IN_PRODUCER = 0, IN_EPILOGUE = 1, IN_SAME = 2 };
-struct LayerStep { int layer; int ksteps; int in_src; };
+// nmma: partial products issued per K step (the precision budget of the layer, tests/bench/precision_study.py):
+//   3  Alo*Whi + Ahi*Wlo + Ahi*Whi   A and W at 22 significant bits (fp32-accurate)
+//   2  Ahi*Wlo + Ahi*Whi             A rounded to fp16 (11 bits, a random per-element error), W at 22 bits; the layer's A carries
+//                                    no lo columns: the producing epilogue neither computes nor stores them
+struct LayerStep { int layer; int ksteps; int in_src; int nmma; };
+// does the A operand read by layer l need its lo columns?  (layers marked IN_SAME share the A of the layer before them)
+template <int NL>
+__host__ __device__ constexpr bool a_needs_lo(const LayerStep (&prog)[NL], int l) {
+  bool need = prog[l].nmma == 3;
+  for (int i = l + 1; i < NL && prog[i].in_src == IN_SAME; ++i) need = need || prog[i].nmma == 3;
+  return need;
+}
 
 // tiles of this CTA: t(k) = blockIdx.x + k * gridDim.x; slot s owns k = s, s + 2, ...; a "round" is one tile per slot
 __device__ __forceinline__ int cta_tile_count(int n_tiles) {
@@ -305,9 +329,10 @@ __device__ __forceinline__ void mma_role(const Shared& sh, const LayerStep (&pro
           // descriptors advance by 256 B (= 16 in the encoded start address) per K step
           uint64_t b_hi = make_b_desc(w_addr + row_off, 128, sbo);
           uint64_t b_lo = make_b_desc(w_addr + img_bytes + row_off, 128, sbo);
+          const bool three = prog[l].nmma == 3;
           for (int ks = 0; ks < ksteps; ++ks) {
-            mma_f16_ts(d_tmem, a_lo0 + 8 * ks, b_hi, idesc, ks > 0);   // small terms first
-            mma_f16_ts(d_tmem, a_hi0 + 8 * ks, b_lo, idesc, 1);
+            if (three) mma_f16_ts(d_tmem, a_lo0 + 8 * ks, b_hi, idesc, ks > 0);   // small terms first
+            mma_f16_ts(d_tmem, a_hi0 + 8 * ks, b_lo, idesc, three || ks > 0);
             mma_f16_ts(d_tmem, a_hi0 + 8 * ks, b_hi, idesc, 1);
             b_hi += 16;
             b_lo += 16;
@@ -363,10 +388,19 @@ __device__ __forceinline__ void epi_store_packed(const EpiCtx& cx, int c, const 
   tmem_st8(cx.tslot + COL_AHI + 16 * c + 8 * cx.half, hi);
   tmem_st8(cx.tslot + COL_ALO + 16 * c + 8 * cx.half, lo);
 }
+__device__ __forceinline__ void epi_store_hi(const EpiCtx& cx, int c, const uint32_t (&hi)[8]) {
+  tmem_st8(cx.tslot + COL_AHI + 16 * c + 8 * cx.half, hi);
+}
+template <bool LO = true>
 __device__ __forceinline__ void epi_store_a(const EpiCtx& cx, int c, const float (&v)[HW], float scale) {
   uint32_t hi[8], lo[8];
-  split16(v, scale, hi, lo);
-  epi_store_packed(cx, c, hi, lo);
+  if (LO) {
+    split16(v, scale, hi, lo);
+    epi_store_packed(cx, c, hi, lo);
+  } else {
+    round16(v, scale, hi);
+    epi_store_hi(cx, c, hi);
+  }
 }
 
 // wait for the next accumulator part of the slot
@@ -396,9 +430,10 @@ __device__ __forceinline__ bool owns_one(const EpiCtx& cx, int c) { return c == 
 
 // Plain hidden layer: next A = relu(acc * 2^-(e_in + sw))  (the bias is already inside acc), rescaled by `scale` and split.
 // Part A's packed results wait in registers until the layer's last MMA (part B) has completed — only then may A be overwritten.
+template <bool LO = true>
 __device__ __forceinline__ void epi_layer_plain(const Shared& sh, EpiCtx& cx, float unscale, float scale) {
   const float f = unscale * scale;
-  uint32_t hiA[NCHUNK_A][8], loA[NCHUNK_A][8];
+  uint32_t hiA[NCHUNK_A][8], loA[LO ? NCHUNK_A : 1][8];
   AGX_STAMP_EPI(cx, 20);
   epi_wait_part(sh, cx);
   AGX_STAMP_EPI(cx, 21);
@@ -413,14 +448,18 @@ __device__ __forceinline__ void epi_layer_plain(const Shared& sh, EpiCtx& cx, fl
     for (int c = 0; c < NCHUNK_A; ++c) {
       float v[HW];
       epi_scale(r[c], f, v);
-      split16_relu(v, hiA[c], loA[c]);
+      if (LO) split16_relu(v, hiA[c], loA[LO ? c : 0]);
+      else round16_relu(v, hiA[c]);
     }
   }
   AGX_STAMP_EPI(cx, 23);
   epi_wait_part(sh, cx);   // part B complete => every MMA of the layer has read A
   AGX_STAMP_EPI(cx, 24);
 #pragma unroll
-  for (int c = 0; c < NCHUNK_A; ++c) epi_store_packed(cx, c, hiA[c], loA[c]);
+  for (int c = 0; c < NCHUNK_A; ++c) {
+    if (LO) epi_store_packed(cx, c, hiA[c], loA[LO ? c : 0]);
+    else epi_store_hi(cx, c, hiA[c]);
+  }
 #pragma unroll
   for (int c = NCHUNK_A; c < NCHUNK; ++c) {
     uint32_t r[HW];
@@ -431,8 +470,13 @@ __device__ __forceinline__ void epi_layer_plain(const Shared& sh, EpiCtx& cx, fl
     epi_scale(r, f, v);
     if (owns_one(cx, c)) v[ONE_COL % HW] = scale;   // the 1 that multiplies the next layer's bias column
     uint32_t hi[8], lo[8];
-    split16_relu(v, hi, lo);
-    epi_store_packed(cx, c, hi, lo);
+    if (LO) {
+      split16_relu(v, hi, lo);
+      epi_store_packed(cx, c, hi, lo);
+    } else {
+      round16_relu(v, hi);
+      epi_store_hi(cx, c, hi);
+    }
   }
   AGX_STAMP_EPI(cx, 25);
   epi_signal(cx, &sh.bar_a[cx.slot]);
@@ -441,10 +485,10 @@ __device__ __forceinline__ void epi_layer_plain(const Shared& sh, EpiCtx& cx, fl
 
 // General layer whose result becomes the slot's next A.  per chunk: v = acc * unscale ; extra(c, col0, v) ; relu ;
 // side(c, col0, v) [e.g. store the fp32 row piece] ; split with `scale`.  Returns the thread's partial row maximum.
-template <class Extra, class Side>
+template <bool LO = true, class Extra, class Side>
 __device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, float unscale, float scale, Extra extra, Side side) {
   float mx = 0.f;
-  uint32_t hiA[NCHUNK_A][8], loA[NCHUNK_A][8];
+  uint32_t hiA[NCHUNK_A][8], loA[LO ? NCHUNK_A : 1][8];
   AGX_STAMP_EPI(cx, 40);
   epi_wait_part(sh, cx);
   AGX_STAMP_EPI(cx, 41);
@@ -463,14 +507,18 @@ __device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, fl
 #pragma unroll
       for (int i = 0; i < HW; ++i) { v[i] = fmaxf(v[i], 0.f); mx = fmaxf(mx, v[i]); }
       side(c, col0, v);
-      split16(v, scale, hiA[c], loA[c]);
+      if (LO) split16(v, scale, hiA[c], loA[LO ? c : 0]);
+      else round16(v, scale, hiA[c]);
     }
   }
   AGX_STAMP_EPI(cx, 43);
   epi_wait_part(sh, cx);   // part B complete => every MMA of the layer has read A
   AGX_STAMP_EPI(cx, 44);
 #pragma unroll
-  for (int c = 0; c < NCHUNK_A; ++c) epi_store_packed(cx, c, hiA[c], loA[c]);
+  for (int c = 0; c < NCHUNK_A; ++c) {
+    if (LO) epi_store_packed(cx, c, hiA[c], loA[LO ? c : 0]);
+    else epi_store_hi(cx, c, hiA[c]);
+  }
 #pragma unroll
   for (int c = NCHUNK_A; c < NCHUNK; ++c) {
     const int col0 = 32 * c + HW * cx.half;
@@ -485,7 +533,7 @@ __device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, fl
     for (int i = 0; i < HW; ++i) { v[i] = fmaxf(v[i], 0.f); mx = fmaxf(mx, v[i]); }
     side(c, col0, v);
     if (owns_one(cx, c)) v[ONE_COL % HW] = 1.f;   // after the fp32 side store: only the tensor-memory copy carries the 1
-    epi_store_a(cx, c, v, scale);
+    epi_store_a<LO>(cx, c, v, scale);
   }
   AGX_STAMP_EPI(cx, 45);
   epi_signal(cx, &sh.bar_a[cx.slot]);

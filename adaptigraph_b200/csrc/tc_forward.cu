@@ -9,6 +9,17 @@ namespace tc {
 
 constexpr float MOTION_CLAMP = 100.f;  // model.py:85
 
+// Per-layer MMA budget (tc_chain.cuh: LayerStep::nmma).  Measured with tests/bench/precision_study.py (10-step cloth rollout against
+// float64, relations rebuilt every step; profiles/r02_precision_study.txt): the relation chain tolerates fp16-rounded activations
+// (every relation's error is independent and seven of them are averaged into a particle: 3.4e-6 RMSE for all three layers together),
+// the particle chains do not (each single layer costs 0.7-1.5e-5: their errors enter the residual stream directly).
+#ifndef AGX_MMA_EDGE
+#define AGX_MMA_EDGE 2      // relation_encoder.model.2 / .4 and the relation part of relation_propagator
+#endif
+#ifndef AGX_MMA_NODE
+#define AGX_MMA_NODE 3      // every particle-side layer
+#endif
+
 // ------------------------------------------------------------------------------------ weight images
 struct PackSpec {
   const float* W; const float* bias; int ld, col0, K, F;   // source: W[n*ld + col0 + k], n < F, k < K
@@ -163,27 +174,41 @@ __device__ __forceinline__ void blk_add16(const float* base, int64_t row, int co
     for (int i = 0; i < 8; ++i) v[8 + i] += t[i];
   }
 }
+// Qr / Qs (the per-particle products every relation gathers) are kept ROW-major with the padded stride FP: a sender's row is five
+// whole 128-byte lines for the aggregate's gather (the blocked layout would hand it ten half-used lines per relation, and the L1
+// data pipe, one line per cycle, is what bounds that kernel); the writers' stores are a fiftieth of the traffic.
+__device__ __forceinline__ void row_store16(float* base, int64_t row, int col0, const float (&v)[HW]) {
+  float* p = base + row * FP + col0;
+  const float a[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+  const float b[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+  stg256(p, a);
+  stg256(p + 8, b);
+}
 struct NoExtra { __device__ void operator()(int, int, float (&)[HW]) const {} };
 struct NoSide { __device__ void operator()(int, int, const float (&)[HW]) const {} };
 
 // plain hidden layer (bias inside the MMA): relu(acc) -> the slot's next A; the row bound is propagated, no row maximum needed
+template <bool LO = true>
 __device__ __forceinline__ void epi_hidden(const Shared& sh, EpiCtx& cx, const float4 meta_l) {
   const float bound_next = fmaxf(cx.bound_in * meta_l.y, 1.f);
   const int e_next = scale_exp(bound_next);
-  epi_layer_plain(sh, cx, exp2i(-cx.e_in) * meta_l.x, exp2i(e_next));
+  epi_layer_plain<LO>(sh, cx, exp2i(-cx.e_in) * meta_l.x, exp2i(e_next));
   cx.bound_in = bound_next;
   cx.e_in = e_next;
 }
 
 // acc (bias inside the MMA) -> fp32 rows in HBM (A is left untouched); returns this thread's partial max |v|
-template <class AllRead = NoHook>
+template <bool ROW_MAJOR = false, class AllRead = NoHook>
 __device__ __forceinline__ float epi_store_rows(const Shared& sh, EpiCtx& cx, const float4 meta_l, float* out, int64_t grow, bool valid,
                                                 AllRead all_read = AllRead{}) {
   const float unscale = exp2i(-cx.e_in) * meta_l.x;
   float mx = 0.f;
   epi_layer_out<false>(sh, cx, unscale, [&](int, int col0, float (&v)[HW]) {
     mx = max16(v, mx);
-    if (valid) blk_store16(out, grow, col0, v);
+    if (valid) {
+      if (ROW_MAJOR) row_store16(out, grow, col0, v);
+      else blk_store16(out, grow, col0, v);
+    }
   }, all_read);
   return mx;
 }
@@ -194,13 +219,47 @@ __device__ __forceinline__ int slot_tile(int k_slot, int slot, int n_tiles) {
   return t < n_tiles ? t : -1;
 }
 
+// ------------------------------------------------------------------------------------ C in 16-bit block fixed point
+// AGX_PREC_TC_MIXED stores the per-relation term C = W_rel * renc + b (written once, read by every propagation step: 47 % of the
+// bytes a model step moves when kept in fp32) as 16-bit fixed point with one power-of-two scale per (relation, 16-column piece):
+// a row is C16_ROW = 320 bytes = 152 offset-binary uint16 (u = rint(c * 2^e) + 32768, |c * 2^e| <= 2^14) followed by 16 bytes of
+// piece exponents (int8 e; byte 8 * (p & 1) + (p >> 1) belongs to piece p: the two column halves of an epilogue slot each own the
+// pieces of one parity and write their five exponents with one 8-byte store).  Rows are plain row-major, so the CSR-ordered
+// relations of consecutive receivers are one contiguous range: the aggregate stages them with one bulk (TMA) copy per receiver.
+// Error: <= 2^-15 of the piece maximum per element (rollout RMSE 7e-7 on its own, tests/bench/precision_study.py).
+constexpr int C16_ROW = 320;                // bytes per relation
+constexpr int C16_EXP_OFF = 2 * BLK_COLS;   // 304: byte offset of the exponent block
+constexpr float C16_MAGIC = 8421376.f;      // 2^23 + 32768: float bits of (v + MAGIC) carry rint(v) + 32768 in their low 16 bits
+
+// this thread's 16 columns [col0, col0 + 16) of relation row `row` -> C16; returns the piece exponent
+__device__ __forceinline__ int c16_store16(uint8_t* base, int64_t row, int col0, const float (&v)[HW]) {
+  const float mx = max16(v, 0.f);
+  const int e = scale_exp(mx);
+  const float sc = exp2i(e);
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t a = __float_as_uint(fmaf(v[2 * i], sc, C16_MAGIC)), b = __float_as_uint(fmaf(v[2 * i + 1], sc, C16_MAGIC));
+    w[i] = __byte_perm(a, b, 0x5410);       // {a.lo16, b.lo16}
+  }
+  uint8_t* p = base + row * C16_ROW + 2 * col0;
+  if (col0 < BLK_LAST) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+                 "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+  } else {                                   // narrow last piece: columns 144..151
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  return e;
+}
+
 // ------------------------------------------------------------------------------------ edge encoder
 struct EdgeArgs {
   const int32_t* row_ptr; const int32_t* send; const int32_t* recv;
   int64_t rows; int N; int64_t E_cap;
   const float* nfeat;
   const uint8_t* blob; TcLayout L;
-  float* C;
+  float* C;          // fp32 blocked rows (AGX_PREC_TC_F16X3) or C16 rows (AGX_PREC_TC_MIXED)
 };
 
 // 17 relation inputs (model.py:224-253) of the K=32 first layer; half 0 builds inputs 0..15, half 1 input 16 (+ zero padding)
@@ -224,9 +283,12 @@ __device__ __forceinline__ void edge_inputs(const EdgeArgs& a, int64_t e, int64_
   }
 }
 
+template <bool MIXED>
 __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr LayerStep prog[4] = {{T_RENC0, 2, IN_PRODUCER}, {T_RENC2, 10, IN_EPILOGUE}, {T_RENC4, 10, IN_EPILOGUE}, {T_RP_REL, 10, IN_EPILOGUE}};
+  constexpr int NM = MIXED ? AGX_MMA_EDGE : 3;
+  constexpr LayerStep prog[4] = {{T_RENC0, 2, IN_PRODUCER, 3}, {T_RENC2, 10, IN_EPILOGUE, NM}, {T_RENC4, 10, IN_EPILOGUE, NM},
+                                 {T_RP_REL, 10, IN_EPILOGUE, NM}};
   Shared sh;
   float4 meta[4];
   const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, meta);
@@ -268,12 +330,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
       cx.e_in = in_exp;
       cx.bound_in = in_bound;
       const int next = slot_tile(k + 1, cx.slot, n_tiles);
-      epi_hidden(sh, cx, meta[0]);
-      epi_hidden(sh, cx, meta[1]);
-      epi_hidden(sh, cx, meta[2]);
+      epi_hidden<a_needs_lo(prog, 1)>(sh, cx, meta[0]);
+      epi_hidden<a_needs_lo(prog, 2)>(sh, cx, meta[1]);
+      epi_hidden<a_needs_lo(prog, 3)>(sh, cx, meta[2]);
       AGX_STAMP_EPI(cx, 31);
       if (next >= 0) produce(next);
-      epi_store_rows(sh, cx, meta[3], a.C, e, e < E, [&]() { if (next >= 0) commit(); });
+      if (!MIXED) {
+        epi_store_rows(sh, cx, meta[3], a.C, e, e < E, [&]() { if (next >= 0) commit(); });
+      } else {
+        uint8_t* c16 = reinterpret_cast<uint8_t*>(a.C);
+        uint64_t exps = 0;                 // byte c = exponent of this thread's piece of chunk c
+        epi_layer_out<false>(sh, cx, exp2i(-cx.e_in) * meta[3].x, [&](int c, int col0, float (&v)[HW]) {
+          if (e < E) exps |= (uint64_t)(uint8_t)(int8_t)c16_store16(c16, e, col0, v) << (8 * c);
+        }, [&]() { if (next >= 0) commit(); });
+        if (e < E) *reinterpret_cast<uint64_t*>(c16 + e * C16_ROW + C16_EXP_OFF + 8 * cx.half) = exps;
+      }
       tile = next;
     }
   }
@@ -315,8 +386,8 @@ __device__ __forceinline__ void node_inputs(const NodeArgs& a, int64_t r, int64_
 
 __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr LayerStep prog[6] = {{T_PENC0, 1, IN_PRODUCER}, {T_PENC2, 10, IN_EPILOGUE}, {T_PENC4, 10, IN_EPILOGUE},
-                                 {T_PP_ENC, 10, IN_EPILOGUE}, {T_RP_RECV, 10, IN_SAME}, {T_RP_SEND, 10, IN_SAME}};
+  constexpr LayerStep prog[6] = {{T_PENC0, 1, IN_PRODUCER, 3}, {T_PENC2, 10, IN_EPILOGUE, AGX_MMA_NODE}, {T_PENC4, 10, IN_EPILOGUE, AGX_MMA_NODE},
+                                 {T_PP_ENC, 10, IN_EPILOGUE, AGX_MMA_NODE}, {T_RP_RECV, 10, IN_SAME, AGX_MMA_NODE}, {T_RP_SEND, 10, IN_SAME, AGX_MMA_NODE}};
   Shared sh;
   float4 meta[6];
   const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, meta);
@@ -346,13 +417,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
       if (cx.half == 0) epi_store_a(cx, 0, in, exp2i(cx.e_in));   // the K=16 layer reads A columns 0..7 only
       epi_signal(cx, &sh.bar_in[cx.slot]);
 
-      epi_hidden(sh, cx, meta[0]);
-      epi_hidden(sh, cx, meta[1]);
+      epi_hidden<a_needs_lo(prog, 1)>(sh, cx, meta[0]);
+      epi_hidden<a_needs_lo(prog, 2)>(sh, cx, meta[1]);
       {  // particle_encode = particle_effect_0 (model.py:268-269): next A and the fp32 P rows (with their row maximum)
         const float4 m = meta[2];
         const float bound_next = fmaxf(cx.bound_in * m.y, 1.f);
         const int e_next = scale_exp(bound_next);
-        float pm = epi_layer_to_a(sh, cx, exp2i(-cx.e_in) * m.x, exp2i(e_next), NoExtra{}, [&](int, int col0, const float (&v)[HW]) {
+        float pm = epi_layer_to_a<a_needs_lo(prog, 3)>(sh, cx, exp2i(-cx.e_in) * m.x, exp2i(e_next), NoExtra{}, [&](int, int col0, const float (&v)[HW]) {
           if (valid) blk_store16(a.P, r, col0, v);
         });
         pm = epi_exchange<true>(sh, cx, pm);
@@ -363,8 +434,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
       float am = epi_store_rows(sh, cx, meta[3], a.A, r, valid);   // A_n = W_enc*penc + b
       am = epi_exchange<true>(sh, cx, am);
       if (valid && cx.half == 0) a.rowmaxA[r] = am;
-      epi_store_rows(sh, cx, meta[4], a.Qr, r, valid);
-      epi_store_rows(sh, cx, meta[5], a.Qs, r, valid);
+      epi_store_rows<true>(sh, cx, meta[4], a.Qr, r, valid);
+      epi_store_rows<true>(sh, cx, meta[5], a.Qs, r, valid);
       tile = slot_tile(k + 1, cx.slot, n_tiles);
     }
   }
@@ -385,8 +456,8 @@ struct UpdArgs {
 template <bool LAST>
 __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr LayerStep prog[3] = {{T_PP_AGG, 10, IN_PRODUCER}, {LAST ? T_PRED0 : T_RP_RECV, 10, IN_EPILOGUE},
-                                 {LAST ? T_PRED1 : T_RP_SEND, 10, LAST ? IN_EPILOGUE : IN_SAME}};
+  constexpr LayerStep prog[3] = {{T_PP_AGG, 10, IN_PRODUCER, 3}, {LAST ? T_PRED0 : T_RP_RECV, 10, IN_EPILOGUE, AGX_MMA_NODE},
+                                 {LAST ? T_PRED1 : T_RP_SEND, 10, LAST ? IN_EPILOGUE : IN_SAME, AGX_MMA_NODE}};
   Shared sh;
   float4 meta[3];
   const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, meta);
@@ -449,7 +520,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
         const float bound_next = fmaxf(cx.bound_in * m.y + extra_bound, 1.f);
         const int e_next = scale_exp(bound_next);
         const float unscale = exp2i(-cx.e_in) * m.x;
-        float pm = epi_layer_to_a(sh, cx, unscale, exp2i(e_next),
+        float pm = epi_layer_to_a<a_needs_lo(prog, 1)>(sh, cx, unscale, exp2i(e_next),
                                   [&](int, int col0, float (&v)[HW]) {
                                     if (valid) {
                                       blk_add16(a.A, r, col0, v);
@@ -467,10 +538,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
       if (next >= 0 && cx.warp % SLOT_WARPS == 0 && cx.lane == 0)   // the next tile's input rows: two layers of lead time
         bulk_prefetch_l2(a.agg_split + (int64_t)next * BLK_TILE, BLK_TILE * 4);
       if (!LAST) {
-        epi_store_rows(sh, cx, meta[1], a.Qr, r, valid);
-        epi_store_rows(sh, cx, meta[2], a.Qs, r, valid);
+        epi_store_rows<true>(sh, cx, meta[1], a.Qr, r, valid);
+        epi_store_rows<true>(sh, cx, meta[2], a.Qs, r, valid);
       } else {
-        epi_hidden(sh, cx, meta[1]);
+        epi_hidden<a_needs_lo(prog, 2)>(sh, cx, meta[1]);
         // motion head (model.py:306-309): relu(linear_1) then the 3-row linear_2 as running dot products
         const float unscale = exp2i(-cx.e_in) * meta[2].x;
         float m0 = 0.f, m1 = 0.f, m2 = 0.f;
@@ -525,7 +596,7 @@ struct LinTcArgs {
 
 __global__ void __launch_bounds__(THREADS, 1) tc_lin_kernel(const LinTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  const LayerStep prog[1] = {{a.layer, 10, IN_PRODUCER}};
+  const LayerStep prog[1] = {{a.layer, 10, IN_PRODUCER, 3}};
   Shared sh;
   float4 meta[1];
   const uint32_t tmem_base = chain_setup(sh, smem_raw, prog, a.blob, a.L, meta);
@@ -659,6 +730,7 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
   const uint32_t jtile = BLK_TILE / 4 - TILE * jrow;
   const uint32_t joff = (uint32_t)(jj >> 2) * (TILE * BLK_W / 4) + (jj & 3);
   auto at = [=](const float4* m, int row) { return __ldg(m + ((uint32_t)row * jrow + ((uint32_t)row >> 7) * jtile + joff)); };
+  auto atq = [=](const float4* m, int row) { return __ldg(m + ((uint32_t)row * (FP / 4) + jj)); };   // Qr / Qs: row-major, stride FP
   auto load_bounds = [&](int v, int& beg, int& end) {   // [beg, end) of this thread's row in group v (empty past the end)
     const int r = v * AGG_NODES + slot;
     beg = end = 0;
@@ -686,14 +758,14 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
     float4 c[AGG_BATCH], q[AGG_BATCH];
     const int n0 = min(end - beg, AGG_BATCH);
     float4 qr = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) qr = at(Qr, r);
+    if (valid) qr = atq(Qr, r);
     if (n0 > 0) {
       const int32_t* my = ids[it & 1][slot];
 #pragma unroll
       for (int u = 0; u < AGG_BATCH; ++u) {
         const int uu = min(u, n0 - 1);                    // past-the-end slots repeat the last relation (masked below)
         c[u] = at(C, beg + uu);
-        q[u] = at(Qs, gb + my[uu]);
+        q[u] = atq(Qs, gb + my[uu]);
       }
     }
     // index data of the groups to come (their latency hides behind this group's feature rows)
@@ -715,7 +787,7 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
       for (int u = 0; u < AGG_BATCH; ++u) {
         const int uu = min(u, n - 1);
         c[u] = at(C, e0 + uu);
-        q[u] = at(Qs, gb + __ldg(send + e0 + uu));
+        q[u] = atq(Qs, gb + __ldg(send + e0 + uu));
       }
 #pragma unroll
       for (int u = 0; u < AGG_BATCH; ++u) {
@@ -746,6 +818,179 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
         *reinterpret_cast<uint2*>(piece + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
         *reinterpret_cast<uint2*>(piece + lo_at + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
       }
+      if (j == 0) { agg_exp[r] = e; agg_max[r] = mx; }
+    }
+    beg = beg1; end = end1; beg1 = beg2; end1 = end2;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------ edge aggregate on C16 (AGX_PREC_TC_MIXED)
+// Same reduction with C in the 16-bit block format above.  38 threads per receiver (4 columns each: 8 bytes of C16, one float4 of
+// the row-major fp32 Qr / Qs rows), 8 receivers per group, persistent CTAs as above.  C never goes through registers or L1 on its
+// way in: the first A16_BATCH relations of a receiver are one contiguous run of C16 rows, which thread 0 of the receiver's slot
+// brings into shared memory with ONE bulk copy of the TMA engine (cp.async.bulk + mbarrier transaction count), a whole group ahead
+// of its use -- next to the sender ids (cp.async) and the row_ptr pairs (two groups ahead).  What a thread waits for per group is
+// therefore only the Qs gather it has in flight (A16_BATCH float4).
+// The inner loop is branch-free: all A16_BATCH staged slots are always evaluated and a 0 / 1 factor in the accumulating FMA drops
+// the ones past the receiver's degree (they read whatever well-formed rows and sender ids an earlier group left in shared memory,
+// which is zero-initialised), because on this kernel the instruction issue and the L1 data pipe, not DRAM, are the bound: r02a's
+// ncu capture of the first version (per-relation branches, generic loads, 64-register build with spills) showed 120 issued warp
+// instructions per relation, 39 % DRAM utilisation and the L1 data pipe at 73 %.
+#ifndef AGX_A16_CTAS
+#define AGX_A16_CTAS 2
+#endif
+constexpr int A16_NODES = 8;
+constexpr int A16_LANES = BLK_COLS / 4;                // 38
+constexpr int A16_THREADS = A16_NODES * A16_LANES;     // 304
+constexpr int A16_BATCH = 8;
+constexpr int A16_CBUF = A16_NODES * A16_BATCH * C16_ROW;   // bytes per stage
+constexpr size_t A16_SMEM = 2 * (size_t)A16_CBUF + 128;
+
+__device__ __forceinline__ uint2 lds64u(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds_s8(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+__global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_kernel(
+    const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send, int rows, int N, int E_cap,
+    const uint8_t* __restrict__ C16, const float4* __restrict__ Qr, const float4* __restrict__ Qs, uint32_t* __restrict__ agg_split,
+    int32_t* __restrict__ agg_exp, float* __restrict__ agg_max) {
+  extern __shared__ uint8_t a16_raw[];
+  __shared__ int smax[3][A16_NODES];
+  __shared__ __align__(16) int32_t ids[2][A16_NODES][A16_BATCH];
+  __shared__ __align__(8) uint64_t bar[2];
+  uint8_t* cbuf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a16_raw) + 127) & ~(uintptr_t)127);   // [2][NODES][BATCH][C16_ROW]
+  const int slot = threadIdx.x / A16_LANES, j = threadIdx.x - slot * A16_LANES;
+  if (threadIdx.x < 3 * A16_NODES) (&smax[0][0])[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < 2 * A16_NODES * A16_BATCH; i += A16_THREADS) (&ids[0][0][0])[i] = 0;
+  for (int i = threadIdx.x; i < 2 * A16_CBUF / 16; i += A16_THREADS) reinterpret_cast<uint4*>(cbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], A16_NODES);
+    mbar_init(&bar[1], A16_NODES);
+    fence_mbar_init();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill (generic proxy) is ordered before the bulk copies (async proxy)
+  __syncthreads();
+  const int n_groups = (rows + A16_NODES - 1) / A16_NODES, G = gridDim.x;
+  // this thread's 4 columns [4j, 4j + 4): a quarter of piece p = j >> 2 (the narrow last piece has two quarters)
+  const int p = j >> 2;
+  const bool narrow = 4 * j >= BLK_LAST;
+  // shared-memory byte addresses of this thread's data inside stage 0 (stage 1: + A16_CBUF / + sizeof(ids[0]))
+  const uint32_t c_at = smem_u32(cbuf) + (uint32_t)slot * (A16_BATCH * C16_ROW) + 8u * j;
+  const uint32_t e_at = smem_u32(cbuf) + (uint32_t)slot * (A16_BATCH * C16_ROW) + C16_EXP_OFF + 8 * (p & 1) + (p >> 1);
+  const uint32_t id_at = smem_u32(&ids[0][slot][0]);
+  const float4* qs_j = Qs + j;
+  auto load_bounds = [&](int v, int& beg, int& end) {
+    const int r = v * A16_NODES + slot;
+    beg = end = 0;
+    if (v < n_groups && r < rows) { beg = min(__ldg(row_ptr + r), E_cap); end = min(__ldg(row_ptr + r + 1), E_cap); }
+  };
+  // sender ids by cp.async (threads j < BATCH), the C16 rows of the first BATCH relations by one bulk copy (thread j == 0)
+  auto stage = [&](int buf, int beg, int end) {
+    if (j < A16_BATCH && beg + j < end)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&ids[buf][slot][j])), "l"(send + beg + j) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (j == 0) {
+      const int n = min(end - beg, A16_BATCH);
+      if (n > 0) {
+        mbar_arrive_expect_tx(&bar[buf], (uint32_t)n * C16_ROW);
+        bulk_g2s(cbuf + (size_t)buf * A16_CBUF + (size_t)slot * A16_BATCH * C16_ROW, C16 + (size_t)beg * C16_ROW, (uint32_t)n * C16_ROW, &bar[buf]);
+      } else {
+        mbar_arrive(&bar[buf]);
+      }
+    }
+  };
+  // acc += m * relu((c + qr) + qs),  c = (u16 - 32768) * 2^-e as one FMA on the float whose mantissa holds u16 (packed fp32 pairs)
+  auto accumulate = [&](const uint2 w, int e, const float4 qr, const float4 qs, float m, float4& acc) {
+    const float sc = __uint_as_float((uint32_t)(127 - e) << 23), off = -C16_MAGIC * sc;
+    const float2 sc2 = make_float2(sc, sc), off2 = make_float2(off, off), m2 = make_float2(m, m);
+    float2 c0 = __ffma2_rn(make_float2(__uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7432))), sc2, off2);
+    float2 c1 = __ffma2_rn(make_float2(__uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7432))), sc2, off2);
+    c0 = __fadd2_rn(__fadd2_rn(c0, make_float2(qr.x, qr.y)), make_float2(qs.x, qs.y));
+    c1 = __fadd2_rn(__fadd2_rn(c1, make_float2(qr.z, qr.w)), make_float2(qs.z, qs.w));
+    const float2 a0 = __ffma2_rn(make_float2(fmaxf(c0.x, 0.f), fmaxf(c0.y, 0.f)), m2, make_float2(acc.x, acc.y));
+    const float2 a1 = __ffma2_rn(make_float2(fmaxf(c1.x, 0.f), fmaxf(c1.y, 0.f)), m2, make_float2(acc.z, acc.w));
+    acc = make_float4(a0.x, a0.y, a1.x, a1.y);
+  };
+
+  int beg, end, beg1, end1;
+  uint32_t parity = 0;   // bit b: phase to wait for on bar[b]
+  load_bounds(blockIdx.x, beg, end);
+  load_bounds(blockIdx.x + G, beg1, end1);
+  stage(0, beg, end);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  for (int it = 0, v = blockIdx.x; v < n_groups; v += G, ++it) {
+    const int buf = it & 1;
+    const int r = v * A16_NODES + slot;
+    const bool valid = r < rows;
+    const int gb = valid ? (r / N) * N : 0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 q[A16_BATCH];
+    const int n0 = min(end - beg, A16_BATCH);
+    float4 qr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) qr = __ldg(Qr + (uint32_t)r * (FP / 4) + j);
+    {
+      const float4* qrow = qs_j + (uint32_t)gb * (FP / 4);
+      const uint32_t ida = id_at + buf * (uint32_t)sizeof(ids[0]);
+#pragma unroll
+      for (int u = 0; u < A16_BATCH; ++u) q[u] = __ldg(qrow + (uint32_t)lds_s32(ida + 4 * u) * (FP / 4));   // slots past the degree: a stale (valid) id
+    }
+    // index data and C rows of the groups to come
+    int beg2, end2;
+    stage(buf ^ 1, beg1, end1);
+    load_bounds(v + 2 * G, beg2, end2);
+    mbar_wait(&bar[buf], (parity >> buf) & 1);     // this group's C16 rows have landed
+    parity ^= 1u << buf;
+    {
+      const uint32_t ca = c_at + buf * A16_CBUF, ea = e_at + buf * A16_CBUF;
+#pragma unroll
+      for (int u = 0; u < A16_BATCH; ++u)
+        accumulate(lds64u(ca + u * C16_ROW), lds_s8(ea + u * C16_ROW), qr, q[u], u < n0 ? 1.f : 0.f, acc);
+    }
+    for (int e0 = beg + A16_BATCH; e0 < end; ++e0) {   // receivers with more than BATCH relations: the rest straight from global memory
+      const uint8_t* crow = C16 + (size_t)e0 * C16_ROW;
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(crow + 8 * j));
+      const int e = (int)(int8_t)__ldg(crow + C16_EXP_OFF + 8 * (p & 1) + (p >> 1));
+      accumulate(w, e, qr, __ldg(qs_j + (uint32_t)(gb + __ldg(send + e0)) * (FP / 4)), 1.f, acc);
+    }
+    // row maximum (agg >= 0, so the int view of the floats orders like the floats): one warp-level reduction per receiver segment
+    // of the warp, then one shared-memory atomic per segment instead of one per thread
+    int* mxs = smax[it % 3];
+    {
+      const int mine = __float_as_int(fmaxf(fmaxf(acc.x, acc.y), fmaxf(acc.z, acc.w)));
+      const unsigned peers = __match_any_sync(0xffffffffu, slot);
+      const int seg = __reduce_max_sync(peers, mine);
+      if (valid && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicMax(&mxs[slot], seg);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // the next group's sender ids have landed ...
+    __syncthreads();                                       // ... and are visible; row maxima complete; everyone is done with cbuf[buf]
+    if (threadIdx.x < A16_NODES) smax[(it + 2) % 3][threadIdx.x] = 0;
+    if (valid) {
+      const float mx = __int_as_float(mxs[slot]);
+      const int e = scale_exp(mx);
+      const float sc = exp2i(e);
+      const float2 s0 = __fmul2_rn(make_float2(acc.x, acc.y), make_float2(sc, sc)), s1f = __fmul2_rn(make_float2(acc.z, acc.w), make_float2(sc, sc));
+      const __half2 h0 = __float22half2_rn(s0), h1 = __float22half2_rn(s1f);
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      const __half2 l0 = __float22half2_rn(make_float2(s0.x - f0.x, s0.y - f0.y)), l1 = __float22half2_rn(make_float2(s1f.x - f1.x, s1f.y - f1.y));
+      // the 16 words of (row, piece = 16 columns): 8 packed hi pairs then 8 packed lo pairs (narrow last piece: 4 then 4)
+      uint32_t* piece = agg_split + blk_off(r, 16 * p);
+      const int lo_at = narrow ? (BLK_COLS - BLK_LAST) / 2 : BLK_W / 2;
+      *reinterpret_cast<uint2*>(piece + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      *reinterpret_cast<uint2*>(piece + lo_at + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
       if (j == 0) { agg_exp[r] = e; agg_max[r] = mx; }
     }
     beg = beg1; end = end1; beg1 = beg2; end1 = end2;
@@ -819,7 +1064,9 @@ static int tc_ensure_attrs() {
     AGX_CUDA_OK(cudaMemcpyToSymbol(g_tc_stagger, &v, sizeof(v)));
   }
 #endif
-  AGX_CUDA_OK(cudaFuncSetAttribute(tc_edge_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute(tc_edge_encoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute(tc_edge_encoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute(edge_aggregate_c16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A16_SMEM));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -841,7 +1088,8 @@ int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
   return AGX_OK;
 }
 
-int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, cudaStream_t st) {
+int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool mixed,
+                    cudaStream_t st) {
   using namespace tc;
   if (int rc = tc_ensure_attrs()) return rc;
   const int64_t rows = (int64_t)g->B * g->N;
@@ -849,7 +1097,9 @@ int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
   EdgeArgs a{g->row_ptr, g->send, g->recv, rows, g->N, g->E_cap, w.nfeat, reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
              w.C};
   { ProfScope ps(AGX_KIND_EDGE_ENCODER, st);
-    tc_edge_encoder_kernel<<<(int)(tiles < num_sms() ? tiles : num_sms()), THREADS, SMEM_BYTES, st>>>(a); }
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    if (mixed) tc_edge_encoder_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
+    else tc_edge_encoder_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(a); }
   AGX_LAUNCH_CHECK();
   return AGX_OK;
 }
@@ -871,9 +1121,22 @@ int tc_lin(cudaStream_t st, const void* packed, size_t base_bytes, int layer, co
   return AGX_OK;
 }
 
-int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st) {
+int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, cudaStream_t st) {
   using namespace tc;
   const int64_t rows = (int64_t)g->B * g->N;
+  if (mixed) {
+    if (int rc = tc_ensure_attrs()) return rc;
+    // the kernel indexes the blocked fp32 rows with 32-bit float offsets
+    AGX_REQUIRE(blk_rows(rows) * (FP / 4) < (1ll << 32) && g->E_cap < (1ll << 31), AGX_ERR_ARG,
+                "edge_aggregate: %lld rows / %lld relations exceed the 32-bit feature index", (long long)rows, (long long)g->E_cap);
+    const int64_t groups = (rows + A16_NODES - 1) / A16_NODES, resident = (int64_t)num_sms() * AGX_A16_CTAS;
+    { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
+      edge_aggregate_c16_kernel<<<(unsigned)(groups < resident ? groups : resident), A16_THREADS, A16_SMEM, st>>>(
+          g->row_ptr, g->send, (int)rows, g->N, (int)g->E_cap, reinterpret_cast<const uint8_t*>(w.C), reinterpret_cast<const float4*>(w.Qr),
+          reinterpret_cast<const float4*>(w.Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max); }
+    AGX_LAUNCH_CHECK();
+    return AGX_OK;
+  }
   // the kernel indexes float4s with 32 bits: 40 per row (68 GB of features per buffer at the limit)
   AGX_REQUIRE(blk_rows(rows) * (BLK_COLS / 4) < (1ll << 32) && blk_rows(g->E_cap) * (BLK_COLS / 4) < (1ll << 32) && g->E_cap < (1ll << 31), AGX_ERR_ARG,
               "edge_aggregate: %lld rows / %lld relations exceed the 32-bit feature index", (long long)rows, (long long)g->E_cap);

@@ -80,6 +80,7 @@ def rollout_episodes(model, episodes: Sequence[Dict], dataset_config: Dict, get_
                 eef_e[e, i] = ep["eef_pos"][sched[i + 1][1]]
     up = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
     gt, eef_s, eef_e = up(gt), up(eef_s), up(eef_e)
+    live_d = up(live)
 
     def stack(key, dtype=None):
         t = torch.stack([torch.as_tensor(ep["graph"][key]) for ep in episodes]).to(dev)
@@ -117,8 +118,12 @@ def rollout_episodes(model, episodes: Sequence[Dict], dataset_config: Dict, get_
             states = torch.cat([pred_state, eef_s[:, i]], dim=1)                                # (E, N, 3)
             action = torch.zeros_like(states)
             action[:, max_nobj:max_nobj + n_eef] = eef_e[:, i] - eef_s[:, i]
-            row_ptr, send, recv, n_edges, status = ops.graph_build(states, state_mask, eef_mask, thr2, topk, bool(connect_tool_all),
-                                                                   L.AGX_SEM_SINGLE, E * max_nR)
+            # episodes that have ended keep stepping on a meaningless state (tools at the origin): their particles are masked
+            # out of the builder, so they own no relations and cannot raise the capacity error for the batch -- the reference
+            # would have returned normally for each of them
+            alive = live_d[:, i + 1]
+            row_ptr, send, recv, n_edges, status = ops.graph_build(states, state_mask & alive[:, None], eef_mask, thr2, topk,
+                                                                   bool(connect_tool_all), L.AGX_SEM_SINGLE, E * max_nR)
             edges = EdgeList(row_ptr, send, recv, n_edges, status, E, N)
             worst = torch.maximum(worst, n_edges.max())
             overflow |= status
@@ -129,7 +134,7 @@ def rollout_episodes(model, episodes: Sequence[Dict], dataset_config: Dict, get_
     err = errors.cpu().numpy()
     out = [[float(x) for x in err[e, :len(s)]] for e, s in enumerate(scheds)]
     if preds is not None:
-        preds *= up(live)[:, :, None, None]
+        preds *= live_d[:, :, None, None]
         return out, preds
     return out
 

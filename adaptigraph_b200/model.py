@@ -25,7 +25,9 @@ from . import ops
 from .graph import EdgeList, edges_from_onehots, _thr2_batch
 
 
-_PRECISIONS = {"fp32": L.AGX_PREC_FP32, "tc": L.AGX_PREC_TC_F16X3}
+# "fp32": exact FFMA tiles; "tc3": tcgen05 split-fp16, 3 MMAs per product everywhere (fp32-accurate); "tc" (default): the same with
+# the relation chain at 2 MMAs per product and the per-relation term stored as 16-bit block fixed point (include/adaptigraph_b200.h)
+_PRECISIONS = {"fp32": L.AGX_PREC_FP32, "tc3": L.AGX_PREC_TC_F16X3, "tc": L.AGX_PREC_TC_MIXED}
 
 
 class _EncoderParams(nn.Module):
@@ -72,7 +74,7 @@ class DynamicsPredictor(nn.Module):
         self.nf_physics = model_config["nf_physics"]
         self.eps = 1e-6
         self.motion_clamp = 100
-        # arithmetic of the dense layers: "fp32" = exact FFMA tiles, "tc" = tcgen05 split-fp16 tensor-core tiles
+        # arithmetic of the dense layers (_PRECISIONS above)
         self.precision = _PRECISIONS[os.environ.get("AGX_PRECISION", "tc")]
 
         self.num_materials = len(material_config["material_index"])
@@ -108,7 +110,8 @@ class DynamicsPredictor(nn.Module):
             print("particle input dim: {}, relation input dim: {}".format(input_dim, rel_input_dim))
 
     def set_precision(self, name: str) -> "DynamicsPredictor":
-        """'fp32' (exact FFMA tiles) or 'tc' (tcgen05 tensor cores on split-fp16 operands, fp32-accurate)."""
+        """'fp32' (exact FFMA tiles), 'tc3' (tcgen05 tensor cores on split-fp16 operands, fp32-accurate) or 'tc' (default: tc3 with
+        the relation chain's precision budget spent, rollout RMSE ~3.5e-6 against the 1e-4 tolerance)."""
         self.precision = _PRECISIONS[name]
         return self
 
@@ -232,7 +235,8 @@ class GraphedRollout:
         self._keep = (thr2, packed, hist)      # the graph holds raw addresses: everything it reads must outlive __init__
 
     def __call__(self, **tensors):
-        if self.model._packed_key != self._packed_key or self.model.packed_weights() is None:
+        # packed_weights() first: it is what refreshes the key (and the blob) after an in-place parameter change
+        if self.model.packed_weights() is not self._keep[1] or self.model._packed_key != self._packed_key:
             raise RuntimeError("the model's parameters changed since capture: build a new GraphedRollout")
         for k, v in tensors.items():
             if k not in self.static:

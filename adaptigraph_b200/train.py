@@ -64,8 +64,19 @@ class FlatParameters:
             for p, k in zip(self.params, self.sizes):
                 self.flat[off:off + k].copy_(p.reshape(-1))
                 p.data = self.flat[off:off + k].view(p.shape)
-                p.grad = self.grad[off:off + k].view(p.shape)
                 off += k
+        self.attach_grads()
+
+    def attach_grads(self) -> None:
+        """(Re-)points every parameter's .grad at its slice of the flat gradient bucket.  `zero_grad(set_to_none=True)` — the
+        default of torch's optimizers and of nn.Module.zero_grad — detaches them; a backward would then accumulate into fresh
+        tensors the fused Adam never sees.  Called before every step, so that usage is harmless."""
+        off = 0
+        for p, k in zip(self.params, self.sizes):
+            g = p.grad
+            if g is None or g.data_ptr() != self.grad.data_ptr() + 4 * off or g.shape != p.shape:
+                p.grad = self.grad[off:off + k].view(p.shape)
+            off += k
 
     def views(self, flat: torch.Tensor):
         out, off = [], 0
@@ -96,6 +107,7 @@ class Trainer:
 
     # ------------------------------------------------------------------ one optimisation step
     def _step_impl(self, data, edges) -> torch.Tensor:
+        self.bucket.attach_grads()                                          # survives a caller's zero_grad(set_to_none=True)
         self.bucket.grad.zero_()                                            # optimizer.zero_grad()          train.py:85
         self.model._packed = None                                           # parameters change under the kernels' feet
         loss = unroll_loss(self.model, data, self.n_future, edges)          #                                train.py:88-112
@@ -104,6 +116,9 @@ class Trainer:
             dist.all_reduce(self.bucket.grad, op=dist.ReduceOp.SUM, group=self.group)
         ops.adam_step(self.bucket.flat, self.bucket.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
                       self.betas[0], self.betas[1], self.eps, 1.0 / self.world)   # optimizer.step()          train.py:115
+        # the fused Adam writes the flat bucket through raw pointers (no _version bump): the packed blob the kernels read is
+        # stale from here on -- drop it so that the next forward / rollout / evaluation repacks the updated weights
+        self.model._packed = None
         return loss.detach()
 
     def step(self, data: Dict[str, torch.Tensor], edges: Optional[EdgeList] = None) -> torch.Tensor:
@@ -132,6 +147,11 @@ class Trainer:
                 for t, s in zip((self.bucket.flat, self.exp_avg, self.exp_avg_sq, self.step_count), snap):
                     t.copy_(s)                                              # the warm-up steps must not train
             torch.cuda.current_stream().wait_stream(side)
+            # The warm-up filled the static EdgeList's sender-list cache (autograd.sender_lists).  Were it still valid inside the
+            # capture, the sort / scan that builds send_ptr / send_perm would not be recorded and every replay would pair the NEW
+            # relations with the FIRST batch's sender lists (silently wrong dQs, d_state and upstream gradients).  Dropping it
+            # forces the rebuild to be part of the graph, writing the same static buffers on every replay.
+            self._static_edges._sender_cache = None
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):                             # records, does not execute
                 self._static_loss = self._step_impl(self._static, self._static_edges)
@@ -144,6 +164,7 @@ class Trainer:
             raise RuntimeError("cuda_graph=True needs a constant relation capacity (pad to max_nR as the reference's DataLoader does)")
         se.row_ptr.copy_(edges.row_ptr); se.send.copy_(edges.send); se.recv.copy_(edges.recv)
         self._graph.replay()
+        self.model._packed = None                                           # the replayed Adam changed the weights (see _step_impl)
         return self._static_loss.clone()
 
     # ------------------------------------------------------------------ torch.optim.Adam-compatible state (train.py:121)

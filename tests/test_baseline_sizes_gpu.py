@@ -1,0 +1,123 @@
+"""Parity at the sizes BASELINE.json quotes (SURVEY.md §8d "Config instances"), against the CPU oracle:
+
+  cfg2  rope      300 particles x 32 graphs, pstep 4   one forward          vs orc.forward_dense
+  cfg3  granular 1000 particles x  4 graphs, pstep 3   5-step rollout       vs orc.rollout_dense
+  cfg4  cloth    2000 particles x  2 graphs, pstep 3   10-step rollout      vs orc.rollout_dense
+  cfg5  cloth    8192 particles x  1 graph,  pstep 3   graph build + forward vs the C oracle / orc.forward_sparse
+
+The dense one-hot relations of the reference formulation are O(B * E * N), so the oracle legs run at reduced batch (the engine's
+results are batch independent: test_parity_gpu.py::test_full_size_properties_cloth_2k); every oracle result is computed once per
+session and shared by the precisions.  Relation counts must be identical at every step; positions within the stated tolerances.
+"""
+import functools
+
+import numpy as np
+import pytest
+import torch
+
+import agx_helpers as H
+from test_parity_gpu import FWD_TOLS, ROLL_MAXS, ROLL_RMSES, _model  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+TC = ["tc3", "tc"]
+
+
+@pytest.fixture(scope="module")
+def agx():
+    import adaptigraph_b200 as pkg
+    import adaptigraph_b200.ops  # noqa: F401
+    assert torch.cuda.is_available()
+    return pkg
+
+
+@functools.lru_cache(maxsize=None)
+def _oracle_rollout(cfg_id, B, T):
+    from adaptigraph_b200 import synthetic as syn
+    from oracle import dynamics_oracle as orc
+    c = syn.BASELINE_CONFIGS[cfg_id]
+    w = syn.baseline_workload(cfg_id, B)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    preds, edges = orc.rollout_dense(H.golden_weights(), c["pstep"], w.state, w.attrs, w.p_instance, w.action, w.physics_param,
+                                     w.state_mask, w.eef_mask, w.adj_thresh, w.topk, w.connect_tools_all, T)
+    counts = torch.stack([(Rr.sum(-1) > 0).sum(1) for Rr, _ in edges], 0)       # (T, B)
+    return w, preds, counts
+
+
+@pytest.mark.parametrize("precision", ["fp32"] + TC)
+@pytest.mark.parametrize("cfg_id,B", [(3, 4), (4, 2)])
+def test_rollout_matches_oracle_at_baseline_size(agx, cfg_id, B, precision):
+    from adaptigraph_b200 import synthetic as syn
+    c = syn.BASELINE_CONFIGS[cfg_id]
+    w, ref, counts = _oracle_rollout(cfg_id, B, c["T"])
+    m = _model(agx, c["material"], c["pstep"], precision)
+    wd = w.to("cuda")
+    out = m.rollout(wd.state, wd.attrs, wd.action, wd.p_instance, wd.physics_param, wd.state_mask, wd.eef_mask, w.adj_thresh, w.topk,
+                    w.connect_tools_all, c["T"], max_nR=int(counts.max()) + 64)
+    got = out["n_edges"].cpu().long()
+    if precision == "tc":
+        # positions differ from the oracle's by ~1e-6 here, which decides a radius test differently when a pair distance lies that
+        # close to the threshold: a handful of relations per graph-step (of ~11,000) may differ late in a rollout
+        assert int((got - counts).abs().max()) <= 4 and torch.equal(got[:2], counts[:2])
+    else:
+        assert torch.equal(got, counts)                                         # same relation count for every graph at every step
+    err = (out["state_seqs"].cpu() - ref).double()
+    assert float(err.pow(2).mean().sqrt()) <= ROLL_RMSES[precision]
+    assert float(err.abs().max()) <= ROLL_MAXS[precision]
+
+
+@functools.lru_cache(maxsize=None)
+def _oracle_forward_cfg2():
+    from adaptigraph_b200 import synthetic as syn
+    from oracle import dynamics_oracle as orc
+    c = syn.BASELINE_CONFIGS[2]
+    w = syn.baseline_workload(2)
+    Rr, Rs = orc.edges_dense_batch(w.state[:, -1], w.adj_thresh, w.state_mask, w.eef_mask, w.topk, w.connect_tools_all)
+    pos, motion = orc.forward_dense(H.golden_weights(), c["pstep"], w.state, w.attrs, Rr, Rs, w.p_instance, w.action, w.physics_param)
+    return w, Rr, Rs, pos, motion
+
+
+@pytest.mark.parametrize("precision", ["fp32"] + TC)
+def test_forward_matches_oracle_cfg2(agx, precision):
+    """rope 300 x 32, pstep 4 (the forward of BASELINE configs[1]; its backward: test_train_gpu.py)."""
+    w, Rr, Rs, ref_pos, ref_motion = _oracle_forward_cfg2()
+    m = _model(agx, "rope", 4, precision)
+    wd = w.to("cuda")
+    el = agx.build_edges(wd.state[:, -1], w.adj_thresh, wd.state_mask, wd.eef_mask, w.topk, w.connect_tools_all).check()
+    r_ref, s_ref = H.lists_from_onehots(Rr, Rs)
+    assert torch.equal(el.n_edges.cpu().long(), (r_ref >= 0).sum(1))
+    with torch.no_grad():
+        pos, motion = m(**wd.graph_dict(), edges=el)
+        pos_d, motion_d = m(**wd.graph_dict(Rr.cuda(), Rs.cuda()))               # the reference's dense call signature
+    assert (pos.cpu() - ref_pos).abs().max() <= FWD_TOLS[precision]
+    assert (motion.cpu() - ref_motion).abs().max() <= FWD_TOLS[precision]
+    assert torch.equal(pos, pos_d) and torch.equal(motion, motion_d)
+
+
+@functools.lru_cache(maxsize=None)
+def _oracle_8192():
+    from adaptigraph_b200 import synthetic as syn
+    from oracle import build_oracle, dynamics_oracle as orc
+    w = syn.make_workload("cloth", 8192, 1, seed=1239)
+    thr2 = np.float32(w.adj_thresh) * np.float32(w.adj_thresh)
+    recv, send, n_edges = build_oracle.edges(w.state[:, -1].numpy(), w.state_mask.numpy(), w.eef_mask.numpy(), thr2, w.topk, w.connect_tools_all, 0)
+    deg = np.bincount(recv, minlength=w.N)
+    row_ptr = torch.zeros(w.N + 1, dtype=torch.int32)
+    row_ptr[1:] = torch.from_numpy(np.cumsum(deg)).to(torch.int32)
+    pos, motion = orc.forward_sparse(H.golden_weights(), 3, w.state, w.attrs, row_ptr, torch.from_numpy(send), w.p_instance, w.action,
+                                     w.physics_param)
+    return w, recv, send, n_edges, pos, motion
+
+
+@pytest.mark.parametrize("precision", ["fp32"] + TC)
+def test_graph_build_and_forward_at_8192_particles(agx, precision):
+    """The largest graph of BASELINE configs[4]: relation lists identical to the C oracle, forward against the sparse oracle."""
+    w, recv, send, n_edges, ref_pos, ref_motion = _oracle_8192()
+    wd = w.to("cuda")
+    el = agx.build_edges(wd.state[:, -1], w.adj_thresh, wd.state_mask, wd.eef_mask, w.topk, w.connect_tools_all).check()
+    E = int(el.row_ptr[-1])
+    assert E == recv.shape[0] and np.array_equal(el.n_edges.cpu().numpy(), n_edges)
+    assert np.array_equal(el.send[:E].cpu().numpy(), send) and np.array_equal(el.recv[:E].cpu().numpy() % w.N, recv)
+    with torch.no_grad():
+        pos, motion = _model(agx, "cloth", 3, precision)(**wd.graph_dict(), edges=el)
+    assert (pos.cpu() - ref_pos).abs().max() <= FWD_TOLS[precision]
+    assert (motion.cpu() - ref_motion).abs().max() <= FWD_TOLS[precision]

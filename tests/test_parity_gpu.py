@@ -10,8 +10,14 @@ pytestmark = pytest.mark.gpu
 
 CASES = H.load_npz("graph_cases.npz")
 FWD = ["forward_rope100_k1.npz", "forward_cloth64_pad_k3.npz", "forward_granular120_k3.npz", "forward_rope300_k4.npz"]
-FWD_TOL = 1e-5      # max-abs on pred_pos / pred_motion, fp32 FFMA path
-ROLL_RMSE = 1e-4    # north_star: RMSE of predicted positions over a 10-step rollout
+# Stated tolerances (BASELINE.json north_star: "predicted positions within 1e-4 RMSE of the reference over a 10-step
+# rollout").  "fp32" = exact FFMA tiles and "tc3" = tcgen05 with 3 split-fp16 MMAs per product are held to the fp32 figures;
+# "tc" (the default: relation chain at 2 MMAs per product, per-relation term as 16-bit block fixed point) is held to a tenth of the
+# north-star tolerance over a rollout and to 5e-5 max-abs on a single forward (tests/bench/precision_study.py predicts 3.5e-6 RMSE).
+FWD_TOLS = {"fp32": 1e-5, "tc3": 1e-5, "tc": 5e-5}      # max-abs on pred_pos / pred_motion of one forward
+ROLL_RMSES = {"fp32": 1e-5, "tc3": 1e-5, "tc": 1e-5}    # RMSE of predicted positions over a rollout (north star: 1e-4)
+ROLL_MAXS = {"fp32": 1e-4, "tc3": 1e-4, "tc": 2e-4}     # max-abs over a rollout
+FWD_TOL = FWD_TOLS["fp32"]
 
 
 @pytest.fixture(scope="module")
@@ -22,7 +28,7 @@ def agx():
     return pkg
 
 
-PRECISIONS = ["fp32", "tc"]   # exact FFMA tiles / tcgen05 split-fp16 tensor-core tiles: same tolerances
+PRECISIONS = ["fp32", "tc3", "tc"]
 
 
 def _model(agx, material, pstep, precision="fp32"):
@@ -111,8 +117,8 @@ def test_forward_matches_reference(agx, fname, path, precision):
             thr, topk, cta, _ = syn.MATERIALS[str(g["material"])]
             el = agx.build_edges(t("state")[:, -1], thr, t("mask"), t("tool_mask"), topk, cta).check()
             pos, motion = m(t("state"), t("attrs"), None, None, t("p_instance"), action=t("action"), edges=el, **kw)
-    assert np.abs(pos.cpu().numpy() - g["pred_pos"]).max() <= FWD_TOL
-    assert np.abs(motion.cpu().numpy() - g["pred_motion"]).max() <= FWD_TOL
+    assert np.abs(pos.cpu().numpy() - g["pred_pos"]).max() <= FWD_TOLS[precision]
+    assert np.abs(motion.cpu().numpy() - g["pred_motion"]).max() <= FWD_TOLS[precision]
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -132,11 +138,11 @@ def test_rollout_matches_reference(agx, fname, precision):
     n_ref = (g["recv"] >= 0).sum(-1).T                                      # (T, B)
     assert np.array_equal(out["n_edges"].cpu().numpy(), n_ref)              # same relation count at every step
     err = out["state_seqs"].cpu().numpy() - g["preds"]
-    assert np.sqrt((err ** 2).mean()) <= ROLL_RMSE
-    assert np.abs(err).max() <= 1e-4
+    assert np.sqrt((err ** 2).mean()) <= ROLL_RMSES[precision]
+    assert np.abs(err).max() <= ROLL_MAXS[precision]
     # the final history holds the last H predictions for object particles
     n_p = g["preds"].shape[2]
-    assert np.abs(out["state"][:, -1, :n_p].cpu().numpy() - g["preds"][:, -1]).max() <= 1e-4
+    assert np.abs(out["state"][:, -1, :n_p].cpu().numpy() - g["preds"][:, -1]).max() <= ROLL_MAXS[precision]
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -157,8 +163,8 @@ def test_forward_matches_oracle_on_seeded_inputs(agx, material, n_p, B, pstep, p
     assert np.array_equal(r, r_ref.numpy()) and np.array_equal(s, s_ref.numpy())
     with torch.no_grad():
         pos, motion = m(**wd.graph_dict(), edges=el)
-    assert (pos.cpu() - ref_pos).abs().max() <= FWD_TOL
-    assert (motion.cpu() - ref_motion).abs().max() <= FWD_TOL
+    assert (pos.cpu() - ref_pos).abs().max() <= FWD_TOLS[precision]
+    assert (motion.cpu() - ref_motion).abs().max() <= FWD_TOLS[precision]
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -179,7 +185,7 @@ def test_graph_without_relations_and_single_particle_tiles(agx, precision):
     assert int(el.row_ptr[-1]) == 0
     with torch.no_grad():
         pos, _ = m(**wd.graph_dict(), edges=el)
-    assert (pos.cpu() - ref_pos).abs().max() <= FWD_TOL
+    assert (pos.cpu() - ref_pos).abs().max() <= FWD_TOLS[precision]
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -265,16 +271,26 @@ def test_backward_is_deterministic_and_edges_path_matches_dense_path(agx):
     assert float(a[0].abs().max()) > 0 and all(float(x.abs().max()) > 0 for x in a[1])
 
 
-def test_tensor_core_path_agrees_with_fp32_path_at_scale(agx):
-    """Same engine, two arithmetic paths, BASELINE-sized graphs: a forward on 8 cloth-2000 graphs."""
+def test_tensor_core_paths_agree_with_fp32_path_and_oracle_at_scale(agx):
+    """Three arithmetic paths of the engine and the CPU oracle (sparse restatement, proven equal to the dense reference form by
+    tests/test_oracle_golden.py), BASELINE-sized graphs: one forward on 8 cloth-2000 graphs."""
     from adaptigraph_b200 import synthetic as syn
-    w = syn.make_workload("cloth", 2000, 8, seed=99).to("cuda")
-    el = agx.build_edges(w.state[:, -1], w.adj_thresh, w.state_mask, w.eef_mask, w.topk, w.connect_tools_all).check()
+    from oracle import dynamics_oracle as orc
+    w = syn.make_workload("cloth", 2000, 8, seed=99)
+    wd = w.to("cuda")
+    el = agx.build_edges(wd.state[:, -1], w.adj_thresh, wd.state_mask, wd.eef_mask, w.topk, w.connect_tools_all).check()
+    E = int(el.row_ptr[-1])
+    ref_pos, ref_mot = orc.forward_sparse(H.golden_weights(), 3, w.state, w.attrs, el.row_ptr.cpu(), el.send[:E].cpu(), w.p_instance,
+                                          w.action, w.physics_param)
     with torch.no_grad():
-        a_pos, a_mot = _model(agx, "cloth", 3, "fp32")(**w.graph_dict(), edges=el)
-        b_pos, b_mot = _model(agx, "cloth", 3, "tc")(**w.graph_dict(), edges=el)
-    assert (a_mot - b_mot).abs().max().item() <= FWD_TOL
-    assert (a_pos - b_pos).abs().max().item() <= FWD_TOL
+        a_pos, a_mot = _model(agx, "cloth", 3, "fp32")(**wd.graph_dict(), edges=el)
+        for prec in ("tc3", "tc"):
+            b_pos, b_mot = _model(agx, "cloth", 3, prec)(**wd.graph_dict(), edges=el)
+            assert (a_mot - b_mot).abs().max().item() <= FWD_TOLS[prec]
+            assert (a_pos - b_pos).abs().max().item() <= FWD_TOLS[prec]
+            assert (b_pos.cpu() - ref_pos).abs().max().item() <= FWD_TOLS[prec]
+            assert (b_mot.cpu() - ref_mot).abs().max().item() <= FWD_TOLS[prec]
+    assert (a_pos.cpu() - ref_pos).abs().max().item() <= FWD_TOL
 
 
 @pytest.mark.parametrize("material,n_p,B", [("cloth", 2000, 4), ("granular", 1000, 4), ("rope", 300, 8), ("granular", 4099, 1)])
@@ -386,11 +402,12 @@ def test_graph_build_cell_grid_stress_matches_c_oracle(agx, name, cta, sem):
     assert np.array_equal(r[:E].cpu().numpy() % N, recv)
 
 
-def test_side_by_side_half_batches_are_bit_identical(agx, monkeypatch):
+@pytest.mark.parametrize("precision", ["tc3", "tc"])
+def test_side_by_side_half_batches_are_bit_identical(agx, monkeypatch, precision):
     """AGX_ROLLOUT_SPLIT=1 runs the two halves of the batch on two streams with half-sized persistent grids: same bits."""
     from adaptigraph_b200 import synthetic as syn
     w = syn.make_workload("cloth", 300, 7, seed=31).to("cuda")          # odd batch: halves of 3 and 4 graphs
-    m = _model(agx, "cloth", 3, "tc")
+    m = _model(agx, "cloth", 3, precision)
     run = lambda: m.rollout(w.state, w.attrs, w.action, w.p_instance, w.physics_param, w.state_mask, w.eef_mask, w.adj_thresh, w.topk,  # noqa: E731
                             w.connect_tools_all, 4, max_nR=3000)
     monkeypatch.delenv("AGX_ROLLOUT_SPLIT", raising=False)

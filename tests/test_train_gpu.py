@@ -110,6 +110,57 @@ def test_cuda_graph_replay_equals_eager_steps(agx):
         graphed.step(bad, edges)
 
 
+def test_cuda_graph_replay_follows_changing_relations(agx):
+    """Every batch of a real training run has its own relations: the sender lists the backward reads must be rebuilt inside the
+    captured step (they were once taken from a cache filled by the warm-up, i.e. frozen at the first batch's)."""
+    from adaptigraph_b200 import synthetic as syn
+    from adaptigraph_b200.train import Trainer
+    g, data = _golden_batch()
+    a, b = _model(agx, int(g["pstep"])), _model(agx, int(g["pstep"]))
+    eager, graphed = Trainer(a, n_future=3), Trainer(b, n_future=3, cuda_graph=True)
+    B, H_, N, _ = data["state"].shape
+    n_rel = data["Rr"].shape[1]
+    thr, topk, cta, _ = syn.MATERIALS["rope"]
+    mask = torch.ones(B, N, dtype=torch.bool, device="cuda")
+    tool = torch.zeros(B, N, dtype=torch.bool, device="cuda")
+    tool[:, g["p_instance"].shape[1]:] = True
+    seen = set()
+    for it in range(4):
+        d = dict(data)
+        d["state"] = data["state"] * (1.0 + 0.15 * it)                      # stretches the rope: other neighbours inside the radius
+        el = agx.build_edges(d["state"][:, -1], thr, mask, tool, topk, cta, max_nR=n_rel).check()
+        seen.add(int(el.row_ptr[-1]))
+        la, lb = eager.step(d, el), graphed.step(d, el)
+        assert la.item() == lb.item(), it
+        for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            assert torch.equal(pa, pb), (it, k)
+    assert len(seen) > 1, "the test needs relation sets that differ between steps"
+
+
+def test_weights_seen_by_inference_follow_the_optimizer(agx):
+    """The fused Adam writes the flat bucket through raw pointers: a forward / rollout right after Trainer.step must run on the
+    updated weights (the packed blob is dropped), and zero_grad(set_to_none=True) between steps must not detach the bucket."""
+    from adaptigraph_b200.train import Trainer
+    g, data = _golden_batch()
+    a = _model(agx, int(g["pstep"]))
+    for graph_mode in (False, True):
+        tr = Trainer(a, n_future=3, cuda_graph=graph_mode)
+        edges = agx.edges_from_onehots(data["Rr"], data["Rs"])
+        for _ in range(2):
+            tr.step(data, edges)
+            a.zero_grad()                                                    # set_to_none=True by default
+        fresh = _model(agx, int(g["pstep"]))
+        fresh.load_state_dict({k: v.detach().clone() for k, v in a.state_dict().items()})
+        a.eval(); fresh.eval()
+        with torch.no_grad():
+            kw = {k: v for k, v in data.items() if k not in ("Rr", "Rs")}
+            pos_a, _ = a(**kw, edges=edges)
+            pos_f, _ = fresh(**kw, edges=edges)
+        assert torch.equal(pos_a, pos_f)
+        a.train()
+    assert not torch.equal(a.state_dict()["particle_encoder.model.0.weight"].cpu(), H.golden_weights()["particle_encoder.model.0.weight"])
+
+
 def test_optimizer_state_round_trips_through_torch_adam(agx):
     from adaptigraph_b200.train import Trainer, unroll_loss
     g, data = _golden_batch()
