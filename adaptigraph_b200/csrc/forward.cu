@@ -33,8 +33,10 @@ constexpr float MOTION_CLAMP = 100.f;  // model.py:85
 struct TcFwdBuffers {
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
   int32_t* agg_exp; float* agg_max;
+  float* P0; float* Qr0; float* Qs0; float* rowmaxP0;   // the particle encoder's copies (read-only for the propagation steps)
 };
-int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, cudaStream_t st);
+int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, bool first, cudaStream_t st);
+int tc_nfeat(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st);
 size_t tc_blob_bytes(size_t base_bytes);
 size_t train_blob_bytes();
 int train_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, cudaStream_t st);
@@ -42,7 +44,7 @@ int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_
 int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, cudaStream_t st);
 int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool mixed,
                     cudaStream_t st);
-int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool last,
+int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool first, bool last,
                    float* pred_pos, int64_t pos_stride_b, float* pred_motion, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------ weight packing
@@ -413,6 +415,7 @@ __global__ void __launch_bounds__(256) rollout_advance_kernel(float* __restrict_
 struct FwdWs {
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
   int32_t* agg_exp; float* agg_max;
+  float* P0; float* Qr0; float* Qs0; float* rowmaxP0;   // tensor-core path: the particle encoder's products, kept across rollout steps
 };
 static size_t fwd_ws_carve(void* base, int64_t rows, int64_t E_cap, FwdWs* out) {
   Carver c(base);
@@ -430,6 +433,10 @@ static size_t fwd_ws_carve(void* base, int64_t rows, int64_t E_cap, FwdWs* out) 
   w.rowmaxA = c.take<float>((size_t)rows);
   w.agg_exp = c.take<int32_t>((size_t)rows);
   w.agg_max = c.take<float>((size_t)rows);
+  w.P0 = c.take<float>(rows_pad * FP);
+  w.Qr0 = c.take<float>(rows_pad * FP);
+  w.Qs0 = c.take<float>(rows_pad * FP);
+  w.rowmaxP0 = c.take<float>((size_t)rows);
   if (out) *out = w;
   return align_up(c.off, 256);
 }
@@ -454,9 +461,11 @@ static int ensure_smem_attrs() {
   return AGX_OK;
 }
 
+// reuse_node_products: the workspace still holds the particle encoder's products of an earlier call on the same attrs / physics /
+// action (a later step of a rollout): only the history records are refreshed (tensor-core path; the fp32 path recomputes)
 static int forward_impl(const AgxModelDims* dims, const float* wts, const AgxGraphIn* g, float* pred_pos,
                         int64_t pos_stride_b, float* pred_motion, int precision, void* workspace, size_t workspace_bytes,
-                        cudaStream_t st, cudaEvent_t after_encoders = nullptr) {
+                        cudaStream_t st, cudaEvent_t after_encoders = nullptr, bool reuse_node_products = false) {
   AGX_REQUIRE(precision == AGX_PREC_FP32 || precision == AGX_PREC_TC_F16X3 || precision == AGX_PREC_TC_MIXED, AGX_ERR_ARG,
               "unknown precision %d", precision);
   const int64_t rows = (int64_t)g->B * g->N;
@@ -469,14 +478,19 @@ static int forward_impl(const AgxModelDims* dims, const float* wts, const AgxGra
     // same stages, dense layers on the tcgen05 tensor cores (tc_forward.cu); MIXED: relation chain at 2 MMAs per K step, C as C16
     const bool mixed = precision == AGX_PREC_TC_MIXED;
     const size_t base = L.total * sizeof(float);
-    const TcFwdBuffers tb{ws.nfeat, ws.P, ws.A, ws.Qr, ws.Qs, ws.agg, ws.C, ws.rowmaxP, ws.rowmaxA, ws.agg_exp, ws.agg_max};
-    if (int rc = tc_node_encoder(g, wts, L, base, tb, st)) return rc;
+    const TcFwdBuffers tb{ws.nfeat, ws.P, ws.A, ws.Qr, ws.Qs, ws.agg, ws.C, ws.rowmaxP, ws.rowmaxA, ws.agg_exp, ws.agg_max,
+                          ws.P0, ws.Qr0, ws.Qs0, ws.rowmaxP0};
+    if (reuse_node_products) {
+      if (int rc = tc_nfeat(g, tb, st)) return rc;
+    } else {
+      if (int rc = tc_node_encoder(g, wts, L, base, tb, st)) return rc;
+    }
     if (g->E_cap > 0)
       if (int rc = tc_edge_encoder(g, wts, L, base, tb, mixed, st)) return rc;
     if (after_encoders) AGX_CUDA_OK(cudaEventRecord(after_encoders, st));   // the tensor-bound phase of this step is enqueued
     for (int k = 0; k < dims->pstep; ++k) {
-      if (int rc = tc_edge_aggregate(g, tb, mixed, st)) return rc;
-      if (int rc = tc_node_update(g, wts, L, base, tb, k + 1 == dims->pstep, pred_pos, pos_stride_b, pred_motion, st)) return rc;
+      if (int rc = tc_edge_aggregate(g, tb, mixed, k == 0, st)) return rc;
+      if (int rc = tc_node_update(g, wts, L, base, tb, k == 0, k + 1 == dims->pstep, pred_pos, pos_stride_b, pred_motion, st)) return rc;
     }
     return AGX_OK;
   }
@@ -700,7 +714,7 @@ int agx_rollout(const AgxModelDims* dims, const void* packed_weights, const AgxR
     const int64_t stride = (int64_t)T * r->n_p * 3;
     float* pred_t = pred_seq + (size_t)b0 * stride + (size_t)t * r->n_p * 3;
     rc = forward_impl(dims, static_cast<const float*>(packed_weights), &g, pred_t, stride, w.motion, precision, w.fwd_ws, w.fwd_ws_bytes, s,
-                      after_encoders);
+                      after_encoders, /*reuse_node_products=*/t > 0);   // attrs, physics and action are fixed for the whole rollout
     if (rc) return rc;
     { ProfScope ps(AGX_KIND_ROLLOUT_ADVANCE, s);
       rollout_advance_kernel<<<Bh, 256, 0, s>>>(state, action, mask, pred_t, stride, r->N, r->n_p, r->y_mode, r->gripper_raise); }

@@ -174,9 +174,10 @@ __device__ __forceinline__ void blk_add16(const float* base, int64_t row, int co
     for (int i = 0; i < 8; ++i) v[8 + i] += t[i];
   }
 }
-// Qr / Qs (the per-particle products every relation gathers) are kept ROW-major with the padded stride FP: a sender's row is five
-// whole 128-byte lines for the aggregate's gather (the blocked layout would hand it ten half-used lines per relation, and the L1
-// data pipe, one line per cycle, is what bounds that kernel); the writers' stores are a fiftieth of the traffic.
+// Row-major variant of blk_store16 (stride FP).  Measured for Qr / Qs on cloth-2k x 128 (r02b): the aggregate's gather gets five
+// whole lines per sender instead of ten half-used ones (-0.014 ms per launch), but the chains' thread-per-row stores then touch 32
+// lines per instruction instead of 16 and node_encoder / node_update lose 0.033 ms each: a net loss, so every intermediate stays
+// blocked.
 __device__ __forceinline__ void row_store16(float* base, int64_t row, int col0, const float (&v)[HW]) {
   float* p = base + row * FP + col0;
   const float a[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
@@ -434,12 +435,24 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
       float am = epi_store_rows(sh, cx, meta[3], a.A, r, valid);   // A_n = W_enc*penc + b
       am = epi_exchange<true>(sh, cx, am);
       if (valid && cx.half == 0) a.rowmaxA[r] = am;
-      epi_store_rows<true>(sh, cx, meta[4], a.Qr, r, valid);
-      epi_store_rows<true>(sh, cx, meta[5], a.Qs, r, valid);
+      epi_store_rows<false>(sh, cx, meta[4], a.Qr, r, valid);
+      epi_store_rows<false>(sh, cx, meta[5], a.Qs, r, valid);
       tile = slot_tile(k + 1, cx.slot, n_tiles);
     }
   }
   chain_teardown(tmem_base);
+}
+
+// The particle encoder's inputs are attrs, the physics parameter and the action (model.py:168-195; state_dim is 0): none of them
+// changes between the steps of a rollout (forward_dynamics.py:156-197 keeps `action` fixed within a push), so its products --
+// particle_encode = P, A_n, Qr, Qs of propagation step 0 -- are computed by the first model step only (agx_rollout) and every later
+// step refreshes just the history record the relation inputs are gathered from.
+__global__ void __launch_bounds__(256) nfeat_kernel(const NodeArgs a) {
+  const int64_t rows = (int64_t)a.B * a.N;
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= rows) return;
+  float in[HW];
+  node_inputs(a, r, rows, 0, in);
 }
 
 // ------------------------------------------------------------------------------------ node update / head
@@ -447,8 +460,8 @@ struct UpdArgs {
   int B, N, n_p;
   const uint32_t* agg_split;   // blocked; per (row, 16-column piece) 8 packed-fp16 hi words then 8 lo words (edge_aggregate, split output)
   const int32_t* agg_exp; const float* agg_max;   // per-row scale exponent / row maximum of agg
-  const float* A; float* P; float* Qr; float* Qs; float* rowmaxP; const float* rowmaxA;
-  const uint8_t* blob; TcLayout L;
+  const float* A; const float* P_in; float* P; float* Qr; float* Qs; const float* rowmaxP_in; float* rowmaxP; const float* rowmaxA;
+  const uint8_t* blob; TcLayout L;   // P_in / rowmaxP_in: the residual stream this step reads (the encoder's copy at pstep 0, else P / rowmaxP)
   const float* head_w;   // fp32 [3][FP] then 4 bias floats (head only)
   const float* state; float* pred_pos; int64_t pos_stride_b; float* pred_motion;
 };
@@ -487,7 +500,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
       if (cx.warp % SLOT_WARPS == 0 && cx.lane == 0) {
         // the residual rows of this tile are read by the first layer's epilogue: start them towards L2 now
         bulk_prefetch_l2(a.A + (int64_t)tile * BLK_TILE, BLK_TILE * 4);   // (buffers are padded to whole tiles)
-        bulk_prefetch_l2(a.P + (int64_t)tile * BLK_TILE, BLK_TILE * 4);
+        bulk_prefetch_l2(a.P_in + (int64_t)tile * BLK_TILE, BLK_TILE * 4);
       }
       // ---- producer: the aggregated relation effects arrive already scaled and split (edge_aggregate): copy to A
       {
@@ -516,7 +529,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
       AGX_STAMP_EPI(cx, 31);
       {  // P <- relu((W_agg*agg + A_n) + P)   (model.py:36-40, :299-301)
         const float4 m = meta[0];
-        const float extra_bound = valid ? a.rowmaxA[r] + a.rowmaxP[r] : 0.f;   // bound on |A_n + P| of this row
+        const float extra_bound = valid ? a.rowmaxA[r] + a.rowmaxP_in[r] : 0.f;   // bound on |A_n + P| of this row
         const float bound_next = fmaxf(cx.bound_in * m.y + extra_bound, 1.f);
         const int e_next = scale_exp(bound_next);
         const float unscale = exp2i(-cx.e_in) * m.x;
@@ -524,7 +537,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
                                   [&](int, int col0, float (&v)[HW]) {
                                     if (valid) {
                                       blk_add16(a.A, r, col0, v);
-                                      blk_add16(a.P, r, col0, v);
+                                      blk_add16(a.P_in, r, col0, v);
                                     }
                                   },
                                   [&](int, int col0, const float (&v)[HW]) {
@@ -538,8 +551,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
       if (next >= 0 && cx.warp % SLOT_WARPS == 0 && cx.lane == 0)   // the next tile's input rows: two layers of lead time
         bulk_prefetch_l2(a.agg_split + (int64_t)next * BLK_TILE, BLK_TILE * 4);
       if (!LAST) {
-        epi_store_rows<true>(sh, cx, meta[1], a.Qr, r, valid);
-        epi_store_rows<true>(sh, cx, meta[2], a.Qs, r, valid);
+        epi_store_rows<false>(sh, cx, meta[1], a.Qr, r, valid);
+        epi_store_rows<false>(sh, cx, meta[2], a.Qs, r, valid);
       } else {
         epi_hidden<a_needs_lo(prog, 2)>(sh, cx, meta[1]);
         // motion head (model.py:306-309): relu(linear_1) then the 3-row linear_2 as running dot products
@@ -730,7 +743,6 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
   const uint32_t jtile = BLK_TILE / 4 - TILE * jrow;
   const uint32_t joff = (uint32_t)(jj >> 2) * (TILE * BLK_W / 4) + (jj & 3);
   auto at = [=](const float4* m, int row) { return __ldg(m + ((uint32_t)row * jrow + ((uint32_t)row >> 7) * jtile + joff)); };
-  auto atq = [=](const float4* m, int row) { return __ldg(m + ((uint32_t)row * (FP / 4) + jj)); };   // Qr / Qs: row-major, stride FP
   auto load_bounds = [&](int v, int& beg, int& end) {   // [beg, end) of this thread's row in group v (empty past the end)
     const int r = v * AGG_NODES + slot;
     beg = end = 0;
@@ -758,14 +770,14 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
     float4 c[AGG_BATCH], q[AGG_BATCH];
     const int n0 = min(end - beg, AGG_BATCH);
     float4 qr = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) qr = atq(Qr, r);
+    if (valid) qr = at(Qr, r);
     if (n0 > 0) {
       const int32_t* my = ids[it & 1][slot];
 #pragma unroll
       for (int u = 0; u < AGG_BATCH; ++u) {
         const int uu = min(u, n0 - 1);                    // past-the-end slots repeat the last relation (masked below)
         c[u] = at(C, beg + uu);
-        q[u] = atq(Qs, gb + my[uu]);
+        q[u] = at(Qs, gb + my[uu]);
       }
     }
     // index data of the groups to come (their latency hides behind this group's feature rows)
@@ -787,7 +799,7 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
       for (int u = 0; u < AGG_BATCH; ++u) {
         const int uu = min(u, n - 1);
         c[u] = at(C, e0 + uu);
-        q[u] = atq(Qs, gb + __ldg(send + e0 + uu));
+        q[u] = at(Qs, gb + __ldg(send + e0 + uu));
       }
 #pragma unroll
       for (int u = 0; u < AGG_BATCH; ++u) {
@@ -827,7 +839,7 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
 
 // ------------------------------------------------------------------------------------ edge aggregate on C16 (AGX_PREC_TC_MIXED)
 // Same reduction with C in the 16-bit block format above.  38 threads per receiver (4 columns each: 8 bytes of C16, one float4 of
-// the row-major fp32 Qr / Qs rows), 8 receivers per group, persistent CTAs as above.  C never goes through registers or L1 on its
+// the blocked fp32 Qr / Qs rows), 8 receivers per group, persistent CTAs as above.  C never goes through registers or L1 on its
 // way in: the first A16_BATCH relations of a receiver are one contiguous run of C16 rows, which thread 0 of the receiver's slot
 // brings into shared memory with ONE bulk copy of the TMA engine (cp.async.bulk + mbarrier transaction count), a whole group ahead
 // of its use -- next to the sender ids (cp.async) and the row_ptr pairs (two groups ahead).  What a thread waits for per group is
@@ -891,7 +903,11 @@ __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_
   const uint32_t c_at = smem_u32(cbuf) + (uint32_t)slot * (A16_BATCH * C16_ROW) + 8u * j;
   const uint32_t e_at = smem_u32(cbuf) + (uint32_t)slot * (A16_BATCH * C16_ROW) + C16_EXP_OFF + 8 * (p & 1) + (p >> 1);
   const uint32_t id_at = smem_u32(&ids[0][slot][0]);
-  const float4* qs_j = Qs + j;
+  // float4 index of the thread's columns in the blocked fp32 rows (tc_chain.cuh: blk_off): row * jrow + (row / 128) * jtile + joff
+  const uint32_t jrow = narrow ? (BLK_COLS - BLK_LAST) / 4 : BLK_W / 4;
+  const uint32_t jtile = BLK_TILE / 4 - TILE * jrow;
+  const uint32_t joff = (uint32_t)p * (TILE * BLK_W / 4) + (j & 3);
+  auto at = [=](const float4* m, uint32_t row) { return __ldg(m + (row * jrow + (row >> 7) * jtile + joff)); };
   auto load_bounds = [&](int v, int& beg, int& end) {
     const int r = v * A16_NODES + slot;
     beg = end = 0;
@@ -941,12 +957,11 @@ __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_
     float4 q[A16_BATCH];
     const int n0 = min(end - beg, A16_BATCH);
     float4 qr = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) qr = __ldg(Qr + (uint32_t)r * (FP / 4) + j);
+    if (valid) qr = at(Qr, (uint32_t)r);
     {
-      const float4* qrow = qs_j + (uint32_t)gb * (FP / 4);
       const uint32_t ida = id_at + buf * (uint32_t)sizeof(ids[0]);
 #pragma unroll
-      for (int u = 0; u < A16_BATCH; ++u) q[u] = __ldg(qrow + (uint32_t)lds_s32(ida + 4 * u) * (FP / 4));   // slots past the degree: a stale (valid) id
+      for (int u = 0; u < A16_BATCH; ++u) q[u] = at(Qs, (uint32_t)(gb + lds_s32(ida + 4 * u)));   // slots past the degree: a stale (valid) id
     }
     // index data and C rows of the groups to come
     int beg2, end2;
@@ -964,7 +979,7 @@ __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_
       const uint8_t* crow = C16 + (size_t)e0 * C16_ROW;
       const uint2 w = __ldg(reinterpret_cast<const uint2*>(crow + 8 * j));
       const int e = (int)(int8_t)__ldg(crow + C16_EXP_OFF + 8 * (p & 1) + (p >> 1));
-      accumulate(w, e, qr, __ldg(qs_j + (uint32_t)(gb + __ldg(send + e0)) * (FP / 4)), 1.f, acc);
+      accumulate(w, e, qr, at(Qs, (uint32_t)(gb + __ldg(send + e0))), 1.f, acc);
     }
     // row maximum (agg >= 0, so the int view of the floats orders like the floats): one warp-level reduction per receiver segment
     // of the warp, then one shared-memory atomic per segment instead of one per thread
@@ -1052,6 +1067,7 @@ int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_
 struct TcFwdBuffers {
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
   int32_t* agg_exp; float* agg_max;
+  float* P0; float* Qr0; float* Qs0; float* rowmaxP0;   // the particle encoder's copies (read-only for the propagation steps)
 };
 
 static int tc_ensure_attrs() {
@@ -1081,9 +1097,21 @@ int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
   const int tiles = (int)((rows + TILE - 1) / TILE);
   NodeArgs a{g->state, g->attrs, g->action, g->p_instance, g->physics, g->B, g->N, g->n_p,
              reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
-             w.nfeat, w.P, w.A, w.Qr, w.Qs, w.rowmaxP, w.rowmaxA};
+             w.nfeat, w.P0, w.A, w.Qr0, w.Qs0, w.rowmaxP0, w.rowmaxA};
   { ProfScope ps(AGX_KIND_NODE_ENCODER, st);
     tc_node_encoder_kernel<<<tiles < num_sms() ? tiles : num_sms(), THREADS, SMEM_BYTES, st>>>(a); }
+  AGX_LAUNCH_CHECK();
+  return AGX_OK;
+}
+
+// history records only (later steps of a rollout: the encoder's products are reused)
+int tc_nfeat(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st) {
+  using namespace tc;
+  const int64_t rows = (int64_t)g->B * g->N;
+  NodeArgs a{g->state, g->attrs, g->action, g->p_instance, g->physics, g->B, g->N, g->n_p, nullptr, TcLayout{},
+             w.nfeat, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  { ProfScope ps(AGX_KIND_NODE_ENCODER, st);
+    nfeat_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(a); }
   AGX_LAUNCH_CHECK();
   return AGX_OK;
 }
@@ -1121,19 +1149,21 @@ int tc_lin(cudaStream_t st, const void* packed, size_t base_bytes, int layer, co
   return AGX_OK;
 }
 
-int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, cudaStream_t st) {
+int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, bool first, cudaStream_t st) {
   using namespace tc;
   const int64_t rows = (int64_t)g->B * g->N;
+  const float* Qr = first ? w.Qr0 : w.Qr;   // propagation step 0 gathers the encoder's products
+  const float* Qs = first ? w.Qs0 : w.Qs;
   if (mixed) {
     if (int rc = tc_ensure_attrs()) return rc;
     // the kernel indexes the blocked fp32 rows with 32-bit float offsets
-    AGX_REQUIRE(blk_rows(rows) * (FP / 4) < (1ll << 32) && g->E_cap < (1ll << 31), AGX_ERR_ARG,
+    AGX_REQUIRE(blk_rows(rows) * (BLK_COLS / 4) < (1ll << 32) && g->E_cap < (1ll << 31), AGX_ERR_ARG,
                 "edge_aggregate: %lld rows / %lld relations exceed the 32-bit feature index", (long long)rows, (long long)g->E_cap);
     const int64_t groups = (rows + A16_NODES - 1) / A16_NODES, resident = (int64_t)num_sms() * AGX_A16_CTAS;
     { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
       edge_aggregate_c16_kernel<<<(unsigned)(groups < resident ? groups : resident), A16_THREADS, A16_SMEM, st>>>(
-          g->row_ptr, g->send, (int)rows, g->N, (int)g->E_cap, reinterpret_cast<const uint8_t*>(w.C), reinterpret_cast<const float4*>(w.Qr),
-          reinterpret_cast<const float4*>(w.Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max); }
+          g->row_ptr, g->send, (int)rows, g->N, (int)g->E_cap, reinterpret_cast<const uint8_t*>(w.C), reinterpret_cast<const float4*>(Qr),
+          reinterpret_cast<const float4*>(Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max); }
     AGX_LAUNCH_CHECK();
     return AGX_OK;
   }
@@ -1143,20 +1173,21 @@ int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, cu
   const int64_t groups = (rows + AGG_NODES - 1) / AGG_NODES, resident = (int64_t)num_sms() * AGG_CTAS_PER_SM;
   { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
     edge_aggregate_split_kernel<<<(unsigned)(groups < resident ? groups : resident), AGG_THREADS, 0, st>>>(
-        g->row_ptr, g->send, (int)rows, g->N, (int)g->E_cap, reinterpret_cast<const float4*>(w.C), reinterpret_cast<const float4*>(w.Qr),
-        reinterpret_cast<const float4*>(w.Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max); }
+        g->row_ptr, g->send, (int)rows, g->N, (int)g->E_cap, reinterpret_cast<const float4*>(w.C), reinterpret_cast<const float4*>(Qr),
+        reinterpret_cast<const float4*>(Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max); }
   AGX_LAUNCH_CHECK();
   return AGX_OK;
 }
 
-int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool last,
-                   float* pred_pos, int64_t pos_stride_b, float* pred_motion, cudaStream_t st) {
+int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool first,
+                   bool last, float* pred_pos, int64_t pos_stride_b, float* pred_motion, cudaStream_t st) {
   using namespace tc;
   if (int rc = tc_ensure_attrs()) return rc;
   const int64_t rows = (int64_t)g->B * g->N;
   const int tiles = (int)((rows + TILE - 1) / TILE);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  UpdArgs a{g->B, g->N, g->n_p, reinterpret_cast<const uint32_t*>(w.agg), w.agg_exp, w.agg_max, w.A, w.P, w.Qr, w.Qs, w.rowmaxP, w.rowmaxA,
+  UpdArgs a{g->B, g->N, g->n_p, reinterpret_cast<const uint32_t*>(w.agg), w.agg_exp, w.agg_max, w.A, first ? w.P0 : w.P, w.P, w.Qr, w.Qs,
+            first ? w.rowmaxP0 : w.rowmaxP, w.rowmaxP, w.rowmaxA,
             reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
             wts + PL.pred2_w, g->state, pred_pos, pos_stride_b, pred_motion};
   if (last) {

@@ -243,7 +243,7 @@ class GraphedRollout:
                 raise KeyError(f"{k} is not a tensor argument of the captured rollout ({', '.join(self._TENSORS)})")
             if v.shape != self.static[k].shape:
                 raise RuntimeError(f"GraphedRollout was captured for {k} of shape {tuple(self.static[k].shape)}, got {tuple(v.shape)}")
-            self.static[k].copy_(v)
+            self.static[k].copy_(v, non_blocking=True)      # pinned host tensors: stream-ordered H2D, no host synchronisation
         self.graph.replay()
         return self.out
 

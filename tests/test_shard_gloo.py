@@ -102,5 +102,6 @@ def test_bench_reference_arm_under_torchrun_prints_one_line():
     lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     j = json.loads(lines[0])
-    assert j["impl"] == "reference" and j["n_gpus"] == 2 and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
+    assert j["impl"] == "reference" and j["n_gpus"] == 2 and j["value"] > 0 and j["cpu_baseline"]["kind"] in ("reference", "port")
+    assert j["cpu_processes"] == 1 and j["scales_with_gpus"] is False
     assert j["e2e"]["h2d_bytes_per_step"] == 0

@@ -1,6 +1,6 @@
 """Summarise an `ncu --page raw --csv` export (run here, no GPU needed):
     ncu -i gpurun_out/X_prof.ncu-rep --page raw --csv > gpurun_out/X_raw.csv
-    python tools/ncu_summary.py gpurun_out/X_raw.csv profiles/X_ncu_summary.txt [profiles/ncu_traffic.json]
+    python tools/ncu_summary.py gpurun_out/X_raw.csv profiles/X_ncu_summary.txt [profiles/ncu_traffic.json [arithmetic]]
 Writes a per-launch table (duration, DRAM bytes, DRAM / tensor / SM utilisation, registers, grid) and, optionally, the per-kernel
 DRAM traffic (bytes per launch, averaged over the captured launches) that bench.py reports as roofline.traffic."""
 import csv
@@ -59,7 +59,8 @@ def main():
             t["dram_read_gb"] /= t["launches"]
             t["dram_write_gb"] /= t["launches"]
             t["traffic_gb_per_launch"] = t["dram_read_gb"] + t["dram_write_gb"]
-        json.dump({"source": raw, "workload": "bench.py default (cloth 2000 x 128 graphs, pstep 3)", "kernels": traffic},
+        json.dump({"source": raw, "workload": "bench.py default (cloth 2000 x 128 graphs, pstep 3)",
+                   "arithmetic": sys.argv[4] if len(sys.argv) > 4 else "tc", "kernels": traffic},
                   open(sys.argv[3], "w"), indent=1)
 
 
