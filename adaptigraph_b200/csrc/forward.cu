@@ -360,9 +360,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 2) node_update_kernel(const NodeU
 // ------------------------------------------------------------------------------------ rollout advance
 // forward_dynamics.py:163-176: tools move by their action delta and take y from the predicted
 // object heights; the history drops its oldest frame and appends [pred ; tools].
+// With nfeat != nullptr the kernel also writes the NEXT step's history records (model.py:155-165 on the advanced history; the
+// tensor-core path's relation encoder gathers them), so that a later rollout step needs no particle-side kernel before its
+// relation encoder: the particle encoder's products are reused (agx_rollout).
 __global__ void __launch_bounds__(256) rollout_advance_kernel(float* __restrict__ state, const float* __restrict__ action,
                                                                const uint8_t* __restrict__ mask, const float* __restrict__ pred,
-                                                               int64_t pred_stride_b, int N, int n_p, int y_mode, float raise) {
+                                                               int64_t pred_stride_b, int N, int n_p, int y_mode, float raise,
+                                                               float* __restrict__ nfeat, const float* __restrict__ attrs,
+                                                               const float* __restrict__ p_instance) {
   __shared__ float red_a[8], red_b[8];
   __shared__ float y_s;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -408,6 +413,14 @@ __global__ void __launch_bounds__(256) rollout_advance_kernel(float* __restrict_
     }
     float* p = state + (((size_t)b * H_FIX + (H_FIX - 1)) * N + n) * 3;
     p[0] = nx; p[1] = ny; p[2] = nz;
+    if (nfeat) {   // the shifted history is s[1], s[2], s[3], (nx, ny, nz): same record as tc_forward.cu's node_inputs
+      const size_t r = (size_t)b * N + n;
+      float4* nf = reinterpret_cast<float4*>(nfeat + r * NFEAT);
+      nf[0] = make_float4(s[2][0] - s[1][0], s[2][1] - s[1][1], s[2][2] - s[1][2], s[3][0] - s[2][0]);
+      nf[1] = make_float4(s[3][1] - s[2][1], s[3][2] - s[2][2], nx - s[3][0], ny - s[3][1]);
+      nf[2] = make_float4(nz - s[3][2], nx, ny, nz);
+      nf[3] = make_float4(attrs[r * 2 + 0], attrs[r * 2 + 1], n < n_p ? p_instance[(size_t)b * n_p + n] : 0.f, 0.f);
+    }
   }
 }
 
@@ -465,7 +478,8 @@ static int ensure_smem_attrs() {
 // action (a later step of a rollout): only the history records are refreshed (tensor-core path; the fp32 path recomputes)
 static int forward_impl(const AgxModelDims* dims, const float* wts, const AgxGraphIn* g, float* pred_pos,
                         int64_t pos_stride_b, float* pred_motion, int precision, void* workspace, size_t workspace_bytes,
-                        cudaStream_t st, cudaEvent_t after_encoders = nullptr, bool reuse_node_products = false) {
+                        cudaStream_t st, cudaEvent_t after_encoders = nullptr, bool reuse_node_products = false,
+                        bool nfeat_ready = false) {
   AGX_REQUIRE(precision == AGX_PREC_FP32 || precision == AGX_PREC_TC_F16X3 || precision == AGX_PREC_TC_MIXED, AGX_ERR_ARG,
               "unknown precision %d", precision);
   const int64_t rows = (int64_t)g->B * g->N;
@@ -481,7 +495,8 @@ static int forward_impl(const AgxModelDims* dims, const float* wts, const AgxGra
     const TcFwdBuffers tb{ws.nfeat, ws.P, ws.A, ws.Qr, ws.Qs, ws.agg, ws.C, ws.rowmaxP, ws.rowmaxA, ws.agg_exp, ws.agg_max,
                           ws.P0, ws.Qr0, ws.Qs0, ws.rowmaxP0};
     if (reuse_node_products) {
-      if (int rc = tc_nfeat(g, tb, st)) return rc;
+      if (!nfeat_ready)                          // (agx_rollout's advance kernel has normally written the records already)
+        if (int rc = tc_nfeat(g, tb, st)) return rc;
     } else {
       if (int rc = tc_node_encoder(g, wts, L, base, tb, st)) return rc;
     }
@@ -714,10 +729,17 @@ int agx_rollout(const AgxModelDims* dims, const void* packed_weights, const AgxR
     const int64_t stride = (int64_t)T * r->n_p * 3;
     float* pred_t = pred_seq + (size_t)b0 * stride + (size_t)t * r->n_p * 3;
     rc = forward_impl(dims, static_cast<const float*>(packed_weights), &g, pred_t, stride, w.motion, precision, w.fwd_ws, w.fwd_ws_bytes, s,
-                      after_encoders, /*reuse_node_products=*/t > 0);   // attrs, physics and action are fixed for the whole rollout
+                      after_encoders, /*reuse_node_products=*/t > 0, /*nfeat_ready=*/t > 0);   // attrs, physics, action: fixed for the rollout
     if (rc) return rc;
+    float* nfeat_next = nullptr;                 // tensor-core path: the advance also prepares the next step's history records
+    if (precision != AGX_PREC_FP32 && t + 1 < T) {
+      FwdWs fws;
+      fwd_ws_carve(w.fwd_ws, (int64_t)Bh * r->N, E_cap_h, &fws);
+      nfeat_next = fws.nfeat;
+    }
     { ProfScope ps(AGX_KIND_ROLLOUT_ADVANCE, s);
-      rollout_advance_kernel<<<Bh, 256, 0, s>>>(state, action, mask, pred_t, stride, r->N, r->n_p, r->y_mode, r->gripper_raise); }
+      rollout_advance_kernel<<<Bh, 256, 0, s>>>(state, action, mask, pred_t, stride, r->N, r->n_p, r->y_mode, r->gripper_raise, nfeat_next,
+                                                g.attrs, g.p_instance); }
     AGX_LAUNCH_CHECK();
     return AGX_OK;
   };

@@ -876,7 +876,7 @@ __device__ __forceinline__ int lds_s32(uint32_t addr) {
 }
 
 __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_kernel(
-    const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send, int rows, int N, int E_cap,
+    const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send, int rows, int N, uint32_t N_magic, int E_cap,
     const uint8_t* __restrict__ C16, const float4* __restrict__ Qr, const float4* __restrict__ Qs, uint32_t* __restrict__ agg_split,
     int32_t* __restrict__ agg_exp, float* __restrict__ agg_max) {
   extern __shared__ uint8_t a16_raw[];
@@ -908,21 +908,23 @@ __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_
   const uint32_t jtile = BLK_TILE / 4 - TILE * jrow;
   const uint32_t joff = (uint32_t)p * (TILE * BLK_W / 4) + (j & 3);
   auto at = [=](const float4* m, uint32_t row) { return __ldg(m + (row * jrow + (row >> 7) * jtile + joff)); };
+  // row bounds of this thread's receiver in group v, as loaded (clamped to the capacity where they are consumed: the loads are
+  // issued two groups ahead and nothing may wait for them before the end of the iteration)
   auto load_bounds = [&](int v, int& beg, int& end) {
     const int r = v * A16_NODES + slot;
     beg = end = 0;
-    if (v < n_groups && r < rows) { beg = min(__ldg(row_ptr + r), E_cap); end = min(__ldg(row_ptr + r + 1), E_cap); }
+    if (v < n_groups && r < rows) { beg = __ldg(row_ptr + r); end = __ldg(row_ptr + r + 1); }
   };
-  // sender ids by cp.async (threads j < BATCH), the C16 rows of the first BATCH relations by one bulk copy (thread j == 0)
-  auto stage = [&](int buf, int beg, int end) {
-    if (j < A16_BATCH && beg + j < end)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&ids[buf][slot][j])), "l"(send + beg + j) : "memory");
+  // relations [b0, e0) of this slot (at most BATCH): sender ids by cp.async (threads j < BATCH), their C16 rows by ONE bulk copy
+  auto stage = [&](int buf, int b0, int e0) {
+    if (j < A16_BATCH && b0 + j < e0)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&ids[buf][slot][j])), "l"(send + b0 + j) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (j == 0) {
-      const int n = min(end - beg, A16_BATCH);
+      const int n = min(e0 - b0, A16_BATCH);
       if (n > 0) {
         mbar_arrive_expect_tx(&bar[buf], (uint32_t)n * C16_ROW);
-        bulk_g2s(cbuf + (size_t)buf * A16_CBUF + (size_t)slot * A16_BATCH * C16_ROW, C16 + (size_t)beg * C16_ROW, (uint32_t)n * C16_ROW, &bar[buf]);
+        bulk_g2s(cbuf + (size_t)buf * A16_CBUF + (size_t)slot * A16_BATCH * C16_ROW, C16 + (size_t)b0 * C16_ROW, (uint32_t)n * C16_ROW, &bar[buf]);
       } else {
         mbar_arrive(&bar[buf]);
       }
@@ -941,33 +943,46 @@ __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_
     acc = make_float4(a0.x, a0.y, a1.x, a1.y);
   };
 
-  int beg, end, beg1, end1;
+  // A task is (receiver group v, batch k): relations [beg + k * BATCH, +BATCH) of every receiver of the group.  Receivers with more
+  // than BATCH relations (granular: up to topk + tools = 25) take further batches through the same pipeline; `more` (CTA-uniform,
+  // from the barrier that ends the previous iteration) says whether the current group has relations left after the current batch.
+  int v = blockIdx.x, k = 0, gcnt = 0;
+  int beg, end, beg1, end1, raw2b = 0, raw2e = 0;
   uint32_t parity = 0;   // bit b: phase to wait for on bar[b]
-  load_bounds(blockIdx.x, beg, end);
-  load_bounds(blockIdx.x + G, beg1, end1);
+  load_bounds(v, beg, end);
+  load_bounds(v + G, beg1, end1);
+  beg = min(beg, E_cap); end = min(end, E_cap); beg1 = min(beg1, E_cap); end1 = min(end1, E_cap);
   stage(0, beg, end);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  for (int it = 0, v = blockIdx.x; v < n_groups; v += G, ++it) {
+  int more = __syncthreads_or(end - beg > A16_BATCH);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 qr = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int it = 0; v < n_groups; ++it) {
     const int buf = it & 1;
     const int r = v * A16_NODES + slot;
     const bool valid = r < rows;
-    const int gb = valid ? (r / N) * N : 0;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 q[A16_BATCH];
-    const int n0 = min(end - beg, A16_BATCH);
-    float4 qr = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) qr = at(Qr, (uint32_t)r);
+    const int n0 = min(end - (beg + k * A16_BATCH), A16_BATCH);          // relations of this batch (<= 0: none)
+    uint32_t gb = 0;
+    if (valid) {   // first particle of the receiver's graph: r - r % N with a multiply-high (one correction step either way)
+      uint32_t qd = __umulhi((uint32_t)r, N_magic);
+      int rem = r - (int)(qd * (uint32_t)N);
+      rem += rem < 0 ? N : 0;
+      rem -= rem >= N ? N : 0;
+      gb = (uint32_t)(r - rem);
+    }
+    if (k == 0 && valid) qr = at(Qr, (uint32_t)r);
     {
       const uint32_t ida = id_at + buf * (uint32_t)sizeof(ids[0]);
 #pragma unroll
-      for (int u = 0; u < A16_BATCH; ++u) q[u] = at(Qs, (uint32_t)(gb + lds_s32(ida + 4 * u)));   // slots past the degree: a stale (valid) id
+      for (int u = 0; u < A16_BATCH; ++u) q[u] = at(Qs, gb + (uint32_t)lds_s32(ida + 4 * u));   // slots past the degree: a stale (valid) id
     }
-    // index data and C rows of the groups to come
-    int beg2, end2;
-    stage(buf ^ 1, beg1, end1);
-    load_bounds(v + 2 * G, beg2, end2);
-    mbar_wait(&bar[buf], (parity >> buf) & 1);     // this group's C16 rows have landed
+    // the next task's index data and C rows; row bounds of the group after the next (consumed at the end of the iteration)
+    const int nk = more ? k + 1 : 0;
+    const int nbeg = more ? beg : beg1, nend = more ? end : end1;
+    stage(buf ^ 1, nbeg + nk * A16_BATCH, nend);
+    if (!more) load_bounds(v + 2 * G, raw2b, raw2e);
+    mbar_wait(&bar[buf], (parity >> buf) & 1);     // this batch's C16 rows have landed
     parity ^= 1u << buf;
     {
       const uint32_t ca = c_at + buf * A16_CBUF, ea = e_at + buf * A16_CBUF;
@@ -975,40 +990,43 @@ __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_
       for (int u = 0; u < A16_BATCH; ++u)
         accumulate(lds64u(ca + u * C16_ROW), lds_s8(ea + u * C16_ROW), qr, q[u], u < n0 ? 1.f : 0.f, acc);
     }
-    for (int e0 = beg + A16_BATCH; e0 < end; ++e0) {   // receivers with more than BATCH relations: the rest straight from global memory
-      const uint8_t* crow = C16 + (size_t)e0 * C16_ROW;
-      const uint2 w = __ldg(reinterpret_cast<const uint2*>(crow + 8 * j));
-      const int e = (int)(int8_t)__ldg(crow + C16_EXP_OFF + 8 * (p & 1) + (p >> 1));
-      accumulate(w, e, qr, at(Qs, (uint32_t)(gb + __ldg(send + e0))), 1.f, acc);
-    }
-    // row maximum (agg >= 0, so the int view of the floats orders like the floats): one warp-level reduction per receiver segment
-    // of the warp, then one shared-memory atomic per segment instead of one per thread
-    int* mxs = smax[it % 3];
-    {
+    int* mxs = smax[gcnt % 3];
+    if (!more) {
+      // row maximum (agg >= 0, so the int view of the floats orders like the floats): one warp-level reduction per receiver
+      // segment of the warp, then one shared-memory atomic per segment instead of one per thread
       const int mine = __float_as_int(fmaxf(fmaxf(acc.x, acc.y), fmaxf(acc.z, acc.w)));
       const unsigned peers = __match_any_sync(0xffffffffu, slot);
       const int seg = __reduce_max_sync(peers, mine);
       if (valid && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicMax(&mxs[slot], seg);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");   // the next group's sender ids have landed ...
-    __syncthreads();                                       // ... and are visible; row maxima complete; everyone is done with cbuf[buf]
-    if (threadIdx.x < A16_NODES) smax[(it + 2) % 3][threadIdx.x] = 0;
-    if (valid) {
-      const float mx = __int_as_float(mxs[slot]);
-      const int e = scale_exp(mx);
-      const float sc = exp2i(e);
-      const float2 s0 = __fmul2_rn(make_float2(acc.x, acc.y), make_float2(sc, sc)), s1f = __fmul2_rn(make_float2(acc.z, acc.w), make_float2(sc, sc));
-      const __half2 h0 = __float22half2_rn(s0), h1 = __float22half2_rn(s1f);
-      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-      const __half2 l0 = __float22half2_rn(make_float2(s0.x - f0.x, s0.y - f0.y)), l1 = __float22half2_rn(make_float2(s1f.x - f1.x, s1f.y - f1.y));
-      // the 16 words of (row, piece = 16 columns): 8 packed hi pairs then 8 packed lo pairs (narrow last piece: 4 then 4)
-      uint32_t* piece = agg_split + blk_off(r, 16 * p);
-      const int lo_at = narrow ? (BLK_COLS - BLK_LAST) / 2 : BLK_W / 2;
-      *reinterpret_cast<uint2*>(piece + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-      *reinterpret_cast<uint2*>(piece + lo_at + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
-      if (j == 0) { agg_exp[r] = e; agg_max[r] = mx; }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // the next task's sender ids have landed ...
+    // ... and are visible; row maxima complete; everyone is done with cbuf[buf]; does the next task's group go on after it?
+    const int more_next = __syncthreads_or(nend - nbeg > (nk + 1) * A16_BATCH);
+    if (!more) {
+      if (threadIdx.x < A16_NODES) smax[(gcnt + 2) % 3][threadIdx.x] = 0;
+      if (valid) {
+        const float mx = __int_as_float(mxs[slot]);
+        const int e = scale_exp(mx);
+        const float sc = exp2i(e);
+        const float2 s0 = __fmul2_rn(make_float2(acc.x, acc.y), make_float2(sc, sc)), s1f = __fmul2_rn(make_float2(acc.z, acc.w), make_float2(sc, sc));
+        const __half2 h0 = __float22half2_rn(s0), h1 = __float22half2_rn(s1f);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __float22half2_rn(make_float2(s0.x - f0.x, s0.y - f0.y)), l1 = __float22half2_rn(make_float2(s1f.x - f1.x, s1f.y - f1.y));
+        // the 16 words of (row, piece = 16 columns): 8 packed hi pairs then 8 packed lo pairs (narrow last piece: 4 then 4)
+        uint32_t* piece = agg_split + blk_off(r, 16 * p);
+        const int lo_at = narrow ? (BLK_COLS - BLK_LAST) / 2 : BLK_W / 2;
+        *reinterpret_cast<uint2*>(piece + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(piece + lo_at + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        if (j == 0) { agg_exp[r] = e; agg_max[r] = mx; }
+      }
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      asm volatile("" : "+r"(raw2b), "+r"(raw2e));         // the row_ptr loads issued above are first waited for HERE
+      beg = beg1; end = end1; beg1 = min(raw2b, E_cap); end1 = min(raw2e, E_cap);
+      v += G;
+      ++gcnt;
     }
-    beg = beg1; end = end1; beg1 = beg2; end1 = end2;
+    k = nk;
+    more = more_next;
   }
 }
 
@@ -1162,7 +1180,8 @@ int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, bo
     const int64_t groups = (rows + A16_NODES - 1) / A16_NODES, resident = (int64_t)num_sms() * AGX_A16_CTAS;
     { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
       edge_aggregate_c16_kernel<<<(unsigned)(groups < resident ? groups : resident), A16_THREADS, A16_SMEM, st>>>(
-          g->row_ptr, g->send, (int)rows, g->N, (int)g->E_cap, reinterpret_cast<const uint8_t*>(w.C), reinterpret_cast<const float4*>(Qr),
+          g->row_ptr, g->send, (int)rows, g->N, (uint32_t)((1ull << 32) / (uint64_t)g->N), (int)g->E_cap, reinterpret_cast<const uint8_t*>(w.C),
+          reinterpret_cast<const float4*>(Qr),
           reinterpret_cast<const float4*>(Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max); }
     AGX_LAUNCH_CHECK();
     return AGX_OK;

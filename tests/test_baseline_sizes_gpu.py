@@ -68,8 +68,7 @@ def test_rollout_matches_oracle_at_baseline_size(agx, cfg_id, B, precision):
     same = (got == counts).all(1)                                               # per step: every graph has the oracle's relation count
     if precision == "tc":
         assert int((got - counts).abs().max()) <= 8 and bool(same[:2].all())
-        t_ok = int(same.long().cumprod(0).sum())                                # steps before the first differing relation set
-        t_ok = min(c["T"], t_ok + 1)                                            # the prediction OF that step was still made on equal relations
+        t_ok = int(same.long().cumprod(0).sum())                                # steps predicted on the oracle's relation sets (counts[t] feeds prediction t)
     else:
         assert bool(same.all())
         t_ok = c["T"]

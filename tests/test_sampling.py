@@ -52,6 +52,46 @@ def test_oracle_sampler_properties():
         assert idx[b, 1] == np.argmax(d[:, 0])                          # second pick = farthest from the first
 
 
+# ------------------------------------------------------------------------------------------- known answers for the DGL sampler
+# dgl.geometry.farthest_point_sampler is a third-party operator absent from /root/reference and from this image, so no run of it
+# can pin the restatement.  These vectors pin its PUBLISHED semantics instead (DGL src/geometry/cpu/geometry_op_impl.cc,
+# FarthestPointSampler): the first pick is start_idx; every later pick scans the points in index order keeping, per point, the
+# minimum SQUARED distance to the picks so far, and takes the point whose kept distance is largest under a strict `>` against a
+# running maximum that starts at 0 with candidate index 0 -- i.e. the LOWEST index among ties, and index 0 once every kept
+# distance is 0.  The expected index lists below were derived by hand from that description on integer lattices (all squared
+# distances are exact small integers in fp32, so no rounding question arises); they were NOT produced by oracle/sampling_oracle.py.
+#
+#   line     x = 0 1 2 3 4 (y = z = 0), start 0, 5 picks
+#            after {0}: d = 0 1 4 9 16 -> 4;  after {0,4}: d = 0 1 4 1 0 -> 2;  after {0,4,2}: d = 0 1 0 1 0 -> tie {1,3} -> 1;  then 3
+#   square   corners (0,0) (2,0) (0,2) (2,2) and centre (1,1) in the xy plane, start 4 (the centre), 5 picks
+#            after {4}: d = 2 2 2 2 0 -> four-way tie -> 0;  after {4,0}: d = 0 2 2 2 0 -> (d to 0 is 4, 4, 8; to the centre 2) tie -> 1;
+#            after {4,0,1}: d = 0 0 2 2 0 -> tie {2,3} -> 2;  then 3
+#   stack    the same point five times, start 3, 4 picks: every kept distance is 0, nothing beats the running maximum 0 -> 0, 0, 0
+#   cube     the 8 corners of the unit cube scaled by 3 in index order zyx (index = 4z + 2y + x), start 5 = (3,0,3), 4 picks
+#            after {5}: squared distances 18 9 27 18 9 0 18 9 -> 2 = (0,3,0);  after {5,2}: d = 9 9 0 9 9 0 9 9 -> tie -> 0;
+#            after {5,2,0}: d = 0 9 0 9 9 0 9 9 -> tie {1,3,4,6,7} -> 1
+#   batch    two clouds of unequal content in one call with per-cloud start indices: `line` with start 2 -> 2, then d = 4 1 0 1 4 ->
+#            tie {0,4} -> 0, then d = 0 1 0 1 4 -> 4, then tie {1,3} -> 1;  and `line` reversed (x = 4 3 2 1 0) with start 0 -> 0 4 2 1
+DGL_KAT = {
+    "line": (np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0], [4, 0, 0]], np.float32), 0, [0, 4, 2, 1, 3]),
+    "square": (np.array([[0, 0, 0], [2, 0, 0], [0, 2, 0], [2, 2, 0], [1, 1, 0]], np.float32), 4, [4, 0, 1, 2, 3]),
+    "stack": (np.tile(np.array([[0.5, -1.25, 2.0]], np.float32), (5, 1)), 3, [3, 0, 0, 0]),
+    "cube": (np.array([[3 * (i & 1), 3 * ((i >> 1) & 1), 3 * (i >> 2)] for i in range(8)], np.float32), 5, [5, 2, 0, 1]),
+}
+DGL_KAT_BATCH = (np.stack([DGL_KAT["line"][0], DGL_KAT["line"][0][::-1].copy()]), [2, 0], [[2, 0, 4, 1], [0, 4, 2, 1]])
+
+
+@pytest.mark.parametrize("name", sorted(DGL_KAT))
+def test_oracle_sampler_matches_dgl_known_answers(name):
+    pos, start, want = DGL_KAT[name]
+    np.testing.assert_array_equal(so.farthest_point_sampler(pos[None], len(want), [start])[0], want)
+
+
+def test_oracle_sampler_matches_dgl_known_answers_batched():
+    pos, starts, want = DGL_KAT_BATCH
+    np.testing.assert_array_equal(so.farthest_point_sampler(pos, 4, starts), want)
+
+
 # ------------------------------------------------------------------------------------------- GPU
 @pytest.fixture(scope="module")
 def sampling():
@@ -174,3 +214,14 @@ def test_wrapper_host_logic_without_a_gpu(monkeypatch):
             np.random.seed(int(FPS[f"{name}/fps{k}/seed"]))
             got = sampling.fps(pcd, int(FPS[f"{name}/fps{k}/max_nobj"]), float(rr[0]) if len(rr) == 1 else list(rr))
             np.testing.assert_array_equal(got, FPS[f"{name}/fps{k}/idx"])
+
+
+@pytest.mark.gpu
+def test_gpu_sampler_matches_dgl_known_answers(sampling):
+    """The CUDA sampler against the hand-derived vectors of the published DGL operator (ties -> lowest index, all-zero -> 0)."""
+    for name, (pos, start, want) in DGL_KAT.items():
+        got = sampling.farthest_point_sampler(torch.from_numpy(pos[None]).cuda(), len(want), start_idx=start)
+        np.testing.assert_array_equal(got.cpu().numpy()[0], want, err_msg=name)
+    pos, starts, want = DGL_KAT_BATCH
+    got = sampling.farthest_point_sampler(torch.from_numpy(pos).cuda(), 4, torch.tensor(starts).cuda())
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
