@@ -17,6 +17,8 @@ AGX_MAX_TOPK = 32
 AGX_SEM_BATCH, AGX_SEM_SINGLE = 0, 1
 AGX_Y_MIN, AGX_Y_MASKED_MEAN = 0, 1
 AGX_PREC_FP32, AGX_PREC_TC_F16X3, AGX_PREC_TC_MIXED = 0, 1, 2
+AGX_ERROR_CHAMFER, AGX_ERROR_BOX = 0, 1
+AGX_PENALTY_ROPE, AGX_PENALTY_CLOTH, AGX_PENALTY_GRANULAR = 0, 1, 2
 AGX_NUM_LAYERS = 11
 AGX_ERR_ARG, AGX_ERR_CAPACITY, AGX_ERR_CUDA = -1, -2, -3
 
@@ -33,6 +35,7 @@ EXPORTS = [
     "agx_version", "agx_last_error", "agx_launch_count",
     "agx_packed_weights_bytes", "agx_pack_weights",
     "agx_graph_workspace_bytes", "agx_graph_build", "agx_onehot_to_ids", "agx_edges_to_onehot", "agx_fps", "agx_chamfer",
+    "agx_running_cost_workspace_bytes", "agx_running_cost",
     "agx_forward_workspace_bytes", "agx_forward",
     "agx_rollout_workspace_bytes", "agx_rollout",
     "agx_profile_enable", "agx_profile_read", "agx_kind_name",
@@ -90,6 +93,8 @@ def _load() -> C.CDLL:
         "agx_edges_to_onehot": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "agx_fps": (C.c_int, [vp, vp, i32, i32, i32, vp, C.c_double, vp, vp, vp]),
         "agx_chamfer": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
+        "agx_running_cost_workspace_bytes": (sz, [i32, i32]),
+        "agx_running_cost": (C.c_int, [vp, vp, i32, vp, vp, i32, vp, i32, i32, C.c_float, i32, i32, i32, vp, sz, vp, vp]),
         "agx_forward_workspace_bytes": (sz, [P(AgxModelDims), i32, i32, i64]),
         "agx_forward": (C.c_int, [P(AgxModelDims), vp, P(AgxGraphIn), vp, i64, vp, i32, vp, sz, vp]),
         "agx_rollout_workspace_bytes": (sz, [P(AgxModelDims), i32, i32, i64, i32]),

@@ -6,14 +6,18 @@
 // B x n_rel x N one-hots; here nothing quadratic ever reaches HBM:
 //
 //   (G0 tool list    with connect_tools_all: ascending list of tool particles per graph, built by sort_cells' CTA)
-//   G0b sort_cells   per graph: lay a uniform grid of cells no narrower than the radius over the two coordinate
-//                    axes of largest extent, counting-sort the particles by cell id (shared-memory histogram +
-//                    block scan), emit the permuted SoA copy of the graph and the first slot of every cell
-//   G1 knn_rows      one thread per receiver: a sender in range lies in the receiver's cell or one of its 8
-//                    neighbours, i.e. in three contiguous slot runs (cells b-1..b+1 of grid rows a-1..a+1), which
-//                    the thread walks in the sorted SoA copy (L1-resident: the threads of a CTA are a few
-//                    neighbouring cells); the k nearest in-radius senders live in a per-thread sorted list in
-//                    shared memory, finally re-sorted by sender id -> <= k candidates
+//   G0b sort_cells   per graph: lay a uniform grid of cells of HALF the radius (GRID_SUBDIV = 2; wider once an axis would need
+//                    more than 64 cells) over the two coordinate axes of largest extent, counting-sort the particles by
+//                    cell id (shared-memory histogram + block scan), emit the permuted SoA copy of the graph and the
+//                    first slot of every cell
+//   G1 knn_rows      one thread per receiver: a sender in range lies within R cells of the receiver's cell along both
+//                    grid axes (R = 2 normally).  The thread walks the square rings m = 0 .. R around its cell -- each a
+//                    few contiguous slot runs of the sorted SoA copy (L1-resident: the threads of a CTA are a few
+//                    neighbouring cells) -- keeping the k nearest in-radius senders in a per-thread sorted list in
+//                    shared memory, and stops after ring m as soon as the list is full and its k-th distance is below
+//                    m cell widths: every sender not yet seen is at least that far away.  With a small top-k inside a
+//                    populous radius (cloth: 5 of ~28) that is a quarter of the candidates of the full window.  The
+//                    list is finally re-sorted by sender id -> <= k candidates
 //   G2 degrees_scan  per-row relation count after the tool rules (:134-144 / :77-80) + block scan; the last block to
 //                    finish scans the block sums -> row offsets, total
 //   G3 fill_rows     one thread per receiver merges candidates and tool senders in ascending sender order
@@ -32,6 +36,7 @@ constexpr int SCAN_BLOCK = 1024;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int GRID_MAX_AXIS = 64;                                  // cells per grid axis (cells widen beyond the radius past that)
 constexpr int GRID_MAX_CELLS = GRID_MAX_AXIS * GRID_MAX_AXIS;
+constexpr int GRID_SUBDIV = 2;                                     // cells per radius (rings searched: up to GRID_SUBDIV)
 
 struct GraphWs {
   int32_t* cand;       // [B*N][topk]
@@ -49,7 +54,7 @@ struct GraphWs {
   int32_t* sidx;       // [B*N] original particle id of each sorted slot
   uint8_t* sflag;      // [B*N] bit0 valid, bit1 tool
   int32_t* cell_start; // [B][GRID_MAX_CELLS + 1] first sorted slot of every cell (entries past the graph's cell count = N)
-  int32_t* grid_dims;  // [B][2] cells along the two grid axes (a = slow, b = fast)
+  int32_t* grid_dims;  // [B][4] cells along the two grid axes (a = slow, b = fast), rings to search, bits of (0.998 * min cell width)^2
 };
 
 static size_t graph_ws_carve(void* base, int B, int N, int topk, GraphWs* ws) {
@@ -72,7 +77,7 @@ static size_t graph_ws_carve(void* base, int B, int N, int topk, GraphWs* ws) {
   w.sidx = c.take<int32_t>(rows);
   w.sflag = c.take<uint8_t>(rows);
   w.cell_start = c.take<int32_t>((size_t)B * (GRID_MAX_CELLS + 1));
-  w.grid_dims = c.take<int32_t>((size_t)B * 2);
+  w.grid_dims = c.take<int32_t>((size_t)B * 4);
   if (ws) *ws = w;
   return align_up(c.off, 256);
 }
@@ -167,15 +172,27 @@ __global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restric
     // every sender with (dis - thr^2) < 0 has |x_i - x_j| <= sqrt(thr^2) up to fp32 rounding: widen by 0.1 % + coordinate ulps
     const float hw = sqrtf(fmaxf(thr2[b], 0.f)) * 1.001f + amax * 1e-6f + 1e-30f;
     const int ax[2] = {a0, a1};
+    // cells of hw / GRID_SUBDIV: two particles within the radius differ by at most `rings` cells along each axis, where
+    // rings * w >= hw (GRID_SUBDIV unless the 64-cell limit widened the cells)
+    int rings = 1;
+    float wmin = __int_as_float(0x7f800000);
     for (int g = 0; g < 2; ++g) {
       const float e = ext[ax[g]];
-      const float w = fmaxf(hw, e * (1.0001f / GRID_MAX_AXIS));
+      const float w = fmaxf(hw * (1.f / GRID_SUBDIV), e * (1.0001f / GRID_MAX_AXIS));
       const float cells = floorf(e / w) + 1.f;                       // <= GRID_MAX_AXIS by construction
       axis_s[g] = ax[g]; lo_s[g] = lo3[ax[g]]; w_s[g] = w;
       n_s[g] = !(cells >= 1.f) ? 1 : (cells > (float)GRID_MAX_AXIS ? GRID_MAX_AXIS : (int)cells);
+      int rg = 1;
+      while (rg < GRID_SUBDIV && (float)rg * w < hw) ++rg;          // smallest count with rg * w >= hw (w >= hw / GRID_SUBDIV)
+      rings = max(rings, rg);
+      wmin = fminf(wmin, w);
     }
-    grid_dims[2 * b] = n_s[0];
-    grid_dims[2 * b + 1] = n_s[1];
+    grid_dims[4 * b] = n_s[0];
+    grid_dims[4 * b + 1] = n_s[1];
+    grid_dims[4 * b + 2] = rings;
+    // a sender outside the rings 0..m is >= m cell widths away along a grid axis; 0.2 % slack covers the fp32 rounding of the
+    // cell coordinate (same kind of slack as hw above) and of the distance itself
+    grid_dims[4 * b + 3] = __float_as_int((wmin * 0.998f) * (wmin * 0.998f));
   }
   __syncthreads();
   const int axa = axis_s[0], axb = axis_s[1], na = n_s[0], nb = n_s[1];
@@ -258,12 +275,13 @@ __global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
   const int b = blockIdx.y, tid = threadIdx.x;
   const size_t gb = (size_t)b * N;
   const float t2 = thr2[b];
-  const int na = grid_dims[2 * b], nb = grid_dims[2 * b + 1];
+  const int na = grid_dims[4 * b], nb = grid_dims[4 * b + 1], rings = grid_dims[4 * b + 2];
+  const float wq = __int_as_float(grid_dims[4 * b + 3]);
   const int32_t* cs = cell_start + (size_t)b * (GRID_MAX_CELLS + 1);
   const int s_beg = blockIdx.x * G1_ROWS_PER_CTA, s_end = min(N, s_beg + G1_ROWS_PER_CTA);
-  // r_lo: a slot at or before everything this CTA's receivers can reach (start of grid row a_first - 1); keeps the offsets small
+  // r_lo: a slot at or before everything this CTA's receivers can reach (start of grid row a_first - rings); keeps the offsets small
   const int a_first = scell[gb + s_beg] / nb;
-  const int r_lo = cs[max(a_first - 1, 0) * nb];
+  const int r_lo = cs[max(a_first - rings, 0) * nb];
   (void)smem_cap;
   float* ld = smem;                                                   // [topk][G1_THREADS]
   int32_t* lj = reinterpret_cast<int32_t*>(ld + topk * G1_THREADS);   // [topk][G1_THREADS]  (sender id << 1) | tool bit
@@ -281,24 +299,22 @@ __global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
   const int li = slot - r_lo;
   const int fi = fl[li];
   const int i = pj[li];
-  int total = 0, cnt = 0;
+  int cnt = 0;
   if (fi & 1) {
     const float xi = px[li], yi = py[li], zi = pz[li];
     const bool tool_i = fi & 2;
     const int ci = scell[gb + slot], ca = ci / nb, cb = ci - ca * nb;
     float kd = __int_as_float(0x7f800000);   // current k-th best (+inf until the list is full)
     int kj = 0x7fffffff;
-    for (int run = 0; run < 3; ++run) {
-      const int a = ca - 1 + run;
-      if (a < 0 || a >= na) continue;
-      const int w_lo = cs[a * nb + max(cb - 1, 0)] - r_lo, w_hi = cs[a * nb + min(cb + 1, nb - 1) + 1] - r_lo;
+    // one contiguous run of sorted slots: cells [b0, b1] of grid row a
+    auto scan_run = [&](int a, int b0, int b1) {
+      const int w_lo = cs[a * nb + b0] - r_lo, w_hi = cs[a * nb + b1 + 1] - r_lo;
       for (int s = w_lo; s < w_hi; ++s) {
         const int fj = fl[s];
         const float dx = __fsub_rn(xi, px[s]), dy = __fsub_rn(yi, py[s]), dz = __fsub_rn(zi, pz[s]);
         const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
         const bool ok = (fj & 1) && !(tool_i && (fj & 2)) && (__fsub_rn(d, t2) < 0.f);
         if (!ok) continue;
-        ++total;                                   // every in-radius sender counts towards min(total, topk)
         const int jc = (pj[s] << 1) | ((fj >> 1) & 1);   // sender id, tool bit in the LSB (order by id is preserved)
         if (!((d < kd) || (d == kd && jc < kj))) continue;
         // sorted insertion (distance, then id); a full list drops its last entry
@@ -316,6 +332,20 @@ __global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
         if (cnt < topk) ++cnt;
         if (cnt == topk) { kd = ld[(topk - 1) * G1_THREADS + tid]; kj = lj[(topk - 1) * G1_THREADS + tid]; }
       }
+    };
+    for (int m = 0; m <= rings; ++m) {
+      // ring m: the grid rows ca - m and ca + m over cells cb - m .. cb + m, and the two end cells of the rows in between
+      for (int a = ca - m; a <= ca + m; ++a) {
+        if (a < 0 || a >= na) continue;
+        if (a == ca - m || a == ca + m) {
+          scan_run(a, max(cb - m, 0), min(cb + m, nb - 1));
+        } else {
+          if (cb - m >= 0) scan_run(a, cb - m, cb - m);
+          if (cb + m < nb) scan_run(a, cb + m, cb + m);
+        }
+      }
+      // every sender outside the rings 0..m is at least m cell widths away: the list is final once its k-th entry is closer
+      if (cnt == topk && kd < (float)(m * m) * wq) break;
     }
   }
   // cnt == min(total, topk); re-sort the kept senders by id (insertion sort on <= topk entries)

@@ -849,10 +849,11 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
 // which is zero-initialised), because on this kernel the instruction issue and the L1 data pipe, not DRAM, are the bound: r02a's
 // ncu capture of the first version (per-relation branches, generic loads, 64-register build with spills) showed 120 issued warp
 // instructions per relation, 39 % DRAM utilisation and the L1 data pipe at 73 %.
-#ifndef AGX_A16_CTAS
-#define AGX_A16_CTAS 2
+#ifndef AGX_A16_NODES
+#define AGX_A16_NODES 4     // receivers per CTA group
+#define AGX_A16_CTAS 4      // resident CTAs per SM
 #endif
-constexpr int A16_NODES = 8;
+constexpr int A16_NODES = AGX_A16_NODES;
 constexpr int A16_LANES = BLK_COLS / 4;                // 38
 constexpr int A16_THREADS = A16_NODES * A16_LANES;     // 304
 constexpr int A16_BATCH = 8;

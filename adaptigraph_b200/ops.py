@@ -182,6 +182,44 @@ def _(x, y):
     return x.new_empty((x.shape[0],))
 
 
+_RC_WS = {}     # (device index, bytes) -> zero-initialised workspace of agx_running_cost (the kernel re-zeroes its counters itself)
+
+
+@torch.library.custom_op("agx::running_cost", mutates_args=())
+def running_cost(state: Tensor, action: Tensor, state_cur: Tensor, bbox: Tensor, target: Tensor, error_mode: int,
+                 penalty_mode: int, sim_real_ratio: float) -> Tensor:
+    """planning/plan.py:27-59 with its error / penalty terms (losses.py) in one launch: state (bsz,L,n,3), action (bsz,L,A>=3),
+    state_cur (n,3), bbox (2,2), target (M,3) points [error_mode 0: chamfer] or (2,2) box [1: box_loss] -> reward_seqs (bsz)."""
+    _need_cuda(state, action, state_cur, bbox, target)
+    state, action, state_cur, bbox, target = _f32(state), _f32(action), _f32(state_cur), _f32(bbox), _f32(target)
+    bsz, Lk, n, D = state.shape
+    if D != 3 or action.shape[:2] != (bsz, Lk) or state_cur.shape != (n, 3) or bbox.shape != (2, 2):
+        raise ValueError(f"running_cost: bad shapes state {tuple(state.shape)} action {tuple(action.shape)} state_cur "
+                         f"{tuple(state_cur.shape)} bbox {tuple(bbox.shape)}")
+    if error_mode == L.AGX_ERROR_CHAMFER:
+        if target.dim() != 2 or target.shape[1] != 3:
+            raise ValueError(f"running_cost: chamfer target must be (M,3), got {tuple(target.shape)}")
+        M = target.shape[0]
+    else:
+        if target.shape != (2, 2):
+            raise ValueError(f"running_cost: box target must be (2,2), got {tuple(target.shape)}")
+        M = 0
+    nws = int(lib.agx_running_cost_workspace_bytes(bsz, Lk))
+    key = (state.device.index, nws)
+    ws = _RC_WS.get(key)
+    if ws is None:
+        ws = _RC_WS[key] = torch.zeros(nws, dtype=torch.uint8, device=state.device)
+    out = torch.empty(bsz, dtype=torch.float32, device=state.device)
+    L.check(lib.agx_running_cost(_ptr(state), _ptr(action), action.shape[2], _ptr(state_cur), _ptr(bbox), error_mode, _ptr(target), M,
+                                 penalty_mode, float(sim_real_ratio), bsz, Lk, n, _ptr(ws), nws, _ptr(out), _stream()), "agx_running_cost")
+    return out
+
+
+@running_cost.register_fake
+def _(state, action, state_cur, bbox, target, error_mode, penalty_mode, sim_real_ratio):
+    return state.new_empty((state.shape[0],))
+
+
 # --------------------------------------------------------------------------- forward / rollout
 @torch.library.custom_op("agx::forward", mutates_args=())
 def forward(packed: Tensor, state: Tensor, attrs: Tensor, action: Tensor, p_instance: Tensor, physics: Tensor,

@@ -157,6 +157,22 @@ AGX_API int agx_fps(const float* pos, const int32_t* n_points, int32_t B, int32_
 AGX_API int agx_chamfer(const float* x, const float* y, int32_t B, int32_t N, int32_t M, int32_t y_batched, float* out,
                 agx_stream_t stream);
 
+/* ---- the planner's reward tail in one launch: running_cost (planning/plan.py:27-59) with its error term (chamfer to target points,
+ * losses.py:4-10, or box_loss to a target box, :25-35; plan.py:146 / :155), its collision penalty (rope / cloth / granular,
+ * losses.py:37-92; plan.py:160-165) and the workspace-box penalty (plan.py:41-51).  state (bsz, L, n, 3) predicted particles per
+ * look-ahead step, action (bsz, L, action_dim >= 3), state_cur (n, 3), bbox (2, 2), target (M, 3) points or (2, 2) box,
+ * reward (bsz) = -2 / (max error + 1e-6) * error[:, -1] - 5 * mean_l penalty - 5 * mean_l box penalty.  n + M <= 17066. */
+#define AGX_ERROR_CHAMFER 0
+#define AGX_ERROR_BOX 1
+#define AGX_PENALTY_ROPE 0
+#define AGX_PENALTY_CLOTH 1
+#define AGX_PENALTY_GRANULAR 2
+AGX_API size_t agx_running_cost_workspace_bytes(int32_t bsz, int32_t L);
+/* workspace: agx_running_cost_workspace_bytes(bsz, L) bytes, ZERO-filled before the first call (the kernel leaves it ready for the next) */
+AGX_API int agx_running_cost(const float* state, const float* action, int32_t action_dim, const float* state_cur, const float* bbox,
+                     int32_t error_mode, const float* target, int32_t M, int32_t penalty_mode, float sim_real_ratio, int32_t bsz,
+                     int32_t L, int32_t n, void* workspace, size_t workspace_bytes, float* reward, agx_stream_t stream);
+
 /* ---- model forward (replaces model.py:129-313) */
 AGX_API size_t agx_forward_workspace_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap);
 /* pred_pos, pred_motion: (B, n_p, 3).  pos_stride_b: floats between consecutive graphs in

@@ -105,7 +105,8 @@ def chamfer(x, y):
 
 def running_cost(state, action, state_cur, error_func, penalty_func, bbox):
     """planning/plan.py:27-59 restated (plan.py itself cannot be imported here: pyflex / GroundingDINO / SAM are absent).
-    PARITY UNPINNED for this function; every term it calls is pinned through tests/golden/rewards.npz."""
+    PINNED: tests/golden/running_cost.npz holds outputs of the reference's own function, whose unmodified source is executed by
+    tests/golden/make_golden_running_cost.py; every term it calls is pinned through tests/golden/rewards.npz."""
     bsz, n_look_forward = state.shape[0], state.shape[1]
     state_flat = state.reshape(bsz * n_look_forward, state.shape[2], state.shape[3])
     error = error_func(state_flat).reshape(bsz, n_look_forward)
@@ -136,3 +137,34 @@ def rope_penalty(state_pred, action, state_init, sim_real_ratio=10.0):
     pusher_size = 0.02 * sim_real_ratio
     action_state_distance = torch.maximum(action_state_distance - pusher_size, torch.zeros_like(action_state_distance))
     return torch.exp(-action_state_distance * 100.)
+
+
+def cloth_penalty(state_pred, action, state_init, sim_real_ratio=10.0):
+    """planning/losses.py:51-65 (CPU torch).  Pinned: tests/golden/rewards.npz holds the reference's output."""
+    action_point_2d = torch.stack([action[:, :, 0], action[:, :, 1]], dim=-1)
+    dist = torch.norm(action_point_2d[:, :, None] - state_init[:, [0, 2]][None, None], dim=-1)
+    dmin = dist.min(dim=-1).values
+    dmin = torch.maximum(dmin - 0.005 * sim_real_ratio, torch.zeros_like(dmin))
+    dmax = torch.minimum(dist.max(dim=-1).values, torch.ones_like(dmin) * 0.4 * sim_real_ratio)
+    dmax = dmax / dmax.max().item()
+    return 1. - torch.exp(-dmin * 100.) - dmax * 0.2
+
+
+def granular_penalty(state_pred, action, state_init, sim_real_ratio=10.0):
+    """planning/losses.py:67-92 (CPU torch).  Pinned: tests/golden/rewards.npz holds the reference's output."""
+    bsz, n_look_forward, _ = action.shape
+    x_start, z_start, theta = action[:, :, 0], action[:, :, 1], action[:, :, 2]
+    pusher_radius = 0.05 * sim_real_ratio
+    delta_x = pusher_radius * torch.sin(theta)
+    delta_z = -pusher_radius * torch.cos(theta)
+    pts = []
+    for f in (1., 0.75, 0.5, 0.25):
+        pts += [x_start - delta_x if f == 1. else x_start - f * delta_x, z_start - delta_z if f == 1. else z_start - f * delta_z]
+    pts += [x_start, z_start]
+    for f in (0.25, 0.5, 0.75, 1.):
+        pts += [x_start + delta_x if f == 1. else x_start + f * delta_x, z_start + delta_z if f == 1. else z_start + f * delta_z]
+    action_point_2d = torch.stack(pts, dim=-1).reshape(bsz, n_look_forward, 9, 2)
+    state_2d = torch.cat([state_init[:, [0, 2]][None, None].repeat(bsz, 1, 1, 1), state_pred[:, :-1, :, [0, 2]]], dim=1)
+    d = torch.norm(action_point_2d[:, :, :, None] - state_2d[:, :, None], dim=-1).min(dim=-1).values.min(dim=-1).values
+    d = torch.maximum(d - 0.02 * sim_real_ratio, torch.zeros_like(d))
+    return torch.exp(-d * 100.)

@@ -10,19 +10,32 @@ import agx_helpers as H
 from oracle import planning_oracle as po
 
 G = H.load_npz("rewards.npz")
+RC = H.load_npz("running_cost.npz")     # the reference's own running_cost (tests/golden/make_golden_running_cost.py)
 CH = sorted({k.split("/")[1] for k in G if k.startswith("chamfer/")})
 TOL = 2e-6
 
 
-def test_oracle_rope_penalty_matches_reference():
+@pytest.mark.parametrize("name", ["rope_penalty", "cloth_penalty", "granular_penalty"])
+def test_oracle_penalties_match_reference(name):
     t = lambda k: torch.from_numpy(G[k])  # noqa: E731
-    np.testing.assert_allclose(po.rope_penalty(t("state"), t("action"), t("state_cur")).numpy(), G["rope_penalty"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(getattr(po, name)(t("state"), t("action"), t("state_cur")).numpy(), G[name], rtol=0, atol=1e-7)
 
 
 @pytest.mark.parametrize("name", CH)
 def test_oracle_chamfer_matches_reference(name):
     out = po.chamfer(torch.from_numpy(G[f"chamfer/{name}/x"]), torch.from_numpy(G[f"chamfer/{name}/y"]))
     np.testing.assert_allclose(out.numpy(), G[f"chamfer/{name}/out"], rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("key", sorted(k for k in RC if k.startswith("reward/")))
+def test_oracle_running_cost_matches_reference(key):
+    """oracle/planning_oracle.py's restatement of plan.py:27-59 against outputs of the reference's own function."""
+    _, ename, pname, ratio = key.split("/")
+    t = lambda k: torch.from_numpy(RC[k])  # noqa: E731
+    crit = partial(po.chamfer, y=t("target_pts")[None]) if ename == "chamfer" else partial(po_box_loss, target=t("target_box"))
+    pen = partial(getattr(po, pname + "_penalty"), sim_real_ratio=float(ratio))
+    got = po.running_cost(t("state"), t("action"), t("state_cur"), crit, pen, RC["bbox"])
+    np.testing.assert_allclose(got.numpy(), RC[key], rtol=1e-6, atol=1e-6)
 
 
 @pytest.fixture(scope="module")
@@ -52,6 +65,36 @@ def test_gpu_chamfer_rejects_bad_input(rw):
         rw.chamfer(torch.zeros(2, 4, 3).cuda(), torch.zeros(3, 4, 3).cuda())         # target batch neither 1 nor B
     with pytest.raises(ValueError):
         rw.chamfer(torch.zeros(1, 9000, 3).cuda(), torch.zeros(1, 9000, 3).cuda())   # beyond the shared-memory staging limit
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", sorted(k for k in RC if k.startswith("reward/")))
+def test_gpu_fused_running_cost_matches_reference(rw, key):
+    """The one-kernel reward tail, called the way plan.py:146-175 binds it, against the reference's own running_cost."""
+    _, ename, pname, ratio = key.split("/")
+    t = lambda k: torch.from_numpy(RC[k]).cuda()  # noqa: E731
+    crit = partial(rw.chamfer, y=t("target_pts")[None]) if ename == "chamfer" else partial(rw.box_loss, target=t("target_box"))
+    pen = partial(getattr(rw, pname + "_penalty"), sim_real_ratio=float(ratio))
+    for _ in range(2):                                                   # the workspace counters must be ready for the next call
+        got = rw.running_cost(t("state"), t("action"), t("state_cur"), error_func=crit, penalty_func=pen, bbox=RC["bbox"])["reward_seqs"]
+        np.testing.assert_allclose(got.cpu().numpy(), RC[key], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.gpu
+def test_gpu_running_cost_accepts_the_references_callables_and_rejects_others(rw):
+    import types
+    t = lambda k: torch.from_numpy(RC[k]).cuda()  # noqa: E731
+    ref_like = types.SimpleNamespace()                                    # functions named like planning.losses' (recognised by name)
+    def chamfer(x, y): raise AssertionError("must not be called")        # noqa: E704
+    def rope_penalty(s, a, c, sim_real_ratio=10.0): raise AssertionError("must not be called")  # noqa: E704
+    got = rw.running_cost(t("state"), t("action"), t("state_cur"), partial(chamfer, y=t("target_pts")[None]), partial(rope_penalty, sim_real_ratio=10.0),
+                          RC["bbox"])["reward_seqs"]
+    np.testing.assert_allclose(got.cpu().numpy(), RC["reward/chamfer/rope/10"], rtol=2e-5, atol=2e-5)
+    with pytest.raises(NotImplementedError):
+        rw.running_cost(t("state"), t("action"), t("state_cur"), lambda s: s.sum((1, 2)), rope_penalty, RC["bbox"])
+    with pytest.raises(RuntimeError):
+        rw.running_cost(t("state").cpu(), t("action").cpu(), t("state_cur").cpu(), partial(chamfer, y=t("target_pts")), rope_penalty, RC["bbox"])
+    del ref_like
 
 
 @pytest.mark.gpu
