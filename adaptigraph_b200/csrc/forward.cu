@@ -393,7 +393,9 @@ __global__ void __launch_bounds__(256) rollout_advance_kernel(float* __restrict_
   }
   __syncthreads();
   const float y_tool = y_s;
-  for (int n = tid; n < N; n += 256) {
+  // grid = (graphs, chunks of 256 particles): every CTA repeats the (cheap) reduction over the graph's predictions above and then
+  // advances its own chunk, so that small batches are not left to one CTA per graph
+  for (int n = blockIdx.y * 256 + tid; n < min(N, (int)(blockIdx.y + 1) * 256); n += 256) {
     float s[H_FIX][3];
 #pragma unroll
     for (int h = 0; h < H_FIX; ++h) {
@@ -738,7 +740,7 @@ int agx_rollout(const AgxModelDims* dims, const void* packed_weights, const AgxR
       nfeat_next = fws.nfeat;
     }
     { ProfScope ps(AGX_KIND_ROLLOUT_ADVANCE, s);
-      rollout_advance_kernel<<<Bh, 256, 0, s>>>(state, action, mask, pred_t, stride, r->N, r->n_p, r->y_mode, r->gripper_raise, nfeat_next,
+      rollout_advance_kernel<<<dim3(Bh, (r->N + 255) / 256), 256, 0, s>>>(state, action, mask, pred_t, stride, r->N, r->n_p, r->y_mode, r->gripper_raise, nfeat_next,
                                                 g.attrs, g.p_instance); }
     AGX_LAUNCH_CHECK();
     return AGX_OK;
