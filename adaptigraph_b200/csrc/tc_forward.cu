@@ -843,12 +843,20 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
 // way in: the first A16_BATCH relations of a receiver are one contiguous run of C16 rows, which thread 0 of the receiver's slot
 // brings into shared memory with ONE bulk copy of the TMA engine (cp.async.bulk + mbarrier transaction count), a whole group ahead
 // of its use -- next to the sender ids (cp.async) and the row_ptr pairs (two groups ahead).  What a thread waits for per group is
-// therefore only the Qs gather it has in flight (A16_BATCH float4).
+// therefore only the Qs gather it has in flight (A16_BATCH float4).  A task is (receiver group, batch of A16_BATCH relations per
+// receiver): receivers of higher degree (granular: up to 25) take further batches through the same pipeline.
 // The inner loop is branch-free: all A16_BATCH staged slots are always evaluated and a 0 / 1 factor in the accumulating FMA drops
 // the ones past the receiver's degree (they read whatever well-formed rows and sender ids an earlier group left in shared memory,
 // which is zero-initialised), because on this kernel the instruction issue and the L1 data pipe, not DRAM, are the bound: r02a's
 // ncu capture of the first version (per-relation branches, generic loads, 64-register build with spills) showed 120 issued warp
 // instructions per relation, 39 % DRAM utilisation and the L1 data pipe at 73 %.
+// Where the time goes now (cloth-2k x 128, 0.249 ms per launch; r02i / r02j, each line one thing removed): no Qs gather 0.190, no
+// arithmetic 0.171, no output 0.226, no bulk copies 0.232, no shared-memory reads of C 0.237 -- no single limiter; issue slots
+// (87 warp instructions per relation, of which 35 are the per-relation loop) and the gather latency share it.  Tried and not
+// adopted (profiles/r02_experiments_not_adopted.patch): issuing the gather of the NEXT task before computing the current one
+// (sender ids staged two tasks ahead; 120 registers, 456 threads per SM): 0.273 ms; CTA shapes 8 receivers x 2 CTAs per SM 0.262,
+// 2 x 8 0.26, 4 x 3 0.26 against 4 x 4 0.250; Qr / Qs rows row-major instead of blocked: -0.014 ms here, +0.033 ms in each of
+// node_encoder / node_update.
 #ifndef AGX_A16_NODES
 #define AGX_A16_NODES 4     // receivers per CTA group
 #define AGX_A16_CTAS 4      // resident CTAs per SM
@@ -1181,7 +1189,8 @@ int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, bo
     const int64_t groups = (rows + A16_NODES - 1) / A16_NODES, resident = (int64_t)num_sms() * AGX_A16_CTAS;
     { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
       edge_aggregate_c16_kernel<<<(unsigned)(groups < resident ? groups : resident), A16_THREADS, A16_SMEM, st>>>(
-          g->row_ptr, g->send, (int)rows, g->N, (uint32_t)((1ull << 32) / (uint64_t)g->N), (int)g->E_cap, reinterpret_cast<const uint8_t*>(w.C),
+          g->row_ptr, g->send, (int)rows, g->N, g->N == 1 ? 0xffffffffu : (uint32_t)((1ull << 32) / (uint64_t)g->N), (int)g->E_cap,
+          reinterpret_cast<const uint8_t*>(w.C),
           reinterpret_cast<const float4*>(Qr),
           reinterpret_cast<const float4*>(Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max); }
     AGX_LAUNCH_CHECK();
