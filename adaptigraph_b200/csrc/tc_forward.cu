@@ -16,6 +16,11 @@ constexpr float MOTION_CLAMP = 100.f;  // model.py:85
 #ifndef AGX_MMA_EDGE
 #define AGX_MMA_EDGE 2      // relation_encoder.model.2 / .4 and the relation part of relation_propagator
 #endif
+// Going below two fp16 MMAs does not pay any more: with the residual term Ahi * Wlo issued as ONE fp8 MMA (kind::f8f6f4, e5m2 copy of
+// A in tensor memory x e4m3 image of Wlo: 1.5 MMA units, same 5e-6 rollout RMSE, all parity tests green) the relation encoder went
+// from 0.466 to 0.460 ms (r02k) -- at two MMAs per product the chain is no longer bound by the MMA count.  Not adopted
+// (profiles/r02_experiment_fp8_residual.patch).  Neither is giving the two column parts of a layer separate accumulator columns
+// (one accumulator hand-over per layer instead of two): 0.477 against 0.479 ms (r02i).
 #ifndef AGX_MMA_NODE
 #define AGX_MMA_NODE 3      // every particle-side layer
 #endif
