@@ -34,6 +34,7 @@ struct TcFwdBuffers {
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
   int32_t* agg_exp; float* agg_max;
   float* P0; float* Qr0; float* Qs0; float* rowmaxP0;   // the particle encoder's copies (read-only for the propagation steps)
+  float* S0;                                            // A_n + P0
 };
 int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, bool first, cudaStream_t st);
 int tc_nfeat(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st);
@@ -431,6 +432,7 @@ struct FwdWs {
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
   int32_t* agg_exp; float* agg_max;
   float* P0; float* Qr0; float* Qs0; float* rowmaxP0;   // tensor-core path: the particle encoder's products, kept across rollout steps
+  float* S0;
 };
 static size_t fwd_ws_carve(void* base, int64_t rows, int64_t E_cap, FwdWs* out) {
   Carver c(base);
@@ -452,6 +454,7 @@ static size_t fwd_ws_carve(void* base, int64_t rows, int64_t E_cap, FwdWs* out) 
   w.Qr0 = c.take<float>(rows_pad * FP);
   w.Qs0 = c.take<float>(rows_pad * FP);
   w.rowmaxP0 = c.take<float>((size_t)rows);
+  w.S0 = c.take<float>(rows_pad * FP);
   if (out) *out = w;
   return align_up(c.off, 256);
 }
@@ -495,7 +498,7 @@ static int forward_impl(const AgxModelDims* dims, const float* wts, const AgxGra
     const bool mixed = precision == AGX_PREC_TC_MIXED;
     const size_t base = L.total * sizeof(float);
     const TcFwdBuffers tb{ws.nfeat, ws.P, ws.A, ws.Qr, ws.Qs, ws.agg, ws.C, ws.rowmaxP, ws.rowmaxA, ws.agg_exp, ws.agg_max,
-                          ws.P0, ws.Qr0, ws.Qs0, ws.rowmaxP0};
+                          ws.P0, ws.Qr0, ws.Qs0, ws.rowmaxP0, ws.S0};
     if (reuse_node_products) {
       if (!nfeat_ready)                          // (agx_rollout's advance kernel has normally written the records already)
         if (int rc = tc_nfeat(g, tb, st)) return rc;

@@ -269,12 +269,11 @@ struct EdgeArgs {
 };
 
 // 17 relation inputs (model.py:224-253) of the K=32 first layer; half 0 builds inputs 0..15, half 1 input 16 (+ zero padding)
-__device__ __forceinline__ void edge_inputs(const EdgeArgs& a, int64_t e, int64_t E, int half, float (&v)[HW]) {
+// r, s: flattened receiver / sender of the relation (r < 0: no relation in this row of the tile)
+__device__ __forceinline__ void edge_inputs(const EdgeArgs& a, int r, int s, int half, float (&v)[HW]) {
 #pragma unroll
   for (int i = 0; i < HW; ++i) v[i] = 0.f;
-  if (e >= 0 && e < E) {
-    const int r = a.recv[e];
-    const int s = (r / a.N) * a.N + a.send[e];
+  if (r >= 0) {
     const float4* fr = reinterpret_cast<const float4*>(a.nfeat + (size_t)r * NFEAT);
     const float4* fs = reinterpret_cast<const float4*>(a.nfeat + (size_t)s * NFEAT);
     if (half == 0) {   // [attr_r, attr_s, |group_r - group_s|, hist diff 0..10]
@@ -316,9 +315,25 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
     uint32_t in_hi[8], in_lo[8];
     int in_exp = 0;
     float in_bound = 1.f;
-    auto produce = [&](int tile) {
+    // The relation's endpoints are fetched a whole tile ahead (two dependent index loads) and their history records pulled
+    // towards L2 / L1 as soon as they are known, so that produce() below waits for one short round trip instead of three long ones
+    // (r02l timeline: the gather sat 3000 cycles in front of the last layer's epilogue).
+    int nr = -1, ns = -1;
+    auto fetch_endpoints = [&](int tile) {
+      const int64_t e = (int64_t)tile * TILE + cx.row;
+      nr = ns = -1;
+      if (e < E) { nr = __ldg(a.recv + e); ns = __ldg(a.send + e); }
+    };
+    auto touch_records = [&]() {
+      if (nr >= 0) {
+        ns += (nr / a.N) * a.N;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nfeat + (size_t)nr * NFEAT));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nfeat + (size_t)ns * NFEAT));
+      }
+    };
+    auto produce = [&]() {
       float vin[HW];
-      edge_inputs(a, (int64_t)tile * TILE + cx.row, E, cx.half, vin);
+      edge_inputs(a, nr, ns, cx.half, vin);
       in_bound = fmaxf(epi_exchange<true>(sh, cx, max16(vin, 0.f)), 1.f);
       if (cx.half == 1) vin[1] = 1.f;   // input 17: the constant that multiplies the bias column of relation_encoder.model.0
       in_exp = scale_exp(in_bound);
@@ -329,18 +344,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
       epi_signal(cx, &sh.bar_in[cx.slot]);
     };
     int tile = slot_tile(0, cx.slot, n_tiles);
-    if (tile >= 0) { produce(tile); commit(); }
+    if (tile >= 0) { fetch_endpoints(tile); touch_records(); produce(); commit(); }
     for (int k = 0; tile >= 0; ++k) {
       const int64_t e = (int64_t)tile * TILE + cx.row;
       AGX_STAMP_EPI(cx, 30);
       cx.e_in = in_exp;
       cx.bound_in = in_bound;
       const int next = slot_tile(k + 1, cx.slot, n_tiles);
+      if (next >= 0) fetch_endpoints(next);
       epi_hidden<a_needs_lo(prog, 1)>(sh, cx, meta[0]);
+      if (next >= 0) touch_records();
       epi_hidden<a_needs_lo(prog, 2)>(sh, cx, meta[1]);
       epi_hidden<a_needs_lo(prog, 3)>(sh, cx, meta[2]);
       AGX_STAMP_EPI(cx, 31);
-      if (next >= 0) produce(next);
+      if (next >= 0) produce();
       if (!MIXED) {
         epi_store_rows(sh, cx, meta[3], a.C, e, e < E, [&]() { if (next >= 0) commit(); });
       } else {
@@ -363,6 +380,7 @@ struct NodeArgs {
   int B, N, n_p;
   const uint8_t* blob; TcLayout L;
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* rowmaxP; float* rowmaxA;
+  float* S0;   // A_n + particle_encode: the residual input of propagation step 0 in one stream instead of two
 };
 
 // node inputs (model.py:168-195) + the nfeat record; only half 0 carries data (6 real inputs of the K=16 layer)
@@ -437,7 +455,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
         cx.e_in = e_next;
         if (valid && cx.half == 0) a.rowmaxP[r] = pm;
       }
-      float am = epi_store_rows(sh, cx, meta[3], a.A, r, valid);   // A_n = W_enc*penc + b
+      float am = 0.f;                                              // A_n = W_enc*penc + b, and S0 = A_n + particle_encode
+      epi_layer_out<false>(sh, cx, exp2i(-cx.e_in) * meta[3].x, [&](int, int col0, float (&v)[HW]) {
+        am = max16(v, am);
+        if (valid) {
+          blk_store16(a.A, r, col0, v);
+          blk_add16(a.P, r, col0, v);        // this thread's own store of a moment ago (L1 / L2 hit)
+          blk_store16(a.S0, r, col0, v);
+        }
+      });
       am = epi_exchange<true>(sh, cx, am);
       if (valid && cx.half == 0) a.rowmaxA[r] = am;
       epi_store_rows<false>(sh, cx, meta[4], a.Qr, r, valid);
@@ -466,6 +492,7 @@ struct UpdArgs {
   const uint32_t* agg_split;   // blocked; per (row, 16-column piece) 8 packed-fp16 hi words then 8 lo words (edge_aggregate, split output)
   const int32_t* agg_exp; const float* agg_max;   // per-row scale exponent / row maximum of agg
   const float* A; const float* P_in; float* P; float* Qr; float* Qs; const float* rowmaxP_in; float* rowmaxP; const float* rowmaxA;
+  const float* S0;   // propagation step 0: A_n + P_in precomputed by the particle encoder (nullptr otherwise)
   const uint8_t* blob; TcLayout L;   // P_in / rowmaxP_in: the residual stream this step reads (the encoder's copy at pstep 0, else P / rowmaxP)
   const float* head_w;   // fp32 [3][FP] then 4 bias floats (head only)
   const float* state; float* pred_pos; int64_t pos_stride_b; float* pred_motion;
@@ -504,8 +531,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
       AGX_STAMP_EPI(cx, 30);
       if (cx.warp % SLOT_WARPS == 0 && cx.lane == 0) {
         // the residual rows of this tile are read by the first layer's epilogue: start them towards L2 now
-        bulk_prefetch_l2(a.A + (int64_t)tile * BLK_TILE, BLK_TILE * 4);   // (buffers are padded to whole tiles)
-        bulk_prefetch_l2(a.P_in + (int64_t)tile * BLK_TILE, BLK_TILE * 4);
+        if (a.S0) {
+          bulk_prefetch_l2(a.S0 + (int64_t)tile * BLK_TILE, BLK_TILE * 4);   // (buffers are padded to whole tiles)
+        } else {
+          bulk_prefetch_l2(a.A + (int64_t)tile * BLK_TILE, BLK_TILE * 4);
+          bulk_prefetch_l2(a.P_in + (int64_t)tile * BLK_TILE, BLK_TILE * 4);
+        }
       }
       // ---- producer: the aggregated relation effects arrive already scaled and split (edge_aggregate): copy to A
       {
@@ -541,8 +572,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
         float pm = epi_layer_to_a<a_needs_lo(prog, 1)>(sh, cx, unscale, exp2i(e_next),
                                   [&](int, int col0, float (&v)[HW]) {
                                     if (valid) {
-                                      blk_add16(a.A, r, col0, v);
-                                      blk_add16(a.P_in, r, col0, v);
+                                      if (a.S0) {
+                                        blk_add16(a.S0, r, col0, v);
+                                      } else {
+                                        blk_add16(a.A, r, col0, v);
+                                        blk_add16(a.P_in, r, col0, v);
+                                      }
                                     }
                                   },
                                   [&](int, int col0, const float (&v)[HW]) {
@@ -1100,6 +1135,7 @@ struct TcFwdBuffers {
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
   int32_t* agg_exp; float* agg_max;
   float* P0; float* Qr0; float* Qs0; float* rowmaxP0;   // the particle encoder's copies (read-only for the propagation steps)
+  float* S0;                                            // A_n + P0
 };
 
 static int tc_ensure_attrs() {
@@ -1129,7 +1165,7 @@ int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
   const int tiles = (int)((rows + TILE - 1) / TILE);
   NodeArgs a{g->state, g->attrs, g->action, g->p_instance, g->physics, g->B, g->N, g->n_p,
              reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
-             w.nfeat, w.P0, w.A, w.Qr0, w.Qs0, w.rowmaxP0, w.rowmaxA};
+             w.nfeat, w.P0, w.A, w.Qr0, w.Qs0, w.rowmaxP0, w.rowmaxA, w.S0};
   { ProfScope ps(AGX_KIND_NODE_ENCODER, st);
     tc_node_encoder_kernel<<<tiles < num_sms() ? tiles : num_sms(), THREADS, SMEM_BYTES, st>>>(a); }
   AGX_LAUNCH_CHECK();
@@ -1141,7 +1177,7 @@ int tc_nfeat(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st) {
   using namespace tc;
   const int64_t rows = (int64_t)g->B * g->N;
   NodeArgs a{g->state, g->attrs, g->action, g->p_instance, g->physics, g->B, g->N, g->n_p, nullptr, TcLayout{},
-             w.nfeat, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+             w.nfeat, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   { ProfScope ps(AGX_KIND_NODE_ENCODER, st);
     nfeat_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(a); }
   AGX_LAUNCH_CHECK();
@@ -1221,7 +1257,7 @@ int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL
   const int tiles = (int)((rows + TILE - 1) / TILE);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   UpdArgs a{g->B, g->N, g->n_p, reinterpret_cast<const uint32_t*>(w.agg), w.agg_exp, w.agg_max, w.A, first ? w.P0 : w.P, w.P, w.Qr, w.Qs,
-            first ? w.rowmaxP0 : w.rowmaxP, w.rowmaxP, w.rowmaxA,
+            first ? w.rowmaxP0 : w.rowmaxP, w.rowmaxP, w.rowmaxA, first ? w.S0 : nullptr,
             reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
             wts + PL.pred2_w, g->state, pred_pos, pos_stride_b, pred_motion};
   if (last) {
