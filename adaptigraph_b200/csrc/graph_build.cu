@@ -83,13 +83,14 @@ static size_t graph_ws_carve(void* base, int B, int N, int topk, GraphWs* ws) {
 }
 
 // ------------------------------------------------------------------------------------ G0
-// Ascending list of the graph's tool particles (ordered compaction), by the graph's CTA of 1024 threads.
+// Ascending list of the graph's tool particles (ordered compaction), by the graph's CTA of T threads.
+template <int T>
 __device__ __forceinline__ void tool_list_block(const uint8_t* __restrict__ tm, int N, int32_t* __restrict__ tools,
                                                 int32_t* __restrict__ n_tools_b, int* warp_tot /*[32] shared*/, int* base_s /*shared*/) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *base_s = 0;
   __syncthreads();
-  for (int j0 = 0; j0 < N; j0 += 1024) {
+  for (int j0 = 0; j0 < N; j0 += T) {
     const int j = j0 + tid;
     const bool f = (j < N) && tm[j];
     const unsigned m = __ballot_sync(FULL, f);
@@ -101,7 +102,7 @@ __device__ __forceinline__ void tool_list_block(const uint8_t* __restrict__ tm, 
     __syncthreads();
     if (tid == 0) {
       int t = 0;
-      for (int w = 0; w < 32; ++w) t += warp_tot[w];
+      for (int w = 0; w < T / 32; ++w) t += warp_tot[w];
       *base_s += t;
     }
     __syncthreads();
@@ -119,7 +120,10 @@ __device__ __forceinline__ int cell_coord(float x, float lo, float w, int n) {
   return min(max((int)fminf(fmaxf(u, 0.f), (float)GRID_MAX_AXIS), 0), n - 1);   // NaN -> 0
 }
 
-__global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restrict__ pos, int64_t pos_stride_b,
+// T threads per graph: 1024, or 256 for the small graphs of the planning configurations (200 particles x thousands of samples:
+// a 1024-thread CTA per graph left most lanes idle and its scan dominated -- 0.11 ms of a 0.25 ms build at 200 x 4096).
+template <int T>
+__global__ void __launch_bounds__(T) sort_cells_kernel(const float* __restrict__ pos, int64_t pos_stride_b,
                                                            const uint8_t* __restrict__ mask, const uint8_t* __restrict__ tool_mask,
                                                            const float* __restrict__ thr2, int N, float* __restrict__ sx,
                                                            float* __restrict__ sy, float* __restrict__ sz, int32_t* __restrict__ scell,
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restric
   const uint8_t* mk = mask + (size_t)b * N;
   const float INF = __int_as_float(0x7f800000);
   float mn[3] = {INF, INF, INF}, mx[3] = {-INF, -INF, -INF};
-  for (int j = tid; j < N; j += 1024) {
+  for (int j = tid; j < N; j += T) {
     if (!mk[j]) continue;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restric
     float ext[3], lo3[3], amax = 0.f;
     for (int a = 0; a < 3; ++a) {
       float lo = INF, hi = -INF;
-      for (int w = 0; w < 32; ++w) { lo = fminf(lo, red[a][w]); hi = fmaxf(hi, red[3 + a][w]); }
+      for (int w = 0; w < T / 32; ++w) { lo = fminf(lo, red[a][w]); hi = fmaxf(hi, red[3 + a][w]); }
       const bool ok = lo <= hi && hi < INF && lo > -INF;   // no valid particle, or non-finite coordinates: a single cell on this axis
       ext[a] = ok ? hi - lo : 0.f;
       lo3[a] = ok ? lo : 0.f;
@@ -201,12 +205,12 @@ __global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restric
   auto cell_of = [&](int j) { return cell_coord(p[3 * j + axa], loa, wa, na) * nb + cell_coord(p[3 * j + axb], lob, wb, nb); };
   // counting sort by cell id.  The order INSIDE a cell is whatever the atomics give: nothing downstream depends on it (knn_rows
   // ranks candidates by (distance, particle id), a strict total order, and emits them sorted by id).
-  for (int c = tid; c <= n_cells; c += 1024) cnt[c] = 0;
+  for (int c = tid; c <= n_cells; c += T) cnt[c] = 0;
   __syncthreads();
-  for (int j = tid; j < N; j += 1024) atomicAdd(&cnt[cell_of(j)], 1);
+  for (int j = tid; j < N; j += T) atomicAdd(&cnt[cell_of(j)], 1);
   __syncthreads();
-  // exclusive scan of cnt[0 .. n_cells] (<= 4097 entries): each thread owns up to 5 consecutive entries
-  constexpr int PER = (GRID_MAX_CELLS + 1 + 1023) / 1024;
+  // exclusive scan of cnt[0 .. n_cells] (<= 4097 entries): each thread owns PER consecutive entries
+  constexpr int PER = (GRID_MAX_CELLS + 1 + T - 1) / T;
   int local[PER], sum = 0;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restric
   if (lane == 31) wsum[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    int w = wsum[lane];
+    int w = lane < T / 32 ? wsum[lane] : 0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(FULL, w, o);
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restric
     run += local[i];
   }
   __syncthreads();
-  for (int j = tid; j < N; j += 1024) {
+  for (int j = tid; j < N; j += T) {
     const int c = cell_of(j);
     const int s = atomicAdd(&cnt[c], 1);
     const size_t o = (size_t)b * N + s;
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(1024) sort_cells_kernel(const float* __restric
   if (tools) {                                   // connect_tools_all
     if (tid == 0) flags[b] = 0;
     __syncthreads();                             // wsum / cnt are free again
-    tool_list_block(tool_mask + (size_t)b * N, N, tools + (size_t)b * N, n_tools + b, wsum, &cnt[0]);
+    tool_list_block<T>(tool_mask + (size_t)b * N, N, tools + (size_t)b * N, n_tools + b, wsum, &cnt[0]);
   }
 }
 
@@ -567,7 +571,11 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
   const int rows = B * N;
   const int nblk = (rows + SCAN_BLOCK - 1) / SCAN_BLOCK;
   { ProfScope ps(AGX_KIND_GRAPH_SORT, st);
-    sort_cells_kernel<<<B, 1024, 0, st>>>(pos, pos_stride_b, mask, tool_mask, thr2, N, ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx,
+    if (N <= 512)
+      sort_cells_kernel<256><<<B, 256, 0, st>>>(pos, pos_stride_b, mask, tool_mask, thr2, N, ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx,
+                                                ws.sflag, ws.cell_start, ws.grid_dims, cta ? ws.tools : nullptr, ws.n_tools, ws.flags, ws.ticket);
+    else
+      sort_cells_kernel<1024><<<B, 1024, 0, st>>>(pos, pos_stride_b, mask, tool_mask, thr2, N, ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx,
                                                   ws.sflag, ws.cell_start, ws.grid_dims, cta ? ws.tools : nullptr, ws.n_tools, ws.flags, ws.ticket); }
   AGX_LAUNCH_CHECK();
   dim3 g1((N + G1_ROWS_PER_CTA - 1) / G1_ROWS_PER_CTA, B);

@@ -13,7 +13,8 @@ rank rolls out its own 128 graphs (weak scaling, no data-path collective; SURVEY
 Engine arm (default) prints one JSON line with
   value    device-resident throughput (inputs in HBM, CUDA events, max over ranks) of the rollout replayed as a CUDA graph
            (`agx.GraphedRollout`, the public API for repeated rollouts of one shape; `--eager` times the plain call)
-  e2e      the same rollout through the public API from pinned HOST buffers, H2D + D2H inside the timed region
+  e2e      the same rollout through the public API from pinned HOST buffers: every step's H2D of its inputs and D2H of its
+           predictions inside the timed region (double-buffered on two copy streams, as a caller with a stream of batches would)
   roofline the dominant kernel's achieved algorithmic B/s against MEASURED_PEAKS.json, from a SEPARATE profiled pass
            (per-kernel CUDA events are never enabled inside the timed regions)
   cpu_baseline the reference's own CPU path on the host cores, bounded sample
@@ -319,35 +320,59 @@ def bench_engine(args, rank, world, local_rank, sweep_point=None):
         value = job_particle_steps / (ms_per_step * 1e-3)
         result_state = out["state_seqs"].clone()
 
-        # ---- end to end from pinned host buffers (H2D of the step's inputs + D2H of the predictions each step)
+        # ---- end to end from pinned host buffers: every step uploads its inputs and reads its predictions back.  Steps are
+        # pipelined the way a caller with a stream of host batches would drive the public API: two staging buffers each way, the
+        # H2D of step i + 1 and the D2H of step i - 1 on their own streams under the rollout of step i.
         host = {k: v.pin_memory() for k, v in dict(state=w_host.state, attrs=w_host.attrs, action=w_host.action, p_instance=w_host.p_instance,
                                                    physics_param=w_host.physics_param, state_mask=w_host.state_mask,
                                                    eef_mask=w_host.eef_mask).items()}
         h2d = sum(v.numel() * v.element_size() for v in host.values())
-        out_host = torch.empty(B, T, n_p, 3, dtype=torch.float32).pin_memory()
-        d2h = out_host.numel() * 4
+        d2h = B * T * n_p * 3 * 4
+        main = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        dev_in = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+        dev_out = [torch.empty(B, T, n_p, 3, dtype=torch.float32, device=dev) for _ in range(2)]
+        host_out = [torch.empty(B, T, n_p, 3, dtype=torch.float32).pin_memory() for _ in range(2)]
+        ev = lambda: [torch.cuda.Event() for _ in range(2)]  # noqa: E731
+        in_ready, in_free, out_ready, out_free = ev(), ev(), ev(), ev()
 
-        def e2e_step():
-            if graphed is not None:                                    # host buffers -> the captured device buffers -> replay
-                o = graphed(**host)
+        def e2e_step(i):
+            b = i & 1
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(in_free[b])                           # staging buffer b was consumed by step i - 2
+                for k, v in host.items():
+                    dev_in[b][k].copy_(v, non_blocking=True)          # H2D
+                in_ready[b].record(s_in)
+            main.wait_event(in_ready[b])
+            if graphed is not None:
+                o = graphed(**dev_in[b])                              # into the captured buffers, replay
             else:
-                d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+                d = dev_in[b]
                 o = model.rollout(d["state"], d["attrs"], d["action"], d["p_instance"], d["physics_param"], d["state_mask"], d["eef_mask"],
                                   w_host.adj_thresh, w_host.topk, w_host.connect_tools_all, T, WORKLOAD["max_nR"], check=False)
-            out_host.copy_(o["state_seqs"], non_blocking=True)
+            in_free[b].record(main)
+            main.wait_event(out_free[b])                              # dev_out[b] has left for the host (step i - 2)
+            dev_out[b].copy_(o["state_seqs"])
+            out_ready[b].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(out_ready[b])
+                host_out[b].copy_(dev_out[b], non_blocking=True)      # D2H
+                out_free[b].record(s_out)
 
-        for _ in range(2):
-            e2e_step()
+        for i in range(2):
+            e2e_step(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
-            e2e_step()
+        for i in range(args.steps):
+            e2e_step(i)
+        main.wait_stream(s_in)
+        main.wait_stream(s_out)                                       # the last step's predictions are on the host
         e1.record()
         barrier()
         e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
         e2e_value = job_particle_steps / (e2e_ms * 1e-3)
-        assert torch.equal(out_host.to(dev), result_state), "the end-to-end pass must reproduce the device-resident result"
+        assert torch.equal(host_out[(args.steps - 1) & 1].to(dev), result_state), "the end-to-end pass must reproduce the device-resident result"
 
         # ---- separate profiled pass (eager, per-kernel CUDA events on the launch stream): never inside a timed region above
         ops.profile_read()
@@ -407,7 +432,8 @@ def bench_engine(args, rank, world, local_rank, sweep_point=None):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(config_block(B), arithmetic=precision, launch="eager" if graphed is None else "cuda graph replay (GraphedRollout)"),
-        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "how": "pinned host inputs uploaded and predictions read back every step; copies double-buffered on two side streams"},
         "gpu_launches": launches_per_rollout * args.steps, "launches_per_model_step": launches_per_rollout / T,
         "roofline": roof, "kernels": kernels, "relations_per_graph": Eg, "clocks": clocks.summary(),
     }
