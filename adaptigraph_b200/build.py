@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libadaptigraph_b200.so")
-SOURCES = ["api.cu", "graph_build.cu", "sampling.cu", "rewards.cu", "forward.cu", "tc_forward.cu", "train.cu", "optim.cu"]
+SOURCES = ["api.cu", "graph_build.cu", "sampling.cu", "rewards.cu", "forward.cu", "tc_forward.cu", "train.cu", "tc_wgrad.cu", "optim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--fmad=true", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared",

@@ -18,6 +18,7 @@
 //                         last pstep the motion head (model.py:306-309) and pred_pos = pos + clamp(motion)
 //         rollout_advance tool kinematics + history shift between rollout steps
 #include "common.cuh"
+#include "tc_forward.cuh"
 #include "mlp_simt.cuh"
 
 namespace agx {
@@ -29,24 +30,11 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
 
 constexpr float MOTION_CLAMP = 100.f;  // model.py:85
 
-// tensor-core path (tc_forward.cu)
-struct TcFwdBuffers {
-  float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
-  int32_t* agg_exp; float* agg_max;
-  float* P0; float* Qr0; float* Qs0; float* rowmaxP0;   // the particle encoder's copies (read-only for the propagation steps)
-  float* S0;                                            // A_n + P0
-};
-int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, bool first, cudaStream_t st);
-int tc_nfeat(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st);
+// tensor-core path (tc_forward.cu): tc_forward.cuh
 size_t tc_blob_bytes(size_t base_bytes);
 size_t train_blob_bytes();
 int train_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, cudaStream_t st);
 int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_t base_bytes, cudaStream_t st);
-int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, cudaStream_t st);
-int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool mixed,
-                    cudaStream_t st);
-int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL, size_t base_bytes, const TcFwdBuffers& w, bool first, bool last,
-                   float* pred_pos, int64_t pos_stride_b, float* pred_motion, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------ weight packing
 __global__ void pack_mat_kernel(const float* __restrict__ W, int ld, int col0, int K, int F, int Kpad, float* __restrict__ dst) {

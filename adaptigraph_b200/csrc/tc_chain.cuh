@@ -483,9 +483,10 @@ __device__ __forceinline__ void epi_layer_plain(const Shared& sh, EpiCtx& cx, fl
   AGX_STAMP_EPI(cx, 26);
 }
 
-// General layer whose result becomes the slot's next A.  per chunk: v = acc * unscale ; extra(c, col0, v) ; relu ;
-// side(c, col0, v) [e.g. store the fp32 row piece] ; split with `scale`.  Returns the thread's partial row maximum.
-template <bool LO = true, class Extra, class Side>
+// General layer whose result becomes the slot's next A.  per chunk: v = acc * unscale ; extra(c, col0, v) ; relu (RELU) ;
+// side(c, col0, v) [e.g. store the fp32 row piece; it may also replace v: what it leaves is what gets split] ; split with `scale`.
+// Returns the thread's partial row maximum of |v| (taken before side).
+template <bool LO = true, bool RELU = true, class Extra, class Side>
 __device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, float unscale, float scale, Extra extra, Side side) {
   float mx = 0.f;
   uint32_t hiA[NCHUNK_A][8], loA[LO ? NCHUNK_A : 1][8];
@@ -505,7 +506,7 @@ __device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, fl
       epi_scale(r[c], unscale, v);
       extra(c, col0, v);
 #pragma unroll
-      for (int i = 0; i < HW; ++i) { v[i] = fmaxf(v[i], 0.f); mx = fmaxf(mx, v[i]); }
+      for (int i = 0; i < HW; ++i) { if (RELU) v[i] = fmaxf(v[i], 0.f); mx = fmaxf(mx, fabsf(v[i])); }
       side(c, col0, v);
       if (LO) split16(v, scale, hiA[c], loA[LO ? c : 0]);
       else round16(v, scale, hiA[c]);
@@ -530,7 +531,7 @@ __device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, fl
     epi_scale(r, unscale, v);
     extra(c, col0, v);
 #pragma unroll
-    for (int i = 0; i < HW; ++i) { v[i] = fmaxf(v[i], 0.f); mx = fmaxf(mx, v[i]); }
+    for (int i = 0; i < HW; ++i) { if (RELU) v[i] = fmaxf(v[i], 0.f); mx = fmaxf(mx, fabsf(v[i])); }
     side(c, col0, v);
     if (owns_one(cx, c)) v[ONE_COL % HW] = 1.f;   // after the fp32 side store: only the tensor-memory copy carries the 1
     epi_store_a<LO>(cx, c, v, scale);

@@ -3,6 +3,7 @@
 // evaluated as split-fp16 MMAs (tc_chain.cuh).  Reference arithmetic: dynamics/gnn/model.py:129-313.
 #include "common.cuh"
 #include "tc_chain.cuh"
+#include "tc_forward.cuh"
 
 namespace agx {
 namespace tc {
@@ -203,6 +204,16 @@ __device__ __forceinline__ void epi_hidden(const Shared& sh, EpiCtx& cx, const f
   cx.e_in = e_next;
 }
 
+// same layer, with the fp32 activations handed to `side` (training: the backward needs every ReLU output)
+template <bool LO = true, class Side>
+__device__ __forceinline__ void epi_hidden_side(const Shared& sh, EpiCtx& cx, const float4 meta_l, Side side) {
+  const float bound_next = fmaxf(cx.bound_in * meta_l.y, 1.f);
+  const int e_next = scale_exp(bound_next);
+  epi_layer_to_a<LO>(sh, cx, exp2i(-cx.e_in) * meta_l.x, exp2i(e_next), NoExtra{}, side);
+  cx.bound_in = bound_next;
+  cx.e_in = e_next;
+}
+
 // acc (bias inside the MMA) -> fp32 rows in HBM (A is left untouched); returns this thread's partial max |v|
 template <bool ROW_MAJOR = false, class AllRead = NoHook>
 __device__ __forceinline__ float epi_store_rows(const Shared& sh, EpiCtx& cx, const float4 meta_l, float* out, int64_t grow, bool valid,
@@ -266,6 +277,9 @@ struct EdgeArgs {
   const float* nfeat;
   const uint8_t* blob; TcLayout L;
   float* C;          // fp32 blocked rows (AGX_PREC_TC_F16X3) or C16 rows (AGX_PREC_TC_MIXED)
+  // training (SAVE): row-major fp32 copies of what the backward reads -- the 17 relation inputs ([E][D_REL_IN]) and the three
+  // ReLU outputs of the relation encoder ([E][FP])
+  float* sv_rel_in; float* sv_g1; float* sv_g2; float* sv_renc;
 };
 
 // 17 relation inputs (model.py:224-253) of the K=32 first layer; half 0 builds inputs 0..15, half 1 input 16 (+ zero padding)
@@ -288,7 +302,7 @@ __device__ __forceinline__ void edge_inputs(const EdgeArgs& a, int r, int s, int
   }
 }
 
-template <bool MIXED>
+template <bool MIXED, bool SAVE = false>
 __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int NM = MIXED ? AGX_MMA_EDGE : 3;
@@ -331,9 +345,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
         asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nfeat + (size_t)ns * NFEAT));
       }
     };
-    auto produce = [&]() {
+    auto produce = [&](int tile_of) {
       float vin[HW];
       edge_inputs(a, nr, ns, cx.half, vin);
+      if (SAVE) {
+        const int64_t e = (int64_t)tile_of * TILE + cx.row;
+        if (e < E) {
+          float4* o = reinterpret_cast<float4*>(a.sv_rel_in + e * D_REL_IN + HW * cx.half);
+          o[0] = make_float4(vin[0], vin[1], vin[2], vin[3]);
+          o[1] = make_float4(vin[4], vin[5], vin[6], vin[7]);
+          if (cx.half == 0) { o[2] = make_float4(vin[8], vin[9], vin[10], vin[11]); o[3] = make_float4(vin[12], vin[13], vin[14], vin[15]); }
+        }
+      }
       in_bound = fmaxf(epi_exchange<true>(sh, cx, max16(vin, 0.f)), 1.f);
       if (cx.half == 1) vin[1] = 1.f;   // input 17: the constant that multiplies the bias column of relation_encoder.model.0
       in_exp = scale_exp(in_bound);
@@ -344,7 +367,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
       epi_signal(cx, &sh.bar_in[cx.slot]);
     };
     int tile = slot_tile(0, cx.slot, n_tiles);
-    if (tile >= 0) { fetch_endpoints(tile); touch_records(); produce(); commit(); }
+    if (tile >= 0) { fetch_endpoints(tile); touch_records(); produce(tile); commit(); }
     for (int k = 0; tile >= 0; ++k) {
       const int64_t e = (int64_t)tile * TILE + cx.row;
       AGX_STAMP_EPI(cx, 30);
@@ -352,12 +375,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_edge_encoder_kernel(const EdgeA
       cx.bound_in = in_bound;
       const int next = slot_tile(k + 1, cx.slot, n_tiles);
       if (next >= 0) fetch_endpoints(next);
-      epi_hidden<a_needs_lo(prog, 1)>(sh, cx, meta[0]);
-      if (next >= 0) touch_records();
-      epi_hidden<a_needs_lo(prog, 2)>(sh, cx, meta[1]);
-      epi_hidden<a_needs_lo(prog, 3)>(sh, cx, meta[2]);
+      if (SAVE) {
+        epi_hidden_side<true>(sh, cx, meta[0], [&](int, int col0, const float (&v)[HW]) { if (e < E) row_store16(a.sv_g1, e, col0, v); });
+        if (next >= 0) touch_records();
+        epi_hidden_side<true>(sh, cx, meta[1], [&](int, int col0, const float (&v)[HW]) { if (e < E) row_store16(a.sv_g2, e, col0, v); });
+        epi_hidden_side<true>(sh, cx, meta[2], [&](int, int col0, const float (&v)[HW]) { if (e < E) row_store16(a.sv_renc, e, col0, v); });
+      } else {
+        epi_hidden<a_needs_lo(prog, 1)>(sh, cx, meta[0]);
+        if (next >= 0) touch_records();
+        epi_hidden<a_needs_lo(prog, 2)>(sh, cx, meta[1]);
+        epi_hidden<a_needs_lo(prog, 3)>(sh, cx, meta[2]);
+      }
       AGX_STAMP_EPI(cx, 31);
-      if (next >= 0) produce();
+      if (next >= 0) produce(next);
       if (!MIXED) {
         epi_store_rows(sh, cx, meta[3], a.C, e, e < E, [&]() { if (next >= 0) commit(); });
       } else {
@@ -381,6 +411,8 @@ struct NodeArgs {
   const uint8_t* blob; TcLayout L;
   float* nfeat; float* P; float* A; float* Qr; float* Qs; float* rowmaxP; float* rowmaxA;
   float* S0;   // A_n + particle_encode: the residual input of propagation step 0 in one stream instead of two
+  // training (SAVE): row-major fp32 copies for the backward -- the node inputs ([rows][D_NODE_IN]) and the encoder's ReLU outputs
+  float* sv_p_in; float* sv_h1; float* sv_h2; float* sv_penc;
 };
 
 // node inputs (model.py:168-195) + the nfeat record; only half 0 carries data (6 real inputs of the K=16 layer)
@@ -408,6 +440,7 @@ __device__ __forceinline__ void node_inputs(const NodeArgs& a, int64_t r, int64_
   }
 }
 
+template <bool SAVE = false>
 __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   constexpr LayerStep prog[6] = {{T_PENC0, 1, IN_PRODUCER, 3}, {T_PENC2, 10, IN_EPILOGUE, AGX_MMA_NODE}, {T_PENC4, 10, IN_EPILOGUE, AGX_MMA_NODE},
@@ -435,20 +468,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_encoder_kernel(const NodeA
       float in[HW];
       node_inputs(a, r, rows, cx.half, in);
       const float mx = fmaxf(epi_exchange<true>(sh, cx, max16(in, 0.f)), 1.f);
+      if (SAVE && valid && cx.half == 0) {
+        float4* o = reinterpret_cast<float4*>(a.sv_p_in + r * D_NODE_IN);
+        o[0] = make_float4(in[0], in[1], in[2], in[3]);
+        o[1] = make_float4(in[4], in[5], 0.f, 0.f);
+      }
       if (cx.half == 0) in[6] = 1.f;      // input 6: the constant that multiplies the bias column of particle_encoder.model.0
       cx.e_in = scale_exp(mx);
       cx.bound_in = mx;
       if (cx.half == 0) epi_store_a(cx, 0, in, exp2i(cx.e_in));   // the K=16 layer reads A columns 0..7 only
       epi_signal(cx, &sh.bar_in[cx.slot]);
 
-      epi_hidden<a_needs_lo(prog, 1)>(sh, cx, meta[0]);
-      epi_hidden<a_needs_lo(prog, 2)>(sh, cx, meta[1]);
+      if (SAVE) {
+        epi_hidden_side<true>(sh, cx, meta[0], [&](int, int col0, const float (&v)[HW]) { if (valid) row_store16(a.sv_h1, r, col0, v); });
+        epi_hidden_side<true>(sh, cx, meta[1], [&](int, int col0, const float (&v)[HW]) { if (valid) row_store16(a.sv_h2, r, col0, v); });
+      } else {
+        epi_hidden<a_needs_lo(prog, 1)>(sh, cx, meta[0]);
+        epi_hidden<a_needs_lo(prog, 2)>(sh, cx, meta[1]);
+      }
       {  // particle_encode = particle_effect_0 (model.py:268-269): next A and the fp32 P rows (with their row maximum)
         const float4 m = meta[2];
         const float bound_next = fmaxf(cx.bound_in * m.y, 1.f);
         const int e_next = scale_exp(bound_next);
         float pm = epi_layer_to_a<a_needs_lo(prog, 3)>(sh, cx, exp2i(-cx.e_in) * m.x, exp2i(e_next), NoExtra{}, [&](int, int col0, const float (&v)[HW]) {
-          if (valid) blk_store16(a.P, r, col0, v);
+          if (valid) {
+            blk_store16(a.P, r, col0, v);
+            if (SAVE) row_store16(a.sv_penc, r, col0, v);
+          }
         });
         pm = epi_exchange<true>(sh, cx, pm);
         cx.bound_in = bound_next;
@@ -496,9 +542,11 @@ struct UpdArgs {
   const uint8_t* blob; TcLayout L;   // P_in / rowmaxP_in: the residual stream this step reads (the encoder's copy at pstep 0, else P / rowmaxP)
   const float* head_w;   // fp32 [3][FP] then 4 bias floats (head only)
   const float* state; float* pred_pos; int64_t pos_stride_b; float* pred_motion;
+  // training (SAVE): row-major fp32 copies for the backward -- the new particle effects and, in the head, its two ReLU outputs
+  float* sv_P; float* sv_u1; float* sv_u2;
 };
 
-template <bool LAST>
+template <bool LAST, bool SAVE = false>
 __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   constexpr LayerStep prog[3] = {{T_PP_AGG, 10, IN_PRODUCER, 3}, {LAST ? T_PRED0 : T_RP_RECV, 10, IN_EPILOGUE, AGX_MMA_NODE},
@@ -582,6 +630,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
                                   },
                                   [&](int, int col0, const float (&v)[HW]) {
                                     if (!LAST && valid) blk_store16(a.P, r, col0, v);
+                                    if (SAVE && valid) row_store16(a.sv_P, r, col0, v);
                                   });
         pm = epi_exchange<true>(sh, cx, pm);
         cx.bound_in = fmaxf(pm, 1.f);                  // actual maximum of the new P row (tighter than the propagated bound)
@@ -594,11 +643,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
         epi_store_rows<false>(sh, cx, meta[1], a.Qr, r, valid);
         epi_store_rows<false>(sh, cx, meta[2], a.Qs, r, valid);
       } else {
-        epi_hidden<a_needs_lo(prog, 2)>(sh, cx, meta[1]);
+        if (SAVE) epi_hidden_side<true>(sh, cx, meta[1], [&](int, int col0, const float (&v)[HW]) { if (valid) row_store16(a.sv_u1, r, col0, v); });
+        else epi_hidden<a_needs_lo(prog, 2)>(sh, cx, meta[1]);
         // motion head (model.py:306-309): relu(linear_1) then the 3-row linear_2 as running dot products
         const float unscale = exp2i(-cx.e_in) * meta[2].x;
         float m0 = 0.f, m1 = 0.f, m2 = 0.f;
         epi_layer_out<true>(sh, cx, unscale, [&](int, int col0, float (&v)[HW]) {
+          if (SAVE && valid) row_store16(a.sv_u2, r, col0, v);
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             const float4 w0 = lds128(sh.head_w + col0 + 4 * h), w1 = lds128(sh.head_w + FP + col0 + 4 * h),
@@ -766,7 +817,7 @@ constexpr int AGG_CTAS_PER_SM = AGX_AGG_CTAS;
 __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_split_kernel(
     const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send, int rows, int N, int E_cap,
     const float4* __restrict__ C, const float4* __restrict__ Qr, const float4* __restrict__ Qs, uint32_t* __restrict__ agg_split,
-    int32_t* __restrict__ agg_exp, float* __restrict__ agg_max) {
+    int32_t* __restrict__ agg_exp, float* __restrict__ agg_max, float4* __restrict__ agg_f32 /* optional row-major copy (training) */) {
   __shared__ int smax[3][AGG_NODES];
   __shared__ __align__(16) int32_t ids[2][AGG_NODES][AGG_BATCH];   // first AGG_BATCH sender ids of every row of this / the next group
   const int slot = threadIdx.x / (FP / 4), j = threadIdx.x - slot * (FP / 4);
@@ -871,6 +922,7 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
         *reinterpret_cast<uint2*>(piece + lo_at + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
       }
       if (j == 0) { agg_exp[r] = e; agg_max[r] = mx; }
+      if (agg_f32) agg_f32[(size_t)r * (FP / 4) + j] = acc;
     }
     beg = beg1; end = end1; beg1 = beg2; end1 = end2;
   }
@@ -1131,13 +1183,6 @@ int tc_pack(const AgxModelDims* dims, const AgxWeights* raw, void* packed, size_
   return AGX_OK;
 }
 
-struct TcFwdBuffers {
-  float* nfeat; float* P; float* A; float* Qr; float* Qs; float* agg; float* C; float* rowmaxP; float* rowmaxA;
-  int32_t* agg_exp; float* agg_max;
-  float* P0; float* Qr0; float* Qs0; float* rowmaxP0;   // the particle encoder's copies (read-only for the propagation steps)
-  float* S0;                                            // A_n + P0
-};
-
 static int tc_ensure_attrs() {
   static thread_local DeviceOnce once;
   if (!once.need()) return AGX_OK;
@@ -1151,9 +1196,13 @@ static int tc_ensure_attrs() {
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_edge_encoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_edge_encoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(edge_aggregate_c16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A16_SMEM));
-  AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_encoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute((tc_edge_encoder_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute(tc_node_encoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute((tc_node_update_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute((tc_node_update_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   return AGX_OK;
 }
@@ -1165,9 +1214,11 @@ int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
   const int tiles = (int)((rows + TILE - 1) / TILE);
   NodeArgs a{g->state, g->attrs, g->action, g->p_instance, g->physics, g->B, g->N, g->n_p,
              reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
-             w.nfeat, w.P0, w.A, w.Qr0, w.Qs0, w.rowmaxP0, w.rowmaxA, w.S0};
+             w.nfeat, w.P0, w.A, w.Qr0, w.Qs0, w.rowmaxP0, w.rowmaxA, w.S0, nullptr, nullptr, nullptr, nullptr};
+  if (w.save) { a.sv_p_in = w.save->p_in; a.sv_h1 = w.save->h1; a.sv_h2 = w.save->h2; a.sv_penc = w.save->penc; }
   { ProfScope ps(AGX_KIND_NODE_ENCODER, st);
-    tc_node_encoder_kernel<<<tiles < num_sms() ? tiles : num_sms(), THREADS, SMEM_BYTES, st>>>(a); }
+    if (w.save) tc_node_encoder_kernel<true><<<tiles < num_sms() ? tiles : num_sms(), THREADS, SMEM_BYTES, st>>>(a);
+    else tc_node_encoder_kernel<false><<<tiles < num_sms() ? tiles : num_sms(), THREADS, SMEM_BYTES, st>>>(a); }
   AGX_LAUNCH_CHECK();
   return AGX_OK;
 }
@@ -1177,7 +1228,7 @@ int tc_nfeat(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st) {
   using namespace tc;
   const int64_t rows = (int64_t)g->B * g->N;
   NodeArgs a{g->state, g->attrs, g->action, g->p_instance, g->physics, g->B, g->N, g->n_p, nullptr, TcLayout{},
-             w.nfeat, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+             w.nfeat, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   { ProfScope ps(AGX_KIND_NODE_ENCODER, st);
     nfeat_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(a); }
   AGX_LAUNCH_CHECK();
@@ -1191,10 +1242,13 @@ int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
   const int64_t rows = (int64_t)g->B * g->N;
   const int64_t tiles = (g->E_cap + TILE - 1) / TILE;
   EdgeArgs a{g->row_ptr, g->send, g->recv, rows, g->N, g->E_cap, w.nfeat, reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
-             w.C};
+             w.C, nullptr, nullptr, nullptr, nullptr};
+  AGX_REQUIRE(!(w.save && mixed), AGX_ERR_ARG, "edge_encoder: the training copies need the fp32 relation term (AGX_PREC_TC_F16X3)");
+  if (w.save) { a.sv_rel_in = w.save->rel_in; a.sv_g1 = w.save->g1; a.sv_g2 = w.save->g2; a.sv_renc = w.save->renc; }
   { ProfScope ps(AGX_KIND_EDGE_ENCODER, st);
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    if (mixed) tc_edge_encoder_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
+    if (w.save) tc_edge_encoder_kernel<false, true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
+    else if (mixed) tc_edge_encoder_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
     else tc_edge_encoder_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(a); }
   AGX_LAUNCH_CHECK();
   return AGX_OK;
@@ -1244,7 +1298,8 @@ int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, bo
   { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
     edge_aggregate_split_kernel<<<(unsigned)(groups < resident ? groups : resident), AGG_THREADS, 0, st>>>(
         g->row_ptr, g->send, (int)rows, g->N, (int)g->E_cap, reinterpret_cast<const float4*>(w.C), reinterpret_cast<const float4*>(Qr),
-        reinterpret_cast<const float4*>(Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max); }
+        reinterpret_cast<const float4*>(Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max,
+        w.save ? reinterpret_cast<float4*>(w.save->agg_f32) : nullptr); }
   AGX_LAUNCH_CHECK();
   return AGX_OK;
 }
@@ -1259,13 +1314,16 @@ int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL
   UpdArgs a{g->B, g->N, g->n_p, reinterpret_cast<const uint32_t*>(w.agg), w.agg_exp, w.agg_max, w.A, first ? w.P0 : w.P, w.P, w.Qr, w.Qs,
             first ? w.rowmaxP0 : w.rowmaxP, w.rowmaxP, w.rowmaxA, first ? w.S0 : nullptr,
             reinterpret_cast<const uint8_t*>(wts), tc_layout(base_bytes),
-            wts + PL.pred2_w, g->state, pred_pos, pos_stride_b, pred_motion};
+            wts + PL.pred2_w, g->state, pred_pos, pos_stride_b, pred_motion, nullptr, nullptr, nullptr};
+  if (w.save) { a.sv_P = w.save->P_next; a.sv_u1 = w.save->u1; a.sv_u2 = w.save->u2; }
   if (last) {
     ProfScope ps(AGX_KIND_NODE_HEAD, st);
-    tc_node_update_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
+    if (w.save) tc_node_update_kernel<true, true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
+    else tc_node_update_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
   } else {
     ProfScope ps(AGX_KIND_NODE_UPDATE, st);
-    tc_node_update_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(a);
+    if (w.save) tc_node_update_kernel<false, true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
+    else tc_node_update_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(a);
   }
   AGX_LAUNCH_CHECK();
   return AGX_OK;

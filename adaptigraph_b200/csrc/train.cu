@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "mlp_simt.cuh"
 #include "tc_chain.cuh"
+#include "tc_forward.cuh"
+#include "tc_wgrad.cuh"
 
 namespace agx {
 
@@ -249,20 +251,27 @@ __global__ void __launch_bounds__(TA_THREADS) train_aggregate_kernel(const int32
   agg[r * (FP / 4) + j] = acc;
 }
 
+// float4 j (columns 4j .. 4j+3) of row `row` of a feature buffer in either layout (blocked: columns 152..159 are not stored, zero)
+__device__ __forceinline__ float4 feat4(const float* base, int64_t row, int j, bool blocked) {
+  if (!blocked) return *reinterpret_cast<const float4*>(base + row * FP + 4 * j);
+  if (4 * j >= tc::BLK_COLS) return make_float4(0.f, 0.f, 0.f, 0.f);
+  return *reinterpret_cast<const float4*>(base + tc::blk_off(row, 4 * j));
+}
+
 // receiver side of the backward: with d = d_agg[n] (*) [pre_e > 0]:  dC[e] += d ;  dQr[n] = sum_{e in row n} d
 __global__ void __launch_bounds__(TA_THREADS) effect_bwd_recv_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send,
-                                                                     int64_t rows, int N, int64_t E_cap, const float4* __restrict__ C,
-                                                                     const float4* __restrict__ Qr, const float4* __restrict__ Qs,
+                                                                     int64_t rows, int N, int64_t E_cap, const float* __restrict__ C,
+                                                                     const float* __restrict__ Qr, const float* __restrict__ Qs, bool blocked,
                                                                      const float4* __restrict__ d_agg, float4* __restrict__ dC,
                                                                      float4* __restrict__ dQr) {
   const int slot = threadIdx.x / (FP / 4), j = threadIdx.x - slot * (FP / 4);
   const int64_t r = (int64_t)blockIdx.x * TA_NODES + slot;
   if (r >= rows) return;
   const int64_t beg = row_ptr[r], end = min((int64_t)row_ptr[r + 1], E_cap), gb = (r / N) * N;
-  const float4 qr = Qr[r * (FP / 4) + j], da = d_agg[r * (FP / 4) + j];
+  const float4 qr = feat4(Qr, r, j, blocked), da = d_agg[r * (FP / 4) + j];
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t e = beg; e < end; ++e) {
-    const float4 p = pre3(C[e * (FP / 4) + j], qr, Qs[(gb + send[e]) * (FP / 4) + j]);
+    const float4 p = pre3(feat4(C, e, j, blocked), qr, feat4(Qs, gb + send[e], j, blocked));
     const float4 d = make_float4(p.x > 0.f ? da.x : 0.f, p.y > 0.f ? da.y : 0.f, p.z > 0.f ? da.z : 0.f, p.w > 0.f ? da.w : 0.f);
     float4 c = dC[e * (FP / 4) + j];
     c.x += d.x; c.y += d.y; c.z += d.z; c.w += d.w;
@@ -275,19 +284,19 @@ __global__ void __launch_bounds__(TA_THREADS) effect_bwd_recv_kernel(const int32
 // sender side: dQs[s] = sum over the relations sent by s (sender-sorted list) of d_agg[recv e] (*) [pre_e > 0]
 __global__ void __launch_bounds__(TA_THREADS) effect_bwd_send_kernel(const int32_t* __restrict__ send_ptr, const int32_t* __restrict__ send_perm,
                                                                      const int32_t* __restrict__ recv, int64_t rows, int64_t E_cap,
-                                                                     const float4* __restrict__ C, const float4* __restrict__ Qr,
-                                                                     const float4* __restrict__ Qs, const float4* __restrict__ d_agg,
+                                                                     const float* __restrict__ C, const float* __restrict__ Qr,
+                                                                     const float* __restrict__ Qs, bool blocked, const float4* __restrict__ d_agg,
                                                                      float4* __restrict__ dQs) {
   const int slot = threadIdx.x / (FP / 4), j = threadIdx.x - slot * (FP / 4);
   const int64_t s = (int64_t)blockIdx.x * TA_NODES + slot;
   if (s >= rows) return;
   const int64_t beg = send_ptr[s], end = min((int64_t)send_ptr[s + 1], E_cap);
-  const float4 qs = Qs[s * (FP / 4) + j];
+  const float4 qs = feat4(Qs, s, j, blocked);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t i = beg; i < end; ++i) {
     const int e = send_perm[i];
     const int r = recv[e];
-    const float4 p = pre3(C[(int64_t)e * (FP / 4) + j], Qr[(int64_t)r * (FP / 4) + j], qs);
+    const float4 p = pre3(feat4(C, e, j, blocked), feat4(Qr, r, j, blocked), qs);
     const float4 da = d_agg[(int64_t)r * (FP / 4) + j];
     acc.x += p.x > 0.f ? da.x : 0.f; acc.y += p.y > 0.f ? da.y : 0.f; acc.z += p.z > 0.f ? da.z : 0.f; acc.w += p.w > 0.f ? da.w : 0.f;
   }
@@ -439,34 +448,51 @@ size_t tc_blob_bytes(size_t base_bytes);
 struct TrainSaved {
   float *nfeat, *p_in, *rel_in, *h1, *h2, *penc, *g1, *g2, *renc, *A, *C, *u1, *u2, *motion;
   float *P[17], *agg[16], *Qr[16], *Qs[16];   // P[0] aliases penc
+  // tensor-core forward (default): C, Qr[k], Qs[k] hold the blocked layout of tc_chain.cuh (only the relation kernels read them);
+  // the chains' own streams follow
+  float *A_blk, *P_blk, *P0_blk, *S0, *rowmaxP, *rowmaxA, *rowmaxP0, *agg_split, *agg_max;
+  int32_t* agg_exp;
 };
+// floats of a [n][FP] feature buffer that may hold either layout
+static size_t feat_floats(int64_t n) {
+  const size_t rm = (size_t)n * FP, bl = (size_t)tc::blk_rows(n) * tc::BLK_COLS;
+  return rm > bl ? rm : bl;
+}
 static size_t saved_carve(void* base, int64_t rows, int64_t E, int K, TrainSaved* out) {
   Carver c(base);
   TrainSaved s;
   s.nfeat = c.take<float>(rows * NFEAT); s.p_in = c.take<float>(rows * D_NODE_IN); s.rel_in = c.take<float>(E * D_REL_IN);
   s.h1 = c.take<float>(rows * FP); s.h2 = c.take<float>(rows * FP); s.penc = c.take<float>(rows * FP);
   s.g1 = c.take<float>(E * FP); s.g2 = c.take<float>(E * FP); s.renc = c.take<float>(E * FP);
-  s.A = c.take<float>(rows * FP); s.C = c.take<float>(E * FP);
+  s.A = c.take<float>(rows * FP); s.C = c.take<float>(feat_floats(E));
   s.u1 = c.take<float>(rows * FP); s.u2 = c.take<float>(rows * FP); s.motion = c.take<float>(rows * 3);
   s.P[0] = s.penc;
   for (int k = 0; k < K; ++k) {
     s.P[k + 1] = c.take<float>(rows * FP); s.agg[k] = c.take<float>(rows * FP);
-    s.Qr[k] = c.take<float>(rows * FP); s.Qs[k] = c.take<float>(rows * FP);
+    s.Qr[k] = c.take<float>(feat_floats(rows)); s.Qs[k] = c.take<float>(feat_floats(rows));
   }
+  const size_t blk = (size_t)tc::blk_rows(rows) * tc::BLK_COLS;
+  s.A_blk = c.take<float>(blk); s.P_blk = c.take<float>(blk); s.P0_blk = c.take<float>(blk); s.S0 = c.take<float>(blk);
+  s.rowmaxP = c.take<float>(rows); s.rowmaxA = c.take<float>(rows); s.rowmaxP0 = c.take<float>(rows);
+  s.agg_split = c.take<float>(blk); s.agg_max = c.take<float>(rows); s.agg_exp = c.take<int32_t>(rows);
   if (out) *out = s;
   return align_up(c.off, 256);
 }
 
 struct TrainScratch {
-  float *dU, *dV, *dP, *dPn, *dA, *dAgg, *dQr, *dQs, *dC, *dE, *dRel, *dm, *part;
+  float *dU, *dV, *dH2, *dH1, *dP, *dPn, *dA, *dAgg, *dQr, *dQs, *dC, *dE, *dG2, *dG1, *dRel, *dm, *part;
 };
+static int wgrad_max_ctas() { return num_sms() + tc::WG_MAX_JOBS; }
 static size_t scratch_carve(void* base, int64_t rows, int64_t E, TrainScratch* out) {
   Carver c(base);
   TrainScratch s;
-  s.dU = c.take<float>(rows * FP); s.dV = c.take<float>(rows * FP); s.dP = c.take<float>(rows * FP); s.dPn = c.take<float>(rows * FP);
+  s.dU = c.take<float>(rows * FP); s.dV = c.take<float>(rows * FP); s.dH2 = c.take<float>(rows * FP); s.dH1 = c.take<float>(rows * FP);
+  s.dP = c.take<float>(rows * FP); s.dPn = c.take<float>(rows * FP);
   s.dA = c.take<float>(rows * FP); s.dAgg = c.take<float>(rows * FP); s.dQr = c.take<float>(rows * FP); s.dQs = c.take<float>(rows * FP);
-  s.dC = c.take<float>(E * FP); s.dE = c.take<float>(E * FP); s.dRel = c.take<float>(E * D_REL_IN); s.dm = c.take<float>(rows * 4);
-  s.part = c.take<float>((size_t)num_sms() * (FP * FP + FP));
+  s.dC = c.take<float>(E * FP); s.dE = c.take<float>(E * FP); s.dG2 = c.take<float>(E * FP); s.dG1 = c.take<float>(E * FP);
+  s.dRel = c.take<float>(E * D_REL_IN); s.dm = c.take<float>(rows * 4);
+  const size_t part_simt = (size_t)num_sms() * (FP * FP + FP), part_tc = tc_wgrad_part_floats(wgrad_max_ctas());
+  s.part = c.take<float>(part_simt > part_tc ? part_simt : part_tc);
   if (out) *out = s;
   return align_up(c.off, 256);
 }
@@ -504,16 +530,70 @@ static int lin(cudaStream_t st, const float* X, int ldx, const float* mask, int 
 // `layer` names the fp16 image of the same matrix inside `packed`.
 int tc_lin(cudaStream_t st, const void* packed, size_t base_bytes, int layer, const float* X, int ldx, const float* mask, int ldm,
            const float* bias, const float* add1, const float* add2, float* Y, int ldy, int64_t M, bool relu, bool accumulate, int n_store);
-static bool train_use_tc() {
-  static const bool v = [] { const char* e = getenv("AGX_TRAIN_PRECISION"); return e && !strcmp(e, "tc"); }();
+static int train_use_tc() {   // 0 fp32, 1 every 160x160 layer, 2 forward layers only, 3 backward (dgrad) layers only
+  static const int v = [] {
+    const char* e = getenv("AGX_TRAIN_PRECISION");
+    if (!e) return 0;
+    return !strcmp(e, "tc") ? 1 : !strcmp(e, "tc_fwd") ? 2 : !strcmp(e, "tc_bwd") ? 3 : !strcmp(e, "tc_one") ? 4 : 0;
+  }();
+  return v;
+}
+// forward of the training step: the tensor-core chains of the inference path with their training copies (default), or the
+// layer-by-layer fp32 FFMA kernels of this file (AGX_TRAIN_FORWARD=fp32)
+static bool train_forward_tc() {
+  static const bool v = [] { const char* e = getenv("AGX_TRAIN_FORWARD"); return !(e && !strcmp(e, "fp32")); }();
+  return v;
+}
+static int train_tc_layer() {
+  static const int v = [] { const char* e = getenv("AGX_TRAIN_TC_LAYER"); return e ? atoi(e) : -1; }();
   return v;
 }
 static int lin160(cudaStream_t st, const float* packed, int layer, const float* X, int ldx, const float* mask, int ldm, const float* Wt,
                   const float* bias, const float* add1, const float* add2, float* Y, int ldy, int64_t M, bool relu, bool accumulate,
                   int n_store = FP) {
-  if (train_use_tc())
+  const int mode = train_use_tc();
+  if (mode == 1 || (mode == 2 && layer < tc::TT_PENC2) || (mode == 3 && layer >= tc::TT_PENC2) || (mode == 4 && layer == train_tc_layer()))
     return tc_lin(st, packed, packed_layout().total * sizeof(float), layer, X, ldx, mask, ldm, bias, add1, add2, Y, ldy, M, relu, accumulate, n_store);
   return lin<FP>(st, X, ldx, mask, ldm, Wt, bias, add1, add2, Y, ldy, M, relu, accumulate, n_store);
+}
+
+// Weight gradients are collected into batches: on the tensor cores (default) a batch is one launch of tc_wgrad.cu's kernel plus
+// its reduction; with AGX_TRAIN_PRECISION=fp32 every job runs at once on the FFMA kernel above.
+static bool train_wgrad_tc() {
+  static const bool v = [] { const char* e = getenv("AGX_TRAIN_WGRAD"); return !(e && !strcmp(e, "fp32")); }();
+  return v;
+}
+static int wgrad(cudaStream_t st, const float* dY, const float* mask, const float* X, int ldx, int kx, int64_t M, float* part, int F, int K,
+                 int ld, int col0, float* dW, float* db);
+struct WgradBatch {
+  tc::WgArgs a;
+  cudaStream_t st;
+  float* part;
+  explicit WgradBatch(cudaStream_t s, float* p) : st(s), part(p) { a.njobs = 0; a.part = nullptr; }
+  int add(const float* dY, const float* mask, const float* X, int ldx, int kx, int64_t M, int F, int K, int ld, int col0, float* dW, float* db,
+          const int32_t* m_limit = nullptr) {
+    if (M <= 0 || !dW) return AGX_OK;
+    if (!train_wgrad_tc()) return wgrad(st, dY, mask, X, ldx, kx, M, part, F, K, ld, col0, dW, db);
+    if (a.njobs == tc::WG_MAX_JOBS) { if (int rc = flush()) return rc; }
+    tc::WgJob& j = a.job[a.njobs++];
+    j.dY = dY; j.mask = mask; j.X = X; j.dW = dW; j.db = db; j.M = M; j.m_limit = m_limit; j.ldx = ldx; j.kx = kx;
+    j.npad = kx >= FP ? FP : (kx + 1 + 15) / 16 * 16;
+    j.bias_col = db ? 1 : 0;
+    j.ld = ld; j.col0 = col0; j.F = F; j.K = K; j.chain_head = 1; j.next = -1;
+    j.cta0 = j.nctas = j.stages_per_cta = 0;
+    return AGX_OK;
+  }
+  int flush() {
+    if (a.njobs == 0) return AGX_OK;
+    const int rc = tc_wgrad_batch(st, a, part, wgrad_max_ctas());
+    a.njobs = 0;
+    return rc;
+  }
+};
+
+static int wb_hold(WgradBatch& wb, const float* dY, const float* mask, const float* X, int ldx, int kx, int64_t M, int F, int K, int ld,
+                   int col0, float* dW, float* db, const int32_t* m_limit = nullptr) {
+  return wb.add(dY, mask, X, ldx, kx, M, F, K, ld, col0, dW, db, m_limit);
 }
 
 // dW (reference layout, += ) and optional db from dY (masked by act > 0) and the layer input X
@@ -583,6 +663,25 @@ int agx_forward_train(const AgxModelDims* dims, const void* packed_weights, cons
   AGX_TRY(train_attrs());
   const PackedLayout L = packed_layout();
   const float* W = static_cast<const float*>(packed_weights);
+  if (train_forward_tc()) {
+    // the inference chains (tc_forward.cu, three fp16 products per term, fp32 C), each epilogue also leaving the fp32 row the
+    // backward reads; per propagation step its own Qr / Qs (blocked) and P / agg (row-major) buffers
+    const size_t base = L.total * sizeof(float);
+    TcTrainSave sv{s.p_in, s.h1, s.h2, s.penc, s.rel_in, s.g1, s.g2, s.renc, nullptr, nullptr, s.u1, s.u2};
+    TcFwdBuffers tb{s.nfeat, s.P_blk, s.A_blk, nullptr, nullptr, s.agg_split, s.C, s.rowmaxP, s.rowmaxA, s.agg_exp, s.agg_max,
+                    s.P0_blk, s.Qr[0], s.Qs[0], s.rowmaxP0, s.S0, &sv};
+    AGX_TRY(tc_node_encoder(g, W, L, base, tb, st));
+    if (g->E_cap > 0) AGX_TRY(tc_edge_encoder(g, W, L, base, tb, false, st));
+    for (int k = 0; k < K; ++k) {
+      sv.agg_f32 = s.agg[k];
+      sv.P_next = s.P[k + 1];
+      tb.Qr = s.Qr[k]; tb.Qs = s.Qs[k];                       // read by the aggregate of step k > 0
+      AGX_TRY(tc_edge_aggregate(g, tb, false, k == 0, st));
+      if (k + 1 < K) { tb.Qr = s.Qr[k + 1]; tb.Qs = s.Qs[k + 1]; }   // written by the update of step k
+      AGX_TRY(tc_node_update(g, W, L, base, tb, k == 0, k + 1 == K, pred_pos, pos_stride_b, pred_motion, st));
+    }
+    return AGX_OK;
+  }
   node_prep_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(g->state, g->attrs, g->action, g->p_instance, g->physics, g->B, g->N, g->n_p,
                                                                    s.nfeat, s.p_in);
   AGX_LAUNCH_CHECK();
@@ -635,25 +734,30 @@ int agx_backward(const AgxModelDims* dims, const void* packed_weights, const Agx
   const float* W = static_cast<const float*>(packed_weights);
   float* const* gw = grads->weight;
   float* const* gb = grads->bias;
+  const bool fwd_tc = train_forward_tc();   // layout of the saved C / Qr / Qs
   AGX_CUDA_OK(cudaMemsetAsync(t.dA, 0, rows * FP * sizeof(float), st));
   AGX_CUDA_OK(cudaMemsetAsync(t.dC, 0, E * FP * sizeof(float), st));
 
   // ---- head
+  WgradBatch wb(st, t.part);
   head_bwd_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(d_pred_pos, d_pred_motion, pred_motion, W + L.pred2_w, g->B, g->N, g->n_p, t.dm, t.dU);
   AGX_LAUNCH_CHECK();
   if (gw[AGX_W_PRED2]) {
     head_wgrad_kernel<<<dim3(F + 1, 3), 256, 0, st>>>(t.dm, s.u2, rows, F, gw[AGX_W_PRED2], gb[AGX_W_PRED2]);
     AGX_LAUNCH_CHECK();
   }
-  AGX_TRY(wgrad(st, t.dU, s.u2, s.u1, FP, FP, rows, t.part, F, F, F, 0, gw[AGX_W_PRED1], gb[AGX_W_PRED1]));
+  // weight-gradient jobs whose operands stay untouched until the end of the backward (dU, dV here; the encoder gradients below)
+  // wait for the final batch; the per-step ones are flushed before their operands are overwritten
+  AGX_TRY(wb_hold(wb, t.dU, s.u2, s.u1, FP, FP, rows, F, F, F, 0, gw[AGX_W_PRED1], gb[AGX_W_PRED1]));
   AGX_TRY(lin160(st, W, tc::TT_PRED1, t.dU, FP, s.u2, FP, W + T.pred1, nullptr, nullptr, nullptr, t.dV, FP, rows, false, false));          // dU1
-  AGX_TRY(wgrad(st, t.dV, s.u1, s.P[K], FP, FP, rows, t.part, F, F, F, 0, gw[AGX_W_PRED0], gb[AGX_W_PRED0]));
+  AGX_TRY(wb_hold(wb, t.dV, s.u1, s.P[K], FP, FP, rows, F, F, F, 0, gw[AGX_W_PRED0], gb[AGX_W_PRED0]));
   AGX_TRY(lin160(st, W, tc::TT_PRED0, t.dV, FP, s.u1, FP, W + T.pred0, nullptr, nullptr, nullptr, t.dP, FP, rows, false, false));          // dP_K
 
   // ---- propagation steps, last to first
   for (int k = K - 1; k >= 0; --k) {
     const float* act = s.P[k + 1];   // ReLU output of this step
-    AGX_TRY(wgrad(st, t.dP, act, s.agg[k], FP, FP, rows, t.part, F, F, 2 * F, F, gw[AGX_W_PPROP], nullptr));
+    WgradBatch ws(st, t.part);
+    AGX_TRY(ws.add(t.dP, act, s.agg[k], FP, FP, rows, F, F, 2 * F, F, gw[AGX_W_PPROP], nullptr));
     mask_rows_kernel<<<(unsigned)((rows * FP + 255) / 256), 256, 0, st>>>(t.dP, act, rows * FP);                              // dP <- d pre_n
     AGX_LAUNCH_CHECK();
     add_rows_kernel<<<(unsigned)((rows * FP + 255) / 256), 256, 0, st>>>(t.dA, t.dP, rows * FP);
@@ -661,40 +765,43 @@ int agx_backward(const AgxModelDims* dims, const void* packed_weights, const Agx
     AGX_TRY(lin160(st, W, tc::TT_PP_AGG, t.dP, FP, nullptr, 0, W + T.pp_agg, nullptr, nullptr, nullptr, t.dAgg, FP, rows, false, false));
     if (g->E_cap > 0) {
       effect_bwd_recv_kernel<<<(unsigned)((rows + TA_NODES - 1) / TA_NODES), TA_THREADS, 0, st>>>(
-          g->row_ptr, g->send, rows, g->N, g->E_cap, reinterpret_cast<const float4*>(s.C), reinterpret_cast<const float4*>(s.Qr[k]),
-          reinterpret_cast<const float4*>(s.Qs[k]), reinterpret_cast<const float4*>(t.dAgg), reinterpret_cast<float4*>(t.dC),
-          reinterpret_cast<float4*>(t.dQr));
+          g->row_ptr, g->send, rows, g->N, g->E_cap, s.C, s.Qr[k], s.Qs[k], fwd_tc, reinterpret_cast<const float4*>(t.dAgg),
+          reinterpret_cast<float4*>(t.dC), reinterpret_cast<float4*>(t.dQr));
       AGX_LAUNCH_CHECK();
       effect_bwd_send_kernel<<<(unsigned)((rows + TA_NODES - 1) / TA_NODES), TA_THREADS, 0, st>>>(
-          send_ptr, send_perm, g->recv, rows, g->E_cap, reinterpret_cast<const float4*>(s.C), reinterpret_cast<const float4*>(s.Qr[k]),
-          reinterpret_cast<const float4*>(s.Qs[k]), reinterpret_cast<const float4*>(t.dAgg), reinterpret_cast<float4*>(t.dQs));
+          send_ptr, send_perm, g->recv, rows, g->E_cap, s.C, s.Qr[k], s.Qs[k], fwd_tc, reinterpret_cast<const float4*>(t.dAgg),
+          reinterpret_cast<float4*>(t.dQs));
       AGX_LAUNCH_CHECK();
-      AGX_TRY(wgrad(st, t.dQr, nullptr, s.P[k], FP, FP, rows, t.part, F, F, 3 * F, F, gw[AGX_W_RPROP], nullptr));
-      AGX_TRY(wgrad(st, t.dQs, nullptr, s.P[k], FP, FP, rows, t.part, F, F, 3 * F, 2 * F, gw[AGX_W_RPROP], nullptr));
+      AGX_TRY(ws.add(t.dQr, nullptr, s.P[k], FP, FP, rows, F, F, 3 * F, F, gw[AGX_W_RPROP], nullptr));
+      AGX_TRY(ws.add(t.dQs, nullptr, s.P[k], FP, FP, rows, F, F, 3 * F, 2 * F, gw[AGX_W_RPROP], nullptr));
+    }
+    AGX_TRY(ws.flush());   // before dP is accumulated into and dQr / dQs are rewritten
+    if (g->E_cap > 0) {
       // dP_k = d pre_n (residual) + dQr*W_recv + dQs*W_send   (accumulated in place: dP already holds d pre_n)
       AGX_TRY(lin160(st, W, tc::TT_RP_RECV, t.dQr, FP, nullptr, 0, W + T.rp_recv, nullptr, nullptr, nullptr, t.dP, FP, rows, false, true));
       AGX_TRY(lin160(st, W, tc::TT_RP_SEND, t.dQs, FP, nullptr, 0, W + T.rp_send, nullptr, nullptr, nullptr, t.dP, FP, rows, false, true));
     }
   }
   // ---- encoders: d penc = dP_0 + dA * W_enc
-  AGX_TRY(wgrad(st, t.dA, nullptr, s.penc, FP, FP, rows, t.part, F, F, 2 * F, 0, gw[AGX_W_PPROP], gb[AGX_W_PPROP]));
+  AGX_TRY(wb_hold(wb, t.dA, nullptr, s.penc, FP, FP, rows, F, F, 2 * F, 0, gw[AGX_W_PPROP], gb[AGX_W_PPROP]));
   AGX_TRY(lin160(st, W, tc::TT_PP_ENC, t.dA, FP, nullptr, 0, W + T.pp_enc, nullptr, nullptr, nullptr, t.dP, FP, rows, false, true));
-  AGX_TRY(wgrad(st, t.dP, s.penc, s.h2, FP, FP, rows, t.part, F, F, F, 0, gw[AGX_W_PENC4], gb[AGX_W_PENC4]));
-  AGX_TRY(lin160(st, W, tc::TT_PENC4, t.dP, FP, s.penc, FP, W + T.penc4, nullptr, nullptr, nullptr, t.dU, FP, rows, false, false));        // dH2
-  AGX_TRY(wgrad(st, t.dU, s.h2, s.h1, FP, FP, rows, t.part, F, F, F, 0, gw[AGX_W_PENC2], gb[AGX_W_PENC2]));
-  AGX_TRY(lin160(st, W, tc::TT_PENC2, t.dU, FP, s.h2, FP, W + T.penc2, nullptr, nullptr, nullptr, t.dV, FP, rows, false, false));          // dH1
-  AGX_TRY(wgrad(st, t.dV, s.h1, s.p_in, D_NODE_IN, D_NODE_IN, rows, t.part, F, d_node, d_node, 0, gw[AGX_W_PENC0], gb[AGX_W_PENC0]));
+  AGX_TRY(wb_hold(wb, t.dP, s.penc, s.h2, FP, FP, rows, F, F, F, 0, gw[AGX_W_PENC4], gb[AGX_W_PENC4]));
+  AGX_TRY(lin160(st, W, tc::TT_PENC4, t.dP, FP, s.penc, FP, W + T.penc4, nullptr, nullptr, nullptr, t.dH2, FP, rows, false, false));
+  AGX_TRY(wb_hold(wb, t.dH2, s.h2, s.h1, FP, FP, rows, F, F, F, 0, gw[AGX_W_PENC2], gb[AGX_W_PENC2]));
+  AGX_TRY(lin160(st, W, tc::TT_PENC2, t.dH2, FP, s.h2, FP, W + T.penc2, nullptr, nullptr, nullptr, t.dH1, FP, rows, false, false));
+  AGX_TRY(wb_hold(wb, t.dH1, s.h1, s.p_in, D_NODE_IN, D_NODE_IN, rows, F, d_node, d_node, 0, gw[AGX_W_PENC0], gb[AGX_W_PENC0]));
   if (g->E_cap > 0) {
-    AGX_TRY(wgrad(st, t.dC, nullptr, s.renc, FP, FP, E, t.part, F, F, 3 * F, 0, gw[AGX_W_RPROP], gb[AGX_W_RPROP]));
+    AGX_TRY(wb_hold(wb, t.dC, nullptr, s.renc, FP, FP, E, F, F, 3 * F, 0, gw[AGX_W_RPROP], gb[AGX_W_RPROP], g->row_ptr + rows));
     AGX_TRY(lin160(st, W, tc::TT_RP_REL, t.dC, FP, nullptr, 0, W + T.rp_rel, nullptr, nullptr, nullptr, t.dE, FP, E, false, false));         // dRenc
-    AGX_TRY(wgrad(st, t.dE, s.renc, s.g2, FP, FP, E, t.part, F, F, F, 0, gw[AGX_W_RENC4], gb[AGX_W_RENC4]));
-    AGX_TRY(lin160(st, W, tc::TT_RENC4, t.dE, FP, s.renc, FP, W + T.renc4, nullptr, nullptr, nullptr, t.dC, FP, E, false, false));          // dG2 (dC is free now)
-    AGX_TRY(wgrad(st, t.dC, s.g2, s.g1, FP, FP, E, t.part, F, F, F, 0, gw[AGX_W_RENC2], gb[AGX_W_RENC2]));
-    AGX_TRY(lin160(st, W, tc::TT_RENC2, t.dC, FP, s.g2, FP, W + T.renc2, nullptr, nullptr, nullptr, t.dE, FP, E, false, false));            // dG1
-    AGX_TRY(wgrad(st, t.dE, s.g1, s.rel_in, D_REL_IN, D_REL_IN, E, t.part, F, d_rel, d_rel, 0, gw[AGX_W_RENC0], gb[AGX_W_RENC0]));
+    AGX_TRY(wb_hold(wb, t.dE, s.renc, s.g2, FP, FP, E, F, F, F, 0, gw[AGX_W_RENC4], gb[AGX_W_RENC4], g->row_ptr + rows));
+    AGX_TRY(lin160(st, W, tc::TT_RENC4, t.dE, FP, s.renc, FP, W + T.renc4, nullptr, nullptr, nullptr, t.dG2, FP, E, false, false));
+    AGX_TRY(wb_hold(wb, t.dG2, s.g2, s.g1, FP, FP, E, F, F, F, 0, gw[AGX_W_RENC2], gb[AGX_W_RENC2], g->row_ptr + rows));
+    AGX_TRY(lin160(st, W, tc::TT_RENC2, t.dG2, FP, s.g2, FP, W + T.renc2, nullptr, nullptr, nullptr, t.dG1, FP, E, false, false));
+    AGX_TRY(wb_hold(wb, t.dG1, s.g1, s.rel_in, D_REL_IN, D_REL_IN, E, F, d_rel, d_rel, 0, gw[AGX_W_RENC0], gb[AGX_W_RENC0], g->row_ptr + rows));
     if (d_state)
-      AGX_TRY(lin160(st, W, tc::TT_RENC0, t.dE, FP, s.g1, FP, W + T.renc0, nullptr, nullptr, nullptr, t.dRel, D_REL_IN, E, false, false, D_REL_IN));   // d rel_in
+      AGX_TRY(lin160(st, W, tc::TT_RENC0, t.dG1, FP, s.g1, FP, W + T.renc0, nullptr, nullptr, nullptr, t.dRel, D_REL_IN, E, false, false, D_REL_IN));   // d rel_in
   }
+  AGX_TRY(wb.flush());
   if (d_state) {
     if (g->E_cap == 0) AGX_CUDA_OK(cudaMemsetAsync(t.dRel, 0, sizeof(float), st));
     state_bwd_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(g->row_ptr, g->E_cap > 0 ? send_ptr : g->row_ptr, send_perm, g->E_cap, t.dRel,
