@@ -39,7 +39,7 @@ EXPORTS = [
     "agx_forward_workspace_bytes", "agx_forward",
     "agx_rollout_workspace_bytes", "agx_rollout",
     "agx_profile_enable", "agx_profile_read", "agx_kind_name",
-    "agx_train_saved_bytes", "agx_train_scratch_bytes", "agx_forward_train", "agx_backward", "agx_adam_step",
+    "agx_train_saved_bytes", "agx_train_scratch_bytes", "agx_train_saved_offsets", "agx_forward_train", "agx_backward", "agx_adam_step",
 ]
 AGX_NUM_KINDS = 12
 
@@ -101,6 +101,7 @@ def _load() -> C.CDLL:
         "agx_rollout": (C.c_int, [P(AgxModelDims), vp, P(AgxRolloutIn), vp, vp, vp, i32, vp, sz, vp]),
         "agx_train_saved_bytes": (sz, [P(AgxModelDims), i32, i32, i64]),
         "agx_train_scratch_bytes": (sz, [P(AgxModelDims), i32, i32, i64]),
+        "agx_train_saved_offsets": (C.c_int, [P(AgxModelDims), i32, i32, i64, P(i64), i32]),
         "agx_forward_train": (C.c_int, [P(AgxModelDims), vp, P(AgxGraphIn), vp, i64, vp, vp, sz, vp]),
         "agx_backward": (C.c_int, [P(AgxModelDims), vp, P(AgxGraphIn), vp, vp, vp, vp, vp, vp, P(AgxWeightGrads), vp, vp, sz, vp]),
         "agx_adam_step": (C.c_int, [vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, vp, vp]),

@@ -486,6 +486,8 @@ __device__ __forceinline__ void epi_layer_plain(const Shared& sh, EpiCtx& cx, fl
 // General layer whose result becomes the slot's next A.  per chunk: v = acc * unscale ; extra(c, col0, v) ; relu (RELU) ;
 // side(c, col0, v) [e.g. store the fp32 row piece; it may also replace v: what it leaves is what gets split] ; split with `scale`.
 // Returns the thread's partial row maximum of |v| (taken before side).
+// (RELU = false is the backward use: no constant-1 column either -- the transposed images have no bias column, and a 1 times the
+// large scale of a small gradient row would overflow fp16.)
 template <bool LO = true, bool RELU = true, class Extra, class Side>
 __device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, float unscale, float scale, Extra extra, Side side) {
   float mx = 0.f;
@@ -533,7 +535,7 @@ __device__ __forceinline__ float epi_layer_to_a(const Shared& sh, EpiCtx& cx, fl
 #pragma unroll
     for (int i = 0; i < HW; ++i) { if (RELU) v[i] = fmaxf(v[i], 0.f); mx = fmaxf(mx, fabsf(v[i])); }
     side(c, col0, v);
-    if (owns_one(cx, c)) v[ONE_COL % HW] = 1.f;   // after the fp32 side store: only the tensor-memory copy carries the 1
+    if (RELU && owns_one(cx, c)) v[ONE_COL % HW] = 1.f;   // after the fp32 side store: only the tensor-memory copy carries the 1
     epi_store_a<LO>(cx, c, v, scale);
   }
   AGX_STAMP_EPI(cx, 45);

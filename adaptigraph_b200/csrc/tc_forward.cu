@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "tc_chain.cuh"
 #include "tc_forward.cuh"
+#include "tc_backward.cuh"
 
 namespace agx {
 namespace tc {
@@ -1330,6 +1331,8 @@ int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL
 }
 
 }  // namespace agx
+
+#include "tc_backward.inl"
 
 #ifdef AGX_TC_TIMELINE
 // Debug-only entry (tools/tc_timeline.py builds a separate library with -DAGX_TC_TIMELINE): points CTA 0's MMA thread at a

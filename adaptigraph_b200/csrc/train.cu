@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "mlp_simt.cuh"
 #include "tc_chain.cuh"
+#include "tc_backward.cuh"
 #include "tc_forward.cuh"
 #include "tc_wgrad.cuh"
 
@@ -262,23 +263,33 @@ __device__ __forceinline__ float4 feat4(const float* base, int64_t row, int j, b
 __global__ void __launch_bounds__(TA_THREADS) effect_bwd_recv_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send,
                                                                      int64_t rows, int N, int64_t E_cap, const float* __restrict__ C,
                                                                      const float* __restrict__ Qr, const float* __restrict__ Qs, bool blocked,
-                                                                     const float4* __restrict__ d_agg, float4* __restrict__ dC,
-                                                                     float4* __restrict__ dQr) {
+                                                                     const float4* __restrict__ d_agg, float4* __restrict__ dC, bool first,
+                                                                     float4* __restrict__ dQr, float* __restrict__ qr_max) {
+  __shared__ int smx[TA_NODES];   // per-row max |dQr| (bit pattern of a non-negative float orders like the float)
+  if (threadIdx.x < TA_NODES) smx[threadIdx.x] = 0;
+  __syncthreads();
   const int slot = threadIdx.x / (FP / 4), j = threadIdx.x - slot * (FP / 4);
   const int64_t r = (int64_t)blockIdx.x * TA_NODES + slot;
-  if (r >= rows) return;
-  const int64_t beg = row_ptr[r], end = min((int64_t)row_ptr[r + 1], E_cap), gb = (r / N) * N;
-  const float4 qr = feat4(Qr, r, j, blocked), da = d_agg[r * (FP / 4) + j];
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t e = beg; e < end; ++e) {
-    const float4 p = pre3(feat4(C, e, j, blocked), qr, feat4(Qs, gb + send[e], j, blocked));
-    const float4 d = make_float4(p.x > 0.f ? da.x : 0.f, p.y > 0.f ? da.y : 0.f, p.z > 0.f ? da.z : 0.f, p.w > 0.f ? da.w : 0.f);
-    float4 c = dC[e * (FP / 4) + j];
-    c.x += d.x; c.y += d.y; c.z += d.z; c.w += d.w;
-    dC[e * (FP / 4) + j] = c;
-    acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+  if (r < rows) {
+    const int64_t beg = row_ptr[r], end = min((int64_t)row_ptr[r + 1], E_cap), gb = (r / N) * N;
+    const float4 qr = feat4(Qr, r, j, blocked), da = d_agg[r * (FP / 4) + j];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t e = beg; e < end; ++e) {
+      const float4 p = pre3(feat4(C, e, j, blocked), qr, feat4(Qs, gb + send[e], j, blocked));
+      const float4 d = make_float4(p.x > 0.f ? da.x : 0.f, p.y > 0.f ? da.y : 0.f, p.z > 0.f ? da.z : 0.f, p.w > 0.f ? da.w : 0.f);
+      float4 c = d;
+      if (!first) {   // the first propagation step visited (the last of the forward) initialises dC
+        c = dC[e * (FP / 4) + j];
+        c.x += d.x; c.y += d.y; c.z += d.z; c.w += d.w;
+      }
+      dC[e * (FP / 4) + j] = c;
+      acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+    }
+    dQr[r * (FP / 4) + j] = acc;
+    if (qr_max) atomicMax(&smx[slot], __float_as_int(fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w)))));
   }
-  dQr[r * (FP / 4) + j] = acc;
+  __syncthreads();
+  if (qr_max && r < rows && j == 0) qr_max[r] = __int_as_float(smx[slot]);
 }
 
 // sender side: dQs[s] = sum over the relations sent by s (sender-sorted list) of d_agg[recv e] (*) [pre_e > 0]
@@ -286,21 +297,28 @@ __global__ void __launch_bounds__(TA_THREADS) effect_bwd_send_kernel(const int32
                                                                      const int32_t* __restrict__ recv, int64_t rows, int64_t E_cap,
                                                                      const float* __restrict__ C, const float* __restrict__ Qr,
                                                                      const float* __restrict__ Qs, bool blocked, const float4* __restrict__ d_agg,
-                                                                     float4* __restrict__ dQs) {
+                                                                     float4* __restrict__ dQs, float* __restrict__ qs_max) {
+  __shared__ int smx[TA_NODES];
+  if (threadIdx.x < TA_NODES) smx[threadIdx.x] = 0;
+  __syncthreads();
   const int slot = threadIdx.x / (FP / 4), j = threadIdx.x - slot * (FP / 4);
   const int64_t s = (int64_t)blockIdx.x * TA_NODES + slot;
-  if (s >= rows) return;
-  const int64_t beg = send_ptr[s], end = min((int64_t)send_ptr[s + 1], E_cap);
-  const float4 qs = feat4(Qs, s, j, blocked);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t i = beg; i < end; ++i) {
-    const int e = send_perm[i];
-    const int r = recv[e];
-    const float4 p = pre3(feat4(C, e, j, blocked), feat4(Qr, r, j, blocked), qs);
-    const float4 da = d_agg[(int64_t)r * (FP / 4) + j];
-    acc.x += p.x > 0.f ? da.x : 0.f; acc.y += p.y > 0.f ? da.y : 0.f; acc.z += p.z > 0.f ? da.z : 0.f; acc.w += p.w > 0.f ? da.w : 0.f;
+  if (s < rows) {
+    const int64_t beg = send_ptr[s], end = min((int64_t)send_ptr[s + 1], E_cap);
+    const float4 qs = feat4(Qs, s, j, blocked);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = beg; i < end; ++i) {
+      const int e = send_perm[i];
+      const int r = recv[e];
+      const float4 p = pre3(feat4(C, e, j, blocked), feat4(Qr, r, j, blocked), qs);
+      const float4 da = d_agg[(int64_t)r * (FP / 4) + j];
+      acc.x += p.x > 0.f ? da.x : 0.f; acc.y += p.y > 0.f ? da.y : 0.f; acc.z += p.z > 0.f ? da.z : 0.f; acc.w += p.w > 0.f ? da.w : 0.f;
+    }
+    dQs[s * (FP / 4) + j] = acc;
+    if (qs_max) atomicMax(&smx[slot], __float_as_int(fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w)))));
   }
-  dQs[s * (FP / 4) + j] = acc;
+  __syncthreads();
+  if (qs_max && s < rows && j == 0) qs_max[s] = __int_as_float(smx[slot]);
 }
 
 // ------------------------------------------------------------------------------------ head and state gradients
@@ -481,6 +499,7 @@ static size_t saved_carve(void* base, int64_t rows, int64_t E, int K, TrainSaved
 
 struct TrainScratch {
   float *dU, *dV, *dH2, *dH1, *dP, *dPn, *dA, *dAgg, *dQr, *dQs, *dC, *dE, *dG2, *dG1, *dRel, *dm, *part;
+  float *preMax, *aBound, *aggMax, *cBound, *qrMax, *qsMax;   // per-row magnitude bounds of the tensor-core backward
 };
 static int wgrad_max_ctas() { return num_sms() + tc::WG_MAX_JOBS; }
 static size_t scratch_carve(void* base, int64_t rows, int64_t E, TrainScratch* out) {
@@ -493,6 +512,8 @@ static size_t scratch_carve(void* base, int64_t rows, int64_t E, TrainScratch* o
   s.dRel = c.take<float>(E * D_REL_IN); s.dm = c.take<float>(rows * 4);
   const size_t part_simt = (size_t)num_sms() * (FP * FP + FP), part_tc = tc_wgrad_part_floats(wgrad_max_ctas());
   s.part = c.take<float>(part_simt > part_tc ? part_simt : part_tc);
+  s.preMax = c.take<float>(rows); s.aBound = c.take<float>(rows); s.aggMax = c.take<float>(rows); s.cBound = c.take<float>(rows);
+  s.qrMax = c.take<float>(rows); s.qsMax = c.take<float>(rows);
   if (out) *out = s;
   return align_up(c.off, 256);
 }
@@ -542,6 +563,11 @@ static int train_use_tc() {   // 0 fp32, 1 every 160x160 layer, 2 forward layers
 // layer-by-layer fp32 FFMA kernels of this file (AGX_TRAIN_FORWARD=fp32)
 static bool train_forward_tc() {
   static const bool v = [] { const char* e = getenv("AGX_TRAIN_FORWARD"); return !(e && !strcmp(e, "fp32")); }();
+  return v;
+}
+// backward: chain kernels on the tensor cores (tc_backward.inl, default) or the layer-by-layer path below (AGX_TRAIN_BACKWARD=fp32)
+static bool train_backward_tc() {
+  static const bool v = [] { const char* e = getenv("AGX_TRAIN_BACKWARD"); return !(e && !strcmp(e, "fp32")); }();
   return v;
 }
 static int train_tc_layer() {
@@ -647,6 +673,21 @@ size_t agx_train_scratch_bytes(const AgxModelDims* dims, int32_t B, int32_t N, i
   return agx::scratch_carve(nullptr, (int64_t)B * N, E_cap > 0 ? E_cap : 1, nullptr);
 }
 
+int agx_train_saved_offsets(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap, int64_t* out, int32_t n) {
+  using namespace agx;
+  AGX_REQUIRE(dims && out && B > 0 && N > 0 && E_cap >= 0 && dims->pstep >= 1 && dims->pstep <= 16, AGX_ERR_ARG, "train_saved_offsets: bad argument");
+  AGX_REQUIRE(n >= 9 + 4 * dims->pstep, AGX_ERR_CAPACITY, "train_saved_offsets: %d entries < %d", n, 9 + 4 * dims->pstep);
+  TrainSaved s;
+  saved_carve(nullptr, (int64_t)B * N, E_cap > 0 ? E_cap : 1, dims->pstep, &s);
+  auto off = [](const float* p) { return (int64_t)reinterpret_cast<intptr_t>(p); };   // carved from a null base: the pointer is the offset
+  const float* fixed[9] = {s.h1, s.h2, s.penc, s.g1, s.g2, s.renc, s.C, s.u1, s.u2};
+  for (int i = 0; i < 9; ++i) out[i] = off(fixed[i]);
+  for (int k = 0; k < dims->pstep; ++k) {
+    out[9 + 4 * k] = off(s.P[k + 1]); out[10 + 4 * k] = off(s.agg[k]); out[11 + 4 * k] = off(s.Qr[k]); out[12 + 4 * k] = off(s.Qs[k]);
+  }
+  return train_forward_tc() ? 1 : 0;
+}
+
 int agx_forward_train(const AgxModelDims* dims, const void* packed_weights, const AgxGraphIn* g, float* pred_pos, int64_t pos_stride_b,
                       float* pred_motion, void* saved, size_t saved_bytes, agx_stream_t stream) {
   using namespace agx;
@@ -735,6 +776,67 @@ int agx_backward(const AgxModelDims* dims, const void* packed_weights, const Agx
   float* const* gw = grads->weight;
   float* const* gb = grads->bias;
   const bool fwd_tc = train_forward_tc();   // layout of the saved C / Qr / Qs
+  if (train_backward_tc()) {
+    // Four kinds of chain kernels (tc_backward.cuh) + the relation kernels + batched weight-gradient jobs.  Every gradient row
+    // leaves its chain masked, so the weight-gradient jobs read two streams (gradient, layer input) and no mask.
+    const size_t base = L.total * sizeof(float);
+    const TcBwdBuffers bb{s.u2, s.u1, s.penc, s.h2, s.h1, s.renc, s.g2, s.g1,
+                          t.dm, t.dU, t.dV, t.dPn, t.dA, t.dAgg, t.dQr, t.dQs, t.dP, t.dH2, t.dH1, t.dC, t.dE, t.dG2, t.dG1, t.dRel,
+                          t.preMax, t.aBound, t.aggMax, t.cBound, t.qrMax, t.qsMax};
+    WgradBatch wb(st, t.part);
+    AGX_TRY(tc_bwd_head(g, W, L, base, bb, s.P[K], d_pred_pos, d_pred_motion, pred_motion, st));
+    if (gw[AGX_W_PRED2]) {
+      head_wgrad_kernel<<<dim3(F + 1, 3), 256, 0, st>>>(t.dm, s.u2, rows, F, gw[AGX_W_PRED2], gb[AGX_W_PRED2]);
+      AGX_LAUNCH_CHECK();
+    }
+    AGX_TRY(wb.add(t.dU, nullptr, s.u1, FP, FP, rows, F, F, F, 0, gw[AGX_W_PRED1], gb[AGX_W_PRED1]));
+    AGX_TRY(wb.add(t.dV, nullptr, s.P[K], FP, FP, rows, F, F, F, 0, gw[AGX_W_PRED0], gb[AGX_W_PRED0]));
+    if (g->E_cap == 0) {
+      AGX_CUDA_OK(cudaMemsetAsync(t.dQr, 0, rows * FP * sizeof(float), st));
+      AGX_CUDA_OK(cudaMemsetAsync(t.dQs, 0, rows * FP * sizeof(float), st));
+      AGX_CUDA_OK(cudaMemsetAsync(t.qrMax, 0, rows * sizeof(float), st));
+      AGX_CUDA_OK(cudaMemsetAsync(t.qsMax, 0, rows * sizeof(float), st));
+    }
+    for (int k = K - 1; k >= 0; --k) {
+      WgradBatch ws(st, t.part);   // this step's jobs run before the next chain kernel rewrites dPre / dQr / dQs
+      AGX_TRY(ws.add(t.dPn, nullptr, s.agg[k], FP, FP, rows, F, F, 2 * F, F, gw[AGX_W_PPROP], nullptr));
+      if (g->E_cap > 0) {
+        effect_bwd_recv_kernel<<<(unsigned)((rows + TA_NODES - 1) / TA_NODES), TA_THREADS, 0, st>>>(
+            g->row_ptr, g->send, rows, g->N, g->E_cap, s.C, s.Qr[k], s.Qs[k], fwd_tc, reinterpret_cast<const float4*>(t.dAgg),
+            reinterpret_cast<float4*>(t.dC), k == K - 1, reinterpret_cast<float4*>(t.dQr), t.qrMax);
+        AGX_LAUNCH_CHECK();
+        effect_bwd_send_kernel<<<(unsigned)((rows + TA_NODES - 1) / TA_NODES), TA_THREADS, 0, st>>>(
+            send_ptr, send_perm, g->recv, rows, g->E_cap, s.C, s.Qr[k], s.Qs[k], fwd_tc, reinterpret_cast<const float4*>(t.dAgg),
+            reinterpret_cast<float4*>(t.dQs), t.qsMax);
+        AGX_LAUNCH_CHECK();
+        AGX_TRY(ws.add(t.dQr, nullptr, s.P[k], FP, FP, rows, F, F, 3 * F, F, gw[AGX_W_RPROP], nullptr));
+        AGX_TRY(ws.add(t.dQs, nullptr, s.P[k], FP, FP, rows, F, F, 3 * F, 2 * F, gw[AGX_W_RPROP], nullptr));
+      }
+      AGX_TRY(ws.flush());
+      if (k > 0) AGX_TRY(tc_bwd_step(g, W, base, bb, s.P[k], st));
+      else AGX_TRY(tc_bwd_node_encoder(g, W, base, bb, st));
+    }
+    AGX_TRY(wb.add(t.dA, nullptr, s.penc, FP, FP, rows, F, F, 2 * F, 0, gw[AGX_W_PPROP], gb[AGX_W_PPROP]));
+    AGX_TRY(wb.add(t.dP, nullptr, s.h2, FP, FP, rows, F, F, F, 0, gw[AGX_W_PENC4], gb[AGX_W_PENC4]));
+    AGX_TRY(wb.add(t.dH2, nullptr, s.h1, FP, FP, rows, F, F, F, 0, gw[AGX_W_PENC2], gb[AGX_W_PENC2]));
+    AGX_TRY(wb.add(t.dH1, nullptr, s.p_in, D_NODE_IN, D_NODE_IN, rows, F, d_node, d_node, 0, gw[AGX_W_PENC0], gb[AGX_W_PENC0]));
+    if (g->E_cap > 0) {
+      AGX_TRY(tc_bwd_edge_encoder(g, W, base, bb, st));
+      const int32_t* n_rel = g->row_ptr + rows;   // relations actually built (rows past it hold nothing)
+      AGX_TRY(wb.add(t.dC, nullptr, s.renc, FP, FP, E, F, F, 3 * F, 0, gw[AGX_W_RPROP], gb[AGX_W_RPROP], n_rel));
+      AGX_TRY(wb.add(t.dE, nullptr, s.g2, FP, FP, E, F, F, F, 0, gw[AGX_W_RENC4], gb[AGX_W_RENC4], n_rel));
+      AGX_TRY(wb.add(t.dG2, nullptr, s.g1, FP, FP, E, F, F, F, 0, gw[AGX_W_RENC2], gb[AGX_W_RENC2], n_rel));
+      AGX_TRY(wb.add(t.dG1, nullptr, s.rel_in, D_REL_IN, D_REL_IN, E, F, d_rel, d_rel, 0, gw[AGX_W_RENC0], gb[AGX_W_RENC0], n_rel));
+    }
+    AGX_TRY(wb.flush());
+    if (d_state) {
+      if (g->E_cap == 0) AGX_CUDA_OK(cudaMemsetAsync(t.dRel, 0, sizeof(float), st));
+      state_bwd_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(g->row_ptr, g->E_cap > 0 ? send_ptr : g->row_ptr, send_perm, g->E_cap, t.dRel,
+                                                                      d_pred_pos, g->B, g->N, g->n_p, d_state);
+      AGX_LAUNCH_CHECK();
+    }
+    return AGX_OK;
+  }
   AGX_CUDA_OK(cudaMemsetAsync(t.dA, 0, rows * FP * sizeof(float), st));
   AGX_CUDA_OK(cudaMemsetAsync(t.dC, 0, E * FP * sizeof(float), st));
 
@@ -766,11 +868,11 @@ int agx_backward(const AgxModelDims* dims, const void* packed_weights, const Agx
     if (g->E_cap > 0) {
       effect_bwd_recv_kernel<<<(unsigned)((rows + TA_NODES - 1) / TA_NODES), TA_THREADS, 0, st>>>(
           g->row_ptr, g->send, rows, g->N, g->E_cap, s.C, s.Qr[k], s.Qs[k], fwd_tc, reinterpret_cast<const float4*>(t.dAgg),
-          reinterpret_cast<float4*>(t.dC), reinterpret_cast<float4*>(t.dQr));
+          reinterpret_cast<float4*>(t.dC), false, reinterpret_cast<float4*>(t.dQr), nullptr);
       AGX_LAUNCH_CHECK();
       effect_bwd_send_kernel<<<(unsigned)((rows + TA_NODES - 1) / TA_NODES), TA_THREADS, 0, st>>>(
           send_ptr, send_perm, g->recv, rows, g->E_cap, s.C, s.Qr[k], s.Qs[k], fwd_tc, reinterpret_cast<const float4*>(t.dAgg),
-          reinterpret_cast<float4*>(t.dQs));
+          reinterpret_cast<float4*>(t.dQs), nullptr);
       AGX_LAUNCH_CHECK();
       AGX_TRY(ws.add(t.dQr, nullptr, s.P[k], FP, FP, rows, F, F, 3 * F, F, gw[AGX_W_RPROP], nullptr));
       AGX_TRY(ws.add(t.dQs, nullptr, s.P[k], FP, FP, rows, F, F, 3 * F, 2 * F, gw[AGX_W_RPROP], nullptr));

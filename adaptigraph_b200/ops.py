@@ -327,6 +327,45 @@ def forward_train(packed: Tensor, state: Tensor, attrs: Tensor, action: Tensor, 
     return pred_pos, pred_motion, saved
 
 
+def train_saved_views(saved: Tensor, F: int, n_his: int, d_attr: int, d_phys: int, d_act: int, pstep: int, B: int, N: int, E_cap: int):
+    """Row-major views / copies ([rows][AGX_FP] fp32) of the forward activations inside the opaque `saved` buffer of
+    `forward_train`, keyed h1, h2, penc, g1, g2, renc, C, u1, u2 and P<k+1>, agg<k>, Qr<k>, Qs<k> per propagation step k.
+    For parity tests (ReLU activity patterns); the blocked C / Qr / Qs of the tensor-core forward are un-blocked here."""
+    dims = make_dims(F, n_his, d_attr, d_phys, d_act, pstep)
+    n = 9 + 4 * pstep
+    offs = (C.c_int64 * n)()
+    blocked = lib.agx_train_saved_offsets(C.byref(dims), B, N, E_cap, offs, n)
+    if blocked < 0:
+        L.check(blocked, "agx_train_saved_offsets")
+    rows, E = B * N, max(E_cap, 1)
+    fl = saved.view(torch.float32)
+
+    def row_major(off, r):
+        return fl[off // 4: off // 4 + r * L.AGX_FP].view(r, L.AGX_FP)
+
+    def unblock(off, r):
+        tiles = (r + 127) // 128
+        t = fl[off // 4: off // 4 + tiles * 128 * 152].view(tiles, 128 * 152)
+        wide = t[:, : 9 * 128 * 16].reshape(tiles, 9, 128, 16).permute(0, 2, 1, 3).reshape(tiles, 128, 144)
+        narrow = t[:, 9 * 128 * 16:].reshape(tiles, 128, 8)
+        out = torch.zeros(tiles * 128, L.AGX_FP, dtype=torch.float32, device=saved.device)
+        out[:, :152] = torch.cat([wide, narrow], 2).reshape(tiles * 128, 152)
+        return out[:r]
+
+    feat = unblock if blocked == 1 else row_major
+    names = ["h1", "h2", "penc", "g1", "g2", "renc", "C", "u1", "u2"]
+    nrow = [rows, rows, rows, E, E, E, E, rows, rows]
+    views = {}
+    for i, (k, r) in enumerate(zip(names, nrow)):
+        views[k] = feat(offs[i], r) if k == "C" else row_major(offs[i], r)
+    for k in range(pstep):
+        views[f"P{k + 1}"] = row_major(offs[9 + 4 * k], rows)
+        views[f"agg{k}"] = row_major(offs[10 + 4 * k], rows)
+        views[f"Qr{k}"] = feat(offs[11 + 4 * k], rows)
+        views[f"Qs{k}"] = feat(offs[12 + 4 * k], rows)
+    return views
+
+
 def backward(packed: Tensor, state: Tensor, attrs: Tensor, action: Tensor, p_inst: Tensor, physics: Tensor, row_ptr: Tensor,
              send: Tensor, recv: Tensor, send_ptr: Tensor, send_perm: Tensor, saved: Tensor, pred_motion: Tensor, d_pos, d_motion,
              grad_w: List[Tensor], grad_b: List[Tensor], d_state, F: int, pstep: int) -> None:

@@ -217,6 +217,15 @@ typedef struct AgxWeightGrads {
 } AgxWeightGrads;
 AGX_API size_t agx_train_saved_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap);
 AGX_API size_t agx_train_scratch_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap);
+/* Where the forward activations live inside `saved` (for parity tests that compare ReLU activity patterns with the reference's;
+ * the backward itself needs nothing from the caller).  Fills out[0 .. n-1] with BYTE offsets, in this order:
+ *   0 h1, 1 h2, 2 penc (= particle effect 0), 3 g1, 4 g2, 5 renc, 6 C, 7 u1, 8 u2, then per propagation step k = 0 .. pstep-1:
+ *   9+4k particle effect k+1, 10+4k agg_k, 11+4k Qr_k, 12+4k Qs_k.
+ * Rows are fp32 with a stride of AGX_FP floats (particles: B*N rows, relations: E_cap rows), except C / Qr / Qs when the return
+ * value is 1: those then use the blocked layout of the tensor-core path -- [row / 128][piece][row % 128][w] floats with nine
+ * 16-column pieces and a tenth of 8 columns (columns 0..151; 152..159 are padding and not stored).  Returns 0 (all row-major),
+ * 1 (blocked C / Qr / Qs) or a negative error code. */
+AGX_API int agx_train_saved_offsets(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap, int64_t* out, int32_t n);
 AGX_API int agx_forward_train(const AgxModelDims* dims, const void* packed_weights, const AgxGraphIn* g, float* pred_pos,
                               int64_t pos_stride_b, float* pred_motion, void* saved, size_t saved_bytes, agx_stream_t stream);
 AGX_API int agx_backward(const AgxModelDims* dims, const void* packed_weights, const AgxGraphIn* g, const void* saved,

@@ -155,10 +155,12 @@ def _lin(p, name, x):
     return torch.nn.functional.linear(x, p[name + ".weight"], p[name + ".bias"])
 
 
-def _encoder(p, prefix, x):
-    """model.py:4-21 — three Linear layers, ReLU after each (including the last)."""
-    for i in (0, 2, 4):
-        x = torch.relu(_lin(p, f"{prefix}.model.{i}", x))
+def _encoder(p, prefix, x, relu=None, names=None):
+    """model.py:4-21 — three Linear layers, ReLU after each (including the last).  `relu(name, x)`, when given, stands in for
+    torch.relu at the site `names[i]` (gradient parity tests substitute the activity pattern of the engine under test)."""
+    for n, i in enumerate((0, 2, 4)):
+        x = _lin(p, f"{prefix}.model.{i}", x)
+        x = torch.relu(x) if relu is None else relu(names[n], x)
     return x
 
 
@@ -198,11 +200,15 @@ def forward_dense(p, pstep, state, attrs, Rr, Rs, p_instance, action, physics_pa
     return pos, motion
 
 
-def forward_sparse(p, pstep, state, attrs, row_ptr, send, p_instance, action, physics_param):
+def forward_sparse(p, pstep, state, attrs, row_ptr, send, p_instance, action, physics_param, relu=None):
     """Same function on CSR edge lists with the propagator weights split per operand
     (W[:, :F] relation part, W[:, F:2F] receiver part, W[:, 2F:] sender part) so the
     per-edge 450->150 product becomes gathers of per-node products.  Equal to
-    `forward_dense` up to fp32 summation order."""
+    `forward_dense` up to fp32 summation order.
+
+    relu: optional `relu(site, x)` replacing torch.relu at the sites h1, h2, penc (particle encoder), g1, g2, renc (relation
+    encoder), e<k> (relation effects of propagation step k), P<k+1> (particle effects), u1, u2 (predictor)."""
+    act = (lambda name, x: torch.relu(x)) if relu is None else relu
     B, H, N, _ = state.shape
     n_p = p_instance.shape[1]
     hist, p_in, group = node_and_relation_inputs(state, attrs, p_instance, action, physics_param)
@@ -212,22 +218,22 @@ def forward_sparse(p, pstep, state, attrs, row_ptr, send, p_instance, action, ph
     fl = lambda t: t.reshape(B * N, -1)  # noqa: E731
     a, g, hs = fl(attrs), fl(group), fl(hist)
     rel_in = torch.cat([a[recv], a[snd], (g[recv] - g[snd]).abs().sum(1, keepdim=True), hs[recv] - hs[snd]], 1)
-    penc = _encoder(p, "particle_encoder", fl(p_in))
-    renc = _encoder(p, "relation_encoder", rel_in)
+    penc = _encoder(p, "particle_encoder", fl(p_in), relu, ("h1", "h2", "penc"))
+    renc = _encoder(p, "relation_encoder", rel_in, relu, ("g1", "g2", "renc"))
     F = penc.shape[1]
     Wr, br = p["relation_propagator.linear.weight"], p["relation_propagator.linear.bias"]
     Wp, bp = p["particle_propagator.linear.weight"], p["particle_propagator.linear.bias"]
     c_edge = renc @ Wr[:, :F].T + br
     a_node = penc @ Wp[:, :F].T + bp
     eff = penc
-    for _ in range(pstep):
+    for k in range(pstep):
         q_r, q_s = eff @ Wr[:, F:2 * F].T, eff @ Wr[:, 2 * F:].T
-        e_out = torch.relu(c_edge + q_r[recv] + q_s[snd])
+        e_out = act(f"e{k}", c_edge + q_r[recv] + q_s[snd])
         agg = torch.zeros_like(eff).index_add_(0, recv, e_out)
-        eff = torch.relu(a_node + agg @ Wp[:, F:].T + eff)
+        eff = act(f"P{k + 1}", a_node + agg @ Wp[:, F:].T + eff)
     eff = eff.reshape(B, N, F)[:, :n_p]
-    h = torch.relu(_lin(p, "non_rigid_predictor.linear_0", eff))
-    h = torch.relu(_lin(p, "non_rigid_predictor.linear_1", h))
+    h = act("u1", _lin(p, "non_rigid_predictor.linear_0", eff))
+    h = act("u2", _lin(p, "non_rigid_predictor.linear_1", h))
     motion = _lin(p, "non_rigid_predictor.linear_2", h)
     return state[:, -1, :n_p] + motion.clamp(-MOTION_CLAMP, MOTION_CLAMP), motion
 

@@ -188,10 +188,57 @@ def test_optimizer_state_round_trips_through_torch_adam(agx):
     assert torch.equal(tr2.bucket.views(tr2.exp_avg)[0], ref_m.cuda())
 
 
-@pytest.mark.parametrize("material,n_p,B,pstep", [("granular", 150, 3, 2), ("cloth", 200, 2, 3)])
+class _ReluWithPattern(torch.autograd.Function):
+    """relu(x) whose backward uses a given 0/1 activity pattern instead of x > 0."""
+
+    @staticmethod
+    def forward(ctx, x, pattern):
+        ctx.save_for_backward(pattern)
+        return x.clamp_min(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (pattern,) = ctx.saved_tensors
+        return g * pattern, None
+
+
+def _engine_patterns(agx, m, wd, el, pstep):
+    """ReLU activity patterns of the engine's training forward (agx_forward_train run once more on the same inputs: it is
+    deterministic), keyed like the sites of oracle.forward_sparse."""
+    from adaptigraph_b200 import ops
+    B, H_, N, _ = wd.state.shape
+    n_p = wd.p_instance.shape[1]
+    f32 = lambda t: t.to(torch.float32).contiguous()  # noqa: E731
+    p_inst = f32(wd.p_instance.reshape(B, n_p, -1)[:, :, 0])
+    F = m.nf_effect
+    _, _, saved = ops.forward_train(m.packed_weights(), f32(wd.state), f32(wd.attrs), f32(wd.action), p_inst, f32(wd.physics_param),
+                                    el.row_ptr, el.send, el.recv, F, pstep)
+    v = ops.train_saved_views(saved, F, H_, wd.attrs.shape[2], wd.physics_param.shape[1], wd.action.shape[2], pstep, B, N, int(el.send.numel()))
+    E = int(el.row_ptr[-1])
+    recv = el.recv[:E].long()
+    snd = el.send[:E].long() + (recv // N) * N
+    pat = {k: (v[k][:, :F] > 0) for k in ("h1", "h2", "penc")}
+    pat.update({k: (v[k][:E, :F] > 0) for k in ("g1", "g2", "renc")})
+    for k in range(pstep):
+        pat[f"e{k}"] = ((v["C"][:E, :F] + v[f"Qr{k}"][recv, :F]) + v[f"Qs{k}"][snd, :F]) > 0      # the backward's own association
+        pat[f"P{k + 1}"] = v[f"P{k + 1}"][:, :F] > 0
+    for k in ("u1", "u2"):
+        pat[k] = v[k].view(B, N, -1)[:, :n_p, :F] > 0
+    return {k: t.cpu() for k, t in pat.items()}, E
+
+
+@pytest.mark.parametrize("material,n_p,B,pstep", [("granular", 150, 3, 2), ("cloth", 200, 2, 3), ("rope", 120, 3, 4)])
 def test_gradients_match_oracle_autograd_on_seeded_graphs(agx, material, n_p, B, pstep):
-    """Beyond the golden unroll (rope, 40 particles): loss and every gradient of one forward against torch autograd over the oracle's
-    dense restatement, on graphs with hundreds of particles, tool senders and padded particles (tensor-core training layers)."""
+    """Beyond the golden unroll (rope, 40 particles): loss and every gradient of one forward + backward (tensor-core chains)
+    against torch autograd over the oracle, on graphs with hundreds of particles, tool senders and padded particles.
+
+    A gradient is a discontinuous function of the forward values: wherever a ReLU input is within rounding of zero, two fp32
+    evaluations of the same model (torch on the CPU, torch on a GPU, this engine) may disagree on whether the unit is active, and
+    each such unit moves the gradients by up to 1e-4 of their maximum.  The comparison is therefore stated the way the rollout
+    parity is stated for relation flips: (a) the engine's activity pattern differs from the oracle's only at
+    ReLU inputs the oracle itself puts within 1e-5 of zero (a handful among millions); (b) on the SAME activity pattern -- the
+    oracle's autograd with the engine's pattern substituted in the ReLU backward -- every gradient agrees to 1e-5 of its maximum;
+    (c) against the oracle's unconditioned gradients the difference stays below 3e-4."""
     from adaptigraph_b200 import synthetic as syn
     from oracle import dynamics_oracle as orc
     w = syn.make_workload(material, n_p, B, seed=77, n_pad=6)
@@ -206,17 +253,36 @@ def test_gradients_match_oracle_autograd_on_seeded_graphs(agx, material, n_p, B,
     tgt = torch.randn(pos.shape, generator=torch.Generator().manual_seed(5)).cuda() * 0.05
     loss = torch.nn.functional.mse_loss(pos, wd.state[:, -1, :pos.shape[1]] + tgt) + 0.1 * motion.square().mean()
     loss.backward()
-    # oracle: dense one-hots + autograd on the CPU
-    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
-    Rr, Rs = orc.edges_dense_batch(w.state[:, -1], w.adj_thresh, w.state_mask, w.eef_mask, w.topk, w.connect_tools_all)
-    st_c = w.state.clone().requires_grad_(True)
-    pos_c, motion_c = orc.forward_dense(p, pstep, st_c, w.attrs, Rr, Rs, w.p_instance, w.action, w.physics_param)
-    loss_c = torch.nn.functional.mse_loss(pos_c, w.state[:, -1, :pos_c.shape[1]] + tgt.cpu()) + 0.1 * motion_c.square().mean()
-    loss_c.backward()
+    patterns, E = _engine_patterns(agx, m, wd, el, pstep)
+
+    def oracle_grads(relu):
+        p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+        st_c = w.state.clone().requires_grad_(True)
+        pos_c, motion_c = orc.forward_sparse(p, pstep, st_c, w.attrs, el.row_ptr.cpu(), el.send.cpu()[:E], w.p_instance, w.action,
+                                             w.physics_param, relu=relu)
+        loss_c = torch.nn.functional.mse_loss(pos_c, w.state[:, -1, :pos_c.shape[1]] + tgt.cpu()) + 0.1 * motion_c.square().mean()
+        loss_c.backward()
+        return loss_c, st_c.grad, {k: v.grad for k, v in p.items()}
+
+    # (a) where the patterns differ, and (b) the oracle's gradients on the engine's pattern
+    differing = []
+
+    def with_engine_pattern(site, x):
+        pat = patterns[site].reshape(x.shape)
+        diff = pat != (x.detach() > 0)
+        if diff.any():
+            differing.append((site, int(diff.sum()), float(x.detach()[diff].abs().max())))
+        return _ReluWithPattern.apply(x, pat.to(x.dtype))
+
+    loss_c, st_ref, p_ref = oracle_grads(with_engine_pattern)
     assert abs(loss.item() - loss_c.item()) <= 1e-6 * max(1.0, abs(loss_c.item()))
-    # the default (fp32 FFMA) training layers measure <= 8e-7 here; AGX_TRAIN_PRECISION=tc would reach 1.4e-4 and fail
-    ref = st_c.grad
-    assert (st.grad.cpu() - ref).abs().max() <= 1e-5 * max(1e-3, float(ref.abs().max()))
+    assert sum(n for _, n, _ in differing) <= 64, differing
+    assert all(mx <= 1e-5 for _, _, mx in differing), differing
+    assert (st.grad.cpu() - st_ref).abs().max() <= 1e-5 * max(1e-3, float(st_ref.abs().max()))
     for k, v in m.named_parameters():
-        ref = p[k].grad
-        assert (v.grad.cpu() - ref).abs().max() <= 1e-5 * max(1e-3, float(ref.abs().max())), k
+        assert (v.grad.cpu() - p_ref[k]).abs().max() <= 1e-5 * max(1e-3, float(p_ref[k].abs().max())), k
+    # (c) the unconditioned oracle
+    _, st_raw, p_raw = oracle_grads(None)
+    assert (st.grad.cpu() - st_raw).abs().max() <= 3e-4 * max(1e-3, float(st_raw.abs().max()))
+    for k, v in m.named_parameters():
+        assert (v.grad.cpu() - p_raw[k]).abs().max() <= 3e-4 * max(1e-3, float(p_raw[k].abs().max())), k
