@@ -14,7 +14,8 @@ struct TcBwdBuffers {
   // gradients, row-major
   float *dm;                 // [rows][4] gradient with respect to the predicted motion
   float *dU2, *dU1;          // masked gradients of the two hidden head layers
-  float *dPre;               // stream: d pre_n of the current propagation step (masked), finally dP_0
+  float *dPre;               // d pre_n (masked) of the propagation step being left: read by the step kernels, written by the head
+  float *dPreOut;            // d pre_n of the step being entered (step kernels) / dP_0 (particle encoder kernel)
   float *dA, *dAgg, *dQr, *dQs;
   float *dPenc, *dH2, *dH1;  // masked gradients of the particle encoder outputs
   float *dC, *dE, *dG2, *dG1, *dRel;   // relation side ([E][FP]; dRel [E][D_REL_IN])

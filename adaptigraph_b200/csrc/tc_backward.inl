@@ -121,7 +121,7 @@ __device__ __forceinline__ float bwd_out(const Shared& sh, EpiCtx& cx, const flo
   return epi_exchange<true>(sh, cx, mx);
 }
 
-// dP = (d pre + dQr W_recv) + dQs W_send, first half: layer TT_RP_RECV's result parks in dPre, dQs becomes the next A.
+// dP = (d pre + dQr W_recv) + dQs W_send, first half: d pre + layer TT_RP_RECV's result parks in dPreOut, dQs becomes the next A.
 // Returns the bound on the parked rows.
 __device__ __forceinline__ float bwd_recv_then_send(const Shared& sh, EpiCtx& cx, const float4 m_recv, const BwdArgs& a, int64_t r, bool valid) {
   const float bound_r = cx.bound_in;
@@ -132,7 +132,7 @@ __device__ __forceinline__ float bwd_recv_then_send(const Shared& sh, EpiCtx& cx
       [&](int, int col0, float (&v)[HW]) {
         if (valid) {
           row_add16(a.b.dPre, r, col0, v);
-          row_store16(a.b.dPre, r, col0, v);
+          row_store16(a.b.dPreOut, r, col0, v);
           row_load16(a.b.dQs, r, col0, v);
         } else {
           zero16(v);
@@ -250,14 +250,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_bwd_step_kernel(const BwdArgs a
       const bool valid = r < a.rows;
       bwd_produce_rows(sh, cx, a.b.dQr, r, valid, valid ? a.b.qrMax[r] : 0.f);
       const float bound_t = bwd_recv_then_send(sh, cx, meta[0], a, r, valid);
-      // dP_k = parked + dQs W_send ; d pre_{k-1} = dP_k (*) [P_k > 0] -> dPre (in place), dA += d pre_{k-1}
-      const float pm = bwd_hidden(sh, cx, meta[1], bound_t, a.b.dPre, a.P_act, a.b.dPre, r, valid);
+      // dP_k = parked + dQs W_send ; d pre_{k-1} = dP_k (*) [P_k > 0] -> dPreOut (in place of the parked rows), dA += d pre_{k-1}
+      const float pm = bwd_hidden(sh, cx, meta[1], bound_t, a.b.dPreOut, a.P_act, a.b.dPreOut, r, valid);
       if (valid) {
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
           const int col0 = 32 * c + HW * cx.half;
           float v[HW];
-          row_load16(a.b.dPre, r, col0, v);
+          row_load16(a.b.dPreOut, r, col0, v);
           row_accumulate16(a.b.dA, r, col0, v);
         }
         if (cx.half == 0) { a.b.preMax[r] = pm; a.b.aBound[r] += pm; }
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_bwd_node_encoder_kernel(const B
       const bool valid = r < a.rows;
       bwd_produce_rows(sh, cx, a.b.dQr, r, valid, valid ? a.b.qrMax[r] : 0.f);
       const float bound_t = bwd_recv_then_send(sh, cx, meta[0], a, r, valid);
-      // dP_0 = parked + dQs W_send -> dPre ; the accumulated dA becomes the next A
+      // dP_0 = parked + dQs W_send -> dPreOut ; the accumulated dA becomes the next A
       float bound_p0;
       {
         const float4 m = meta[1];
@@ -304,8 +304,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_bwd_node_encoder_kernel(const B
             sh, cx, exp2i(-cx.e_in) * m.x, exp2i(e_a), NoExtra{},
             [&](int, int col0, float (&v)[HW]) {
               if (valid) {
-                row_add16(a.b.dPre, r, col0, v);
-                row_store16(a.b.dPre, r, col0, v);
+                row_add16(a.b.dPreOut, r, col0, v);
+                row_store16(a.b.dPreOut, r, col0, v);
                 row_load16(a.b.dA, r, col0, v);
               } else {
                 zero16(v);
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_bwd_node_encoder_kernel(const B
         cx.e_in = e_a;
         cx.bound_in = bound_a;
       }
-      bwd_hidden(sh, cx, meta[2], bound_p0, a.b.dPre, a.b.penc, a.b.dPenc, r, valid);   // d penc = (dP_0 + dA W_enc) (*) [penc > 0]
+      bwd_hidden(sh, cx, meta[2], bound_p0, a.b.dPreOut, a.b.penc, a.b.dPenc, r, valid);   // d penc = (dP_0 + dA W_enc) (*) [penc > 0]
       bwd_hidden(sh, cx, meta[3], 0.f, nullptr, a.b.h2, a.b.dH2, r, valid);
       bwd_out(sh, cx, meta[4], a.b.h1, a.b.dH1, r, valid);
       tile = slot_tile(k + 1, cx.slot, n_tiles);

@@ -41,6 +41,11 @@ constexpr size_t WG_SMEM = (size_t)WG_OFF_CTRL + 512;
 constexpr int WG_TMEM_COLS = 512;                // two accumulator blocks of 160 columns (block 1: operand rows 128..159)
 constexpr int WG_SCALE_TARGET = 12;              // a fresh scale puts the stage maximum at <= 2^12 ...
 constexpr float WG_SCALE_LIMIT = 32768.f;        // ... and is kept until a later stage would exceed 2^15 (fp16 overflows at 65504)
+// The tensor core adds into its fp32 accumulator with truncation, a bias of about 2^-25 per MMA that grows linearly with the
+// length of the chain (measured: weight gradients over 9632 rows off by 3e-5 of their maximum with one chain of 600 MMAs per
+// CTA, 2e-6 with chains of 48).  The accumulators are therefore drained into the fp32 partial product (round-to-nearest adds)
+// every WG_DRAIN_EVERY stages.
+constexpr int WG_DRAIN_EVERY = 16;
 static_assert(WG_SMEM <= 227 * 1024, "shared memory");
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgArgs a)
   float sa = 1.f, sb = 1.f;
   bool have_a = false, have_b = false, acc_valid = false, drained = false;
 
-  // accumulators -> partial product (=, or += after an earlier drain).  warp w: lane quarter w % 4, 16-column chunks w / 4, + 4, ...
+  // accumulators -> partial product (a store the first time, vector reductions afterwards).  warp w: lane quarter w % 4, 16-column chunks w / 4, + 4, ...
   auto drain = [&]() {
     wait_buf(0);
     wait_buf(1);
@@ -141,8 +146,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgArgs a)
         for (int i = 0; i < 4; ++i) {
           float4 v = make_float4(__uint_as_float(r[4 * i]) * unscale, __uint_as_float(r[4 * i + 1]) * unscale,
                                  __uint_as_float(r[4 * i + 2]) * unscale, __uint_as_float(r[4 * i + 3]) * unscale);
-          if (drained) { const float4 p = o[i]; v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
-          o[i] = v;
+          if (drained)   // fire-and-forget vector add: no read round trip; one thread per address, in program order (deterministic)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+          else
+            o[i] = v;
         }
       }
     }
@@ -201,17 +208,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgArgs a)
     return mx;
   };
 
-  int pass = 0;
+  int pass = 0, since_drain = 0;
   uint32_t raw_par0 = 0, raw_par1 = 0;
   for (int s = 0; s < nst; ++s) {
     const int buf = s & 1;
+    if (since_drain == WG_DRAIN_EVERY) { drain(); since_drain = 0; }
+    ++since_drain;
     uint8_t* stage = smem + buf * WG_STAGE;
     const uint8_t* raw = smem + WG_OFF_RAW + buf * WG_RAW;
     const int64_t m0 = r0 + (int64_t)s * WG_ROWS;
     const int rows_here = (int)min((int64_t)WG_ROWS, r1 - m0);
+#ifdef AGX_WG_TIMELINE
+    const long long t0 = clock64();
+#endif
     wait_buf(buf);   // the MMAs that last read this operand buffer are complete
+#ifdef AGX_WG_TIMELINE
+    const long long t1 = clock64();
+#endif
     if (buf) { mbar_wait(&bar_raw[1], raw_par1); raw_par1 ^= 1; }
     else { mbar_wait(&bar_raw[0], raw_par0); raw_par0 ^= 1; }
+#ifdef AGX_WG_TIMELINE
+    const long long t2 = clock64();
+#endif
     // A pass converts the stage under the current scales and finds its maxima on the way.  When a maximum does not fit (always in
     // the very first pass, where no scale exists yet) the accumulators are drained, the scale is renewed and the pass repeated.
     for (;;) {
@@ -271,7 +289,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgArgs a)
       }
       mma_commit(&bar_done[buf]);
 #ifdef AGX_WG_TIMELINE
-      if (blockIdx.x == gridDim.x - 1 && s >= 4 && s < 14)
+      if (blockIdx.x == 0 && s >= 4 && s < 24)
         printf("stage %d: wait_buf %lld wait_raw %lld convert %lld issue %lld passes %d\n", s, t1 - t0, t2 - t1, t3 - t2, clock64() - t3, pass);
 #endif
     }

@@ -500,9 +500,10 @@ static size_t saved_carve(void* base, int64_t rows, int64_t E, int K, TrainSaved
 struct TrainScratch {
   float *dU, *dV, *dH2, *dH1, *dP, *dPn, *dA, *dAgg, *dQr, *dQs, *dC, *dE, *dG2, *dG1, *dRel, *dm, *part;
   float *preMax, *aBound, *aggMax, *cBound, *qrMax, *qsMax;   // per-row magnitude bounds of the tensor-core backward
+  float *dPreK[16], *dQrK[16], *dQsK[16], *dP0;   // per propagation step: kept until the single weight-gradient batch at the end
 };
 static int wgrad_max_ctas() { return num_sms() + tc::WG_MAX_JOBS; }
-static size_t scratch_carve(void* base, int64_t rows, int64_t E, TrainScratch* out) {
+static size_t scratch_carve(void* base, int64_t rows, int64_t E, int K, TrainScratch* out) {
   Carver c(base);
   TrainScratch s;
   s.dU = c.take<float>(rows * FP); s.dV = c.take<float>(rows * FP); s.dH2 = c.take<float>(rows * FP); s.dH1 = c.take<float>(rows * FP);
@@ -514,6 +515,8 @@ static size_t scratch_carve(void* base, int64_t rows, int64_t E, TrainScratch* o
   s.part = c.take<float>(part_simt > part_tc ? part_simt : part_tc);
   s.preMax = c.take<float>(rows); s.aBound = c.take<float>(rows); s.aggMax = c.take<float>(rows); s.cBound = c.take<float>(rows);
   s.qrMax = c.take<float>(rows); s.qsMax = c.take<float>(rows);
+  for (int k = 0; k < K; ++k) { s.dPreK[k] = c.take<float>(rows * FP); s.dQrK[k] = c.take<float>(rows * FP); s.dQsK[k] = c.take<float>(rows * FP); }
+  s.dP0 = c.take<float>(rows * FP);
   if (out) *out = s;
   return align_up(c.off, 256);
 }
@@ -606,6 +609,8 @@ struct WgradBatch {
     j.npad = kx >= FP ? FP : (kx + 1 + 15) / 16 * 16;
     j.bias_col = db ? 1 : 0;
     j.ld = ld; j.col0 = col0; j.F = F; j.K = K; j.chain_head = 1; j.next = -1;
+    for (int i = a.njobs - 2; i >= 0; --i)   // same destination as an earlier job of the batch: summed by that job's reduction
+      if (a.job[i].dW == dW && a.job[i].col0 == col0 && a.job[i].next < 0) { a.job[i].next = a.njobs - 1; j.chain_head = 0; j.db = nullptr; break; }
     j.cta0 = j.nctas = j.stages_per_cta = 0;
     return AGX_OK;
   }
@@ -670,7 +675,8 @@ size_t agx_train_saved_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int
 }
 size_t agx_train_scratch_bytes(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap) {
   if (!dims || B <= 0 || N <= 0 || E_cap < 0) return 0;
-  return agx::scratch_carve(nullptr, (int64_t)B * N, E_cap > 0 ? E_cap : 1, nullptr);
+  if (dims->pstep < 1 || dims->pstep > 16) return 0;
+  return agx::scratch_carve(nullptr, (int64_t)B * N, E_cap > 0 ? E_cap : 1, dims->pstep, nullptr);
 }
 
 int agx_train_saved_offsets(const AgxModelDims* dims, int32_t B, int32_t N, int64_t E_cap, int64_t* out, int32_t n) {
@@ -767,7 +773,7 @@ int agx_backward(const AgxModelDims* dims, const void* packed_weights, const Agx
   TrainSaved s;
   saved_carve(const_cast<void*>(saved), rows, E, K, &s);
   TrainScratch t;
-  const size_t need = scratch_carve(scratch, rows, E, &t);
+  const size_t need = scratch_carve(scratch, rows, E, K, &t);
   AGX_REQUIRE(scratch_bytes >= need, AGX_ERR_CAPACITY, "backward: scratch %zu < %zu bytes", scratch_bytes, need);
   AGX_TRY(train_attrs());
   const PackedLayout L = packed_layout();
@@ -781,7 +787,7 @@ int agx_backward(const AgxModelDims* dims, const void* packed_weights, const Agx
     // leaves its chain masked, so the weight-gradient jobs read two streams (gradient, layer input) and no mask.
     const size_t base = L.total * sizeof(float);
     const TcBwdBuffers bb{s.u2, s.u1, s.penc, s.h2, s.h1, s.renc, s.g2, s.g1,
-                          t.dm, t.dU, t.dV, t.dPn, t.dA, t.dAgg, t.dQr, t.dQs, t.dP, t.dH2, t.dH1, t.dC, t.dE, t.dG2, t.dG1, t.dRel,
+                          t.dm, t.dU, t.dV, t.dPreK[K - 1], nullptr, t.dA, t.dAgg, t.dQr, t.dQs, t.dP, t.dH2, t.dH1, t.dC, t.dE, t.dG2, t.dG1, t.dRel,
                           t.preMax, t.aBound, t.aggMax, t.cBound, t.qrMax, t.qsMax};
     WgradBatch wb(st, t.part);
     AGX_TRY(tc_bwd_head(g, W, L, base, bb, s.P[K], d_pred_pos, d_pred_motion, pred_motion, st));
@@ -792,29 +798,33 @@ int agx_backward(const AgxModelDims* dims, const void* packed_weights, const Agx
     AGX_TRY(wb.add(t.dU, nullptr, s.u1, FP, FP, rows, F, F, F, 0, gw[AGX_W_PRED1], gb[AGX_W_PRED1]));
     AGX_TRY(wb.add(t.dV, nullptr, s.P[K], FP, FP, rows, F, F, F, 0, gw[AGX_W_PRED0], gb[AGX_W_PRED0]));
     if (g->E_cap == 0) {
-      AGX_CUDA_OK(cudaMemsetAsync(t.dQr, 0, rows * FP * sizeof(float), st));
-      AGX_CUDA_OK(cudaMemsetAsync(t.dQs, 0, rows * FP * sizeof(float), st));
+      for (int k = 0; k < K; ++k) {
+        AGX_CUDA_OK(cudaMemsetAsync(t.dQrK[k], 0, rows * FP * sizeof(float), st));
+        AGX_CUDA_OK(cudaMemsetAsync(t.dQsK[k], 0, rows * FP * sizeof(float), st));
+      }
       AGX_CUDA_OK(cudaMemsetAsync(t.qrMax, 0, rows * sizeof(float), st));
       AGX_CUDA_OK(cudaMemsetAsync(t.qsMax, 0, rows * sizeof(float), st));
     }
     for (int k = K - 1; k >= 0; --k) {
-      WgradBatch ws(st, t.part);   // this step's jobs run before the next chain kernel rewrites dPre / dQr / dQs
-      AGX_TRY(ws.add(t.dPn, nullptr, s.agg[k], FP, FP, rows, F, F, 2 * F, F, gw[AGX_W_PPROP], nullptr));
+      // every step keeps its own d pre / dQr / dQs rows, so that all weight-gradient jobs run as ONE batch at the end
+      TcBwdBuffers bk = bb;
+      bk.dPre = t.dPreK[k]; bk.dQr = t.dQrK[k]; bk.dQs = t.dQsK[k];
+      bk.dPreOut = k > 0 ? t.dPreK[k - 1] : t.dP0;
+      AGX_TRY(wb.add(bk.dPre, nullptr, s.agg[k], FP, FP, rows, F, F, 2 * F, F, gw[AGX_W_PPROP], nullptr));
       if (g->E_cap > 0) {
         effect_bwd_recv_kernel<<<(unsigned)((rows + TA_NODES - 1) / TA_NODES), TA_THREADS, 0, st>>>(
             g->row_ptr, g->send, rows, g->N, g->E_cap, s.C, s.Qr[k], s.Qs[k], fwd_tc, reinterpret_cast<const float4*>(t.dAgg),
-            reinterpret_cast<float4*>(t.dC), k == K - 1, reinterpret_cast<float4*>(t.dQr), t.qrMax);
+            reinterpret_cast<float4*>(t.dC), k == K - 1, reinterpret_cast<float4*>(bk.dQr), t.qrMax);
         AGX_LAUNCH_CHECK();
         effect_bwd_send_kernel<<<(unsigned)((rows + TA_NODES - 1) / TA_NODES), TA_THREADS, 0, st>>>(
             send_ptr, send_perm, g->recv, rows, g->E_cap, s.C, s.Qr[k], s.Qs[k], fwd_tc, reinterpret_cast<const float4*>(t.dAgg),
-            reinterpret_cast<float4*>(t.dQs), t.qsMax);
+            reinterpret_cast<float4*>(bk.dQs), t.qsMax);
         AGX_LAUNCH_CHECK();
-        AGX_TRY(ws.add(t.dQr, nullptr, s.P[k], FP, FP, rows, F, F, 3 * F, F, gw[AGX_W_RPROP], nullptr));
-        AGX_TRY(ws.add(t.dQs, nullptr, s.P[k], FP, FP, rows, F, F, 3 * F, 2 * F, gw[AGX_W_RPROP], nullptr));
+        AGX_TRY(wb.add(bk.dQr, nullptr, s.P[k], FP, FP, rows, F, F, 3 * F, F, gw[AGX_W_RPROP], nullptr));
+        AGX_TRY(wb.add(bk.dQs, nullptr, s.P[k], FP, FP, rows, F, F, 3 * F, 2 * F, gw[AGX_W_RPROP], nullptr));
       }
-      AGX_TRY(ws.flush());
-      if (k > 0) AGX_TRY(tc_bwd_step(g, W, base, bb, s.P[k], st));
-      else AGX_TRY(tc_bwd_node_encoder(g, W, base, bb, st));
+      if (k > 0) AGX_TRY(tc_bwd_step(g, W, base, bk, s.P[k], st));
+      else AGX_TRY(tc_bwd_node_encoder(g, W, base, bk, st));
     }
     AGX_TRY(wb.add(t.dA, nullptr, s.penc, FP, FP, rows, F, F, 2 * F, 0, gw[AGX_W_PPROP], gb[AGX_W_PPROP]));
     AGX_TRY(wb.add(t.dP, nullptr, s.h2, FP, FP, rows, F, F, F, 0, gw[AGX_W_PENC4], gb[AGX_W_PENC4]));
