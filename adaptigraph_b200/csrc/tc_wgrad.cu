@@ -62,6 +62,37 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
 // exponent e with bound * 2^e <= 2^WG_SCALE_TARGET
 __device__ __forceinline__ int wg_scale_exp(float bound) { return scale_exp(bound) - (TARGET_EXP - WG_SCALE_TARGET); }
 
+// The split of a batch over the grid is computed ON THE DEVICE, identically by every CTA and by the reduction: the number of
+// relation rows that exist is only known there (AgxGraphIn.E_cap is a capacity, often twice the relations actually built), and a
+// split by capacity would leave half the relation CTAs without work.  Every CTA gets the same number of stages, the smallest
+// that fits the batch into `budget` CTAs; the assignment is a pure function of the job sizes (deterministic).
+struct WgPlan {
+  int spc;                          // stages per CTA
+  int cta0[WG_MAX_JOBS + 1];        // first CTA of every job (cta0[njobs] = CTAs in use)
+  int64_t M[WG_MAX_JOBS];           // rows that exist
+};
+__device__ __forceinline__ void wg_plan(const WgArgs& a, int budget, WgPlan& p) {
+  int64_t total = 0;
+  for (int i = 0; i < a.njobs; ++i) {
+    const WgJob& j = a.job[i];
+    p.M[i] = j.m_limit ? min(j.M, (int64_t)__ldg(j.m_limit)) : j.M;
+    total += (p.M[i] + WG_ROWS - 1) / WG_ROWS;
+  }
+  int64_t spc = max((total + budget - 1) / budget, (int64_t)1);
+  for (;; ++spc) {
+    int64_t n = 0;
+    for (int i = 0; i < a.njobs; ++i) n += ((p.M[i] + WG_ROWS - 1) / WG_ROWS + spc - 1) / spc;
+    if (n <= budget) break;
+  }
+  p.spc = (int)spc;
+  int c = 0;
+  for (int i = 0; i < a.njobs; ++i) {
+    p.cta0[i] = c;
+    c += (int)(((p.M[i] + WG_ROWS - 1) / WG_ROWS + spc - 1) / spc);
+  }
+  p.cta0[a.njobs] = c;
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_done = reinterpret_cast<uint64_t*>(smem + WG_OFF_CTRL);         // [2] MMAs that read operand buffer b are complete
@@ -71,17 +102,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgArgs a)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   int ji = 0;
-  while (ji + 1 < a.njobs && (int)blockIdx.x >= a.job[ji + 1].cta0) ++ji;
+  int64_t r0, r1;
+  {
+    WgPlan plan;
+    wg_plan(a, (int)gridDim.x, plan);
+    if ((int)blockIdx.x >= plan.cta0[a.njobs]) return;   // (uniform over the CTA) more CTAs than the rows that exist need
+    while ((int)blockIdx.x >= plan.cta0[ji + 1]) ++ji;
+    r0 = (int64_t)((int)blockIdx.x - plan.cta0[ji]) * plan.spc * WG_ROWS;
+    r1 = min(plan.M[ji], r0 + (int64_t)plan.spc * WG_ROWS);
+  }
   const WgJob& jb = a.job[ji];
-  const int64_t r0 = (int64_t)((int)blockIdx.x - jb.cta0) * jb.stages_per_cta * WG_ROWS;
-  const int64_t M = jb.m_limit ? min(jb.M, (int64_t)__ldg(jb.m_limit)) : jb.M;
-  const int64_t r1 = min(M, r0 + (int64_t)jb.stages_per_cta * WG_ROWS);
   float* out = a.part + (size_t)blockIdx.x * (FP * FP);
   const int npad = jb.npad;
-  if (r0 >= r1) {   // no rows (only when a job was given more CTAs than stages): the partial is zero
-    for (int i = tid; i < FP * npad; i += WG_THREADS) out[(i / npad) * FP + (i % npad)] = 0.f;
-    return;
-  }
   const int nst = (int)((r1 - r0 + WG_ROWS - 1) / WG_ROWS);
   const bool has_mask = jb.mask != nullptr;
   const int ldx = jb.ldx;
@@ -303,20 +335,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgArgs a)
 
 // dW[n * ld + col0 + j] += sum over the job's CTAs (in order) of part[cta][n][j]  (n < F, j < K);  db[n] += ... part[cta][n][npad-1].
 // Jobs chained through `next` add into the same destination and are summed by the same thread, in chain order.
-__global__ void wgrad_tc_reduce_kernel(const WgArgs a, const float* __restrict__ part) {
+__global__ void wgrad_tc_reduce_kernel(const WgArgs a, const float* __restrict__ part, int budget) {
   const WgJob& head = a.job[blockIdx.y];
   if (!head.chain_head) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int F = head.F, K = head.K;
   if (i >= F * K + (head.db ? F : 0)) return;
+  WgPlan plan;
+  wg_plan(a, budget, plan);
   const bool is_b = i >= F * K;
   const int n = is_b ? i - F * K : i / K;
   const int j = is_b ? head.npad - 1 : i - n * K;
   float s = 0.f;
   for (int jj = blockIdx.y; jj >= 0; jj = a.job[jj].next) {
-    const WgJob& jb = a.job[jj];
-    const float* p = part + (size_t)jb.cta0 * (FP * FP) + (size_t)n * FP + j;
-    for (int c = 0; c < jb.nctas; ++c) s += p[(size_t)c * (FP * FP)];
+    const float* p = part + (size_t)plan.cta0[jj] * (FP * FP) + (size_t)n * FP + j;
+    const int nctas = plan.cta0[jj + 1] - plan.cta0[jj];
+    for (int c = 0; c < nctas; ++c) s += p[(size_t)c * (FP * FP)];
   }
   if (is_b) head.db[n] += s;
   else head.dW[(size_t)n * head.ld + head.col0 + j] += s;
@@ -332,32 +366,13 @@ int tc_wgrad_batch(cudaStream_t st, tc::WgArgs& a, float* part, int max_ctas) {
   if (a.njobs <= 0) return AGX_OK;
   static thread_local DeviceOnce once;
   if (once.need()) AGX_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
-  int64_t total_stages = 0;
-  for (int i = 0; i < a.njobs; ++i) total_stages += (a.job[i].M + WG_ROWS - 1) / WG_ROWS;
-  // every CTA the same number of stages, the smallest that fits the whole batch into one wave (one CTA per SM)
-  const int budget = num_sms();
-  int64_t spc = (total_stages + budget - 1) / budget;
-  for (;; ++spc) {
-    int64_t n = 0;
-    for (int i = 0; i < a.njobs; ++i) n += ((a.job[i].M + WG_ROWS - 1) / WG_ROWS + spc - 1) / spc;
-    if (n <= budget) break;
-  }
-  int cta = 0;
-  for (int i = 0; i < a.njobs; ++i) {
-    WgJob& j = a.job[i];
-    const int64_t stages = (j.M + WG_ROWS - 1) / WG_ROWS;
-    j.stages_per_cta = (int)spc;
-    j.nctas = (int)((stages + spc - 1) / spc);
-    j.cta0 = cta;
-    cta += j.nctas;
-  }
-  AGX_REQUIRE(cta <= max_ctas, AGX_ERR_CAPACITY, "tc_wgrad: %d partial products > %d reserved", cta, max_ctas);
+  const int budget = max_ctas < num_sms() ? max_ctas : num_sms();   // one wave, one CTA per SM; the device plans the split
   a.part = part;
   { ProfScope ps(AGX_KIND_OTHER, st);
-    wgrad_tc_kernel<<<cta, WG_THREADS, WG_SMEM, st>>>(a); }
+    wgrad_tc_kernel<<<budget, WG_THREADS, WG_SMEM, st>>>(a); }
   AGX_LAUNCH_CHECK();
   { ProfScope ps(AGX_KIND_OTHER, st);
-    wgrad_tc_reduce_kernel<<<dim3((FP * FP + FP + 255) / 256, a.njobs), 256, 0, st>>>(a, part); }
+    wgrad_tc_reduce_kernel<<<dim3((FP * FP + FP + 255) / 256, a.njobs), 256, 0, st>>>(a, part, budget); }
   AGX_LAUNCH_CHECK();
   return AGX_OK;
 }

@@ -20,7 +20,6 @@ struct WgJob {
   int bias_col;
   int ld, col0, F, K;
   int chain_head, next; // jobs adding into the same destination form a chain (next = -1 ends it); only the head reduces
-  int cta0, nctas, stages_per_cta;   // filled by tc_wgrad_batch
 };
 struct WgArgs {
   WgJob job[WG_MAX_JOBS];

@@ -611,7 +611,6 @@ struct WgradBatch {
     j.ld = ld; j.col0 = col0; j.F = F; j.K = K; j.chain_head = 1; j.next = -1;
     for (int i = a.njobs - 2; i >= 0; --i)   // same destination as an earlier job of the batch: summed by that job's reduction
       if (a.job[i].dW == dW && a.job[i].col0 == col0 && a.job[i].next < 0) { a.job[i].next = a.njobs - 1; j.chain_head = 0; j.db = nullptr; break; }
-    j.cta0 = j.nctas = j.stages_per_cta = 0;
     return AGX_OK;
   }
   int flush() {
