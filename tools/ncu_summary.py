@@ -10,7 +10,8 @@ import sys
 
 KIND = [("edge_aggregate", "edge_aggregate"), ("tc_edge_encoder", "edge_encoder"), ("tc_node_encoder", "node_encoder"),
         ("tc_node_update_kernel<(bool)0>", "node_update"), ("tc_node_update_kernel<(bool)1>", "node_update_head"),
-        ("tc_node_update_kernel<0>", "node_update"), ("tc_node_update_kernel<1>", "node_update_head"), ("knn_rows", "graph_knn_rows")]
+        ("tc_node_update_kernel<0>", "node_update"), ("tc_node_update_kernel<1>", "node_update_head"),
+        ("tc_node_update_kernel<0,", "node_update"), ("tc_node_update_kernel<1,", "node_update_head"), ("knn_rows", "graph_knn_rows")]
 COLS = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "rdGB"), ("dram__bytes_write.sum", "wrGB"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
