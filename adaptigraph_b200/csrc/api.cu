@@ -26,6 +26,11 @@ int64_t& launch_counter() {
   return n;
 }
 
+int pdl_mask() {
+  static const int mask = [] { const char* e = getenv("AGX_PDL"); return e ? atoi(e) : 3; }();
+  return mask;
+}
+
 static thread_local int g_sm_share = 0;   // > 0: persistent grids are sized for this many SMs (two half-batches side by side)
 void set_sm_share(int n) { g_sm_share = n; }
 

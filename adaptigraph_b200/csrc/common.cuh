@@ -70,6 +70,40 @@ struct DeviceOnce {
 };
 void set_sm_share(int n);   // thread-local: size persistent grids for n SMs (0 = all)
 
+// ---- programmatic dependent launch: a kernel of the rollout / forward chain is launched with the stream-serialisation
+// attribute, so its launch (and, once the previous grid's CTAs have exited, its prologue: barrier init, tensor-memory allocation,
+// shared-memory set-up) no longer waits for the previous grid's completion to be processed; every such kernel executes
+// pdl_wait() before its first global-memory access -- the wait returns once ALL earlier grids have completed and their writes
+// are visible, so the ordering guarantees are those of a plain stream.  AGX_PDL is a mask (default 3; 0 = plain launches, the
+// device-side instructions are then no-ops).
+// Measured (profiles/r02H_pdl_ab.txt, cloth-2k x 128 rollout as a CUDA graph): attribute alone +0.5 % (132.0-132.3 M vs
+// 131.1-131.7 M particle-steps/s); with an EARLY griddepcontrol.launch_dependents at the top of the chain / aggregate kernels
+// -8 % (121.5 M; -7 % at 16 graphs), on the small kernels +-0 -- so no kernel triggers early (AGX_PDL_EARLY_TRIGGER restores it).
+int pdl_mask();   // AGX_PDL: bit 0 = the small kernels (graph builder, rollout_advance), bit 1 = the chain / aggregate kernels
+constexpr int PDL_SMALL = 1, PDL_BIG = 2;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+#ifdef AGX_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_mask() & cls) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- optional per-kernel timing (agx_profile_*): CUDA events recorded on the launch stream
 // around every kernel, summed per kernel kind when read.  Off by default.
 struct ProfScope {

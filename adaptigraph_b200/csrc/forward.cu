@@ -360,6 +360,8 @@ __global__ void __launch_bounds__(256) rollout_advance_kernel(float* __restrict_
   __shared__ float red_a[8], red_b[8];
   __shared__ float y_s;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();
+  pdl_trigger();
   const float* pb = pred + (size_t)b * pred_stride_b;
   float va = (y_mode == AGX_Y_MIN) ? __int_as_float(0x7f800000) : 0.f, vb = 0.f;
   for (int n = tid; n < n_p; n += 256) {
@@ -731,7 +733,7 @@ int agx_rollout(const AgxModelDims* dims, const void* packed_weights, const AgxR
       nfeat_next = fws.nfeat;
     }
     { ProfScope ps(AGX_KIND_ROLLOUT_ADVANCE, s);
-      rollout_advance_kernel<<<dim3(Bh, (r->N + 255) / 256), 256, 0, s>>>(state, action, mask, pred_t, stride, r->N, r->n_p, r->y_mode, r->gripper_raise, nfeat_next,
+      launch_pdl(PDL_SMALL, rollout_advance_kernel, dim3(Bh, (r->N + 255) / 256), 256, 0, s, state, action, mask, pred_t, stride, r->N, r->n_p, r->y_mode, r->gripper_raise, nfeat_next,
                                                 g.attrs, g.p_instance); }
     AGX_LAUNCH_CHECK();
     return AGX_OK;

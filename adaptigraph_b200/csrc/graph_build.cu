@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(T) sort_cells_kernel(const float* __restrict__
   __shared__ float lo_s[2], w_s[2];
   __shared__ int axis_s[2], n_s[2];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();      // the positions come from the previous kernel of the stream (common.cuh: programmatic dependent launch)
+  pdl_trigger();
   const float* p = pos + (size_t)b * pos_stride_b;
   const uint8_t* mk = mask + (size_t)b * N;
   const float INF = __int_as_float(0x7f800000);
@@ -278,6 +280,8 @@ __global__ void __launch_bounds__(G1_THREADS) knn_rows_kernel(
   extern __shared__ float smem[];
   const int b = blockIdx.y, tid = threadIdx.x;
   const size_t gb = (size_t)b * N;
+  pdl_wait();
+  pdl_trigger();
   const float t2 = thr2[b];
   const int na = grid_dims[4 * b], nb = grid_dims[4 * b + 1], rings = grid_dims[4 * b + 2];
   const float wq = __int_as_float(grid_dims[4 * b + 3]);
@@ -392,6 +396,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK) degrees_scan_kernel(
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = blockIdx.x * SCAN_BLOCK + tid;
   int d = 0;
+  pdl_wait();
+  pdl_trigger();
   if (r < rows) {
     const int b = r / N;
     bool kb, at;
@@ -473,6 +479,8 @@ __global__ void __launch_bounds__(256) fill_rows_kernel(
     int32_t* __restrict__ send, int32_t* __restrict__ recv, int64_t cap, int32_t* __restrict__ n_edges,
     int32_t* __restrict__ status) {
   const int r = blockIdx.x * 256 + threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   if (r >= rows) return;
   const int b = r / N, n = r - b * N;
   const int start = lpre[r] + blk[r / SCAN_BLOCK];
@@ -572,23 +580,23 @@ int graph_build_impl(const float* pos, int64_t pos_stride_b, const uint8_t* mask
   const int nblk = (rows + SCAN_BLOCK - 1) / SCAN_BLOCK;
   { ProfScope ps(AGX_KIND_GRAPH_SORT, st);
     if (N <= 512)
-      sort_cells_kernel<256><<<B, 256, 0, st>>>(pos, pos_stride_b, mask, tool_mask, thr2, N, ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx,
+      launch_pdl(PDL_SMALL, sort_cells_kernel<256>, B, 256, 0, st, pos, pos_stride_b, mask, tool_mask, thr2, N, ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx,
                                                 ws.sflag, ws.cell_start, ws.grid_dims, cta ? ws.tools : nullptr, ws.n_tools, ws.flags, ws.ticket);
     else
-      sort_cells_kernel<1024><<<B, 1024, 0, st>>>(pos, pos_stride_b, mask, tool_mask, thr2, N, ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx,
+      launch_pdl(PDL_SMALL, sort_cells_kernel<1024>, B, 1024, 0, st, pos, pos_stride_b, mask, tool_mask, thr2, N, ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx,
                                                   ws.sflag, ws.cell_start, ws.grid_dims, cta ? ws.tools : nullptr, ws.n_tools, ws.flags, ws.ticket); }
   AGX_LAUNCH_CHECK();
   dim3 g1((N + G1_ROWS_PER_CTA - 1) / G1_ROWS_PER_CTA, B);
   { ProfScope ps(AGX_KIND_GRAPH_KNN, st);
-    knn_rows_kernel<<<g1, G1_THREADS, smem, st>>>(ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx, ws.sflag, ws.cell_start, ws.grid_dims, thr2, N, topk,
+    launch_pdl(PDL_SMALL, knn_rows_kernel, g1, G1_THREADS, smem, st, ws.sx, ws.sy, ws.sz, ws.scell, ws.sidx, ws.sflag, ws.cell_start, ws.grid_dims, thr2, N, topk,
                                                    cta && sem == AGX_SEM_BATCH, N, ws.cand, ws.cnt, ws.flags); }
   AGX_LAUNCH_CHECK();
   { ProfScope ps(AGX_KIND_GRAPH_SCAN, st);
-    degrees_scan_kernel<<<nblk, SCAN_BLOCK, 0, st>>>(ws.cnt, mask, tool_mask, ws.flags, ws.n_tools, rows, N, cta, sem,
+    launch_pdl(PDL_SMALL, degrees_scan_kernel, nblk, SCAN_BLOCK, 0, st, ws.cnt, mask, tool_mask, ws.flags, ws.n_tools, rows, N, cta, sem,
                                                       ws.deg, ws.lpre, ws.blk, ws.ticket, ws.total, row_ptr + rows); }
   AGX_LAUNCH_CHECK();
   { ProfScope ps(AGX_KIND_GRAPH_FILL, st);
-    fill_rows_kernel<<<(rows + 255) / 256, 256, 0, st>>>(ws.cand, ws.cnt, ws.lpre, ws.blk, ws.total, mask, tool_mask, ws.flags,
+    launch_pdl(PDL_SMALL, fill_rows_kernel, (rows + 255) / 256, 256, 0, st, ws.cand, ws.cnt, ws.lpre, ws.blk, ws.total, mask, tool_mask, ws.flags,
                                                       ws.n_tools, ws.tools, rows, N, topk, cta, sem, row_ptr, send, recv,
                                                       cap, n_edges, status); }
   AGX_LAUNCH_CHECK();

@@ -111,6 +111,8 @@ __device__ __forceinline__ uint32_t chain_setup(Shared& sh, uint8_t* smem_raw, c
     fence_mbar_init();
   }
   if (warp == MMA_WARP0) tmem_alloc(sh.tmem_ptr, TMEM_COLS);
+  pdl_wait();      // nothing above touches global memory: barrier init and the tensor-memory allocation overlap the previous kernel's tail
+  pdl_trigger();
   const float4* m = reinterpret_cast<const float4*>(blob + L.meta);
 #pragma unroll
   for (int l = 0; l < NL; ++l) meta[l] = m[prog[l].layer];
@@ -823,6 +825,8 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
   __shared__ __align__(16) int32_t ids[2][AGG_NODES][AGG_BATCH];   // first AGG_BATCH sender ids of every row of this / the next group
   const int slot = threadIdx.x / (FP / 4), j = threadIdx.x - slot * (FP / 4);
   if (threadIdx.x < 3 * AGG_NODES) (&smax[0][0])[threadIdx.x] = 0;
+  pdl_wait();
+  pdl_trigger();
   const int n_groups = (rows + AGG_NODES - 1) / AGG_NODES, G = gridDim.x;
   // float4 j of a row in the blocked layout (tc_chain.cuh: blk_off), as a 32-bit float4 index (the host checks that it fits):
   // (row / 128) * tile + piece * 128 * 4 + (row % 128) * (floats4 per piece row) + j % 4; the narrow last piece has two float4 per
@@ -997,6 +1001,8 @@ __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill (generic proxy) is ordered before the bulk copies (async proxy)
   __syncthreads();
+  pdl_wait();      // the shared-memory set-up above overlaps the previous kernel's tail
+  pdl_trigger();
   const int n_groups = (rows + A16_NODES - 1) / A16_NODES, G = gridDim.x;
   // this thread's 4 columns [4j, 4j + 4): a quarter of piece p = j >> 2 (the narrow last piece has two quarters)
   const int p = j >> 2;
@@ -1218,8 +1224,8 @@ int tc_node_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
              w.nfeat, w.P0, w.A, w.Qr0, w.Qs0, w.rowmaxP0, w.rowmaxA, w.S0, nullptr, nullptr, nullptr, nullptr};
   if (w.save) { a.sv_p_in = w.save->p_in; a.sv_h1 = w.save->h1; a.sv_h2 = w.save->h2; a.sv_penc = w.save->penc; }
   { ProfScope ps(AGX_KIND_NODE_ENCODER, st);
-    if (w.save) tc_node_encoder_kernel<true><<<tiles < num_sms() ? tiles : num_sms(), THREADS, SMEM_BYTES, st>>>(a);
-    else tc_node_encoder_kernel<false><<<tiles < num_sms() ? tiles : num_sms(), THREADS, SMEM_BYTES, st>>>(a); }
+    if (w.save) launch_pdl(PDL_BIG, tc_node_encoder_kernel<true>, tiles < num_sms() ? tiles : num_sms(), THREADS, SMEM_BYTES, st, a);
+    else launch_pdl(PDL_BIG, tc_node_encoder_kernel<false>, tiles < num_sms() ? tiles : num_sms(), THREADS, SMEM_BYTES, st, a); }
   AGX_LAUNCH_CHECK();
   return AGX_OK;
 }
@@ -1248,9 +1254,9 @@ int tc_edge_encoder(const AgxGraphIn* g, const float* wts, const PackedLayout& P
   if (w.save) { a.sv_rel_in = w.save->rel_in; a.sv_g1 = w.save->g1; a.sv_g2 = w.save->g2; a.sv_renc = w.save->renc; }
   { ProfScope ps(AGX_KIND_EDGE_ENCODER, st);
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    if (w.save) tc_edge_encoder_kernel<false, true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
-    else if (mixed) tc_edge_encoder_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
-    else tc_edge_encoder_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(a); }
+    if (w.save) launch_pdl(PDL_BIG, tc_edge_encoder_kernel<false, true>, grid, THREADS, SMEM_BYTES, st, a);
+    else if (mixed) launch_pdl(PDL_BIG, tc_edge_encoder_kernel<true>, grid, THREADS, SMEM_BYTES, st, a);
+    else launch_pdl(PDL_BIG, tc_edge_encoder_kernel<false>, grid, THREADS, SMEM_BYTES, st, a); }
   AGX_LAUNCH_CHECK();
   return AGX_OK;
 }
@@ -1284,7 +1290,7 @@ int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, bo
                 "edge_aggregate: %lld rows / %lld relations exceed the 32-bit feature index", (long long)rows, (long long)g->E_cap);
     const int64_t groups = (rows + A16_NODES - 1) / A16_NODES, resident = (int64_t)num_sms() * AGX_A16_CTAS;
     { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
-      edge_aggregate_c16_kernel<<<(unsigned)(groups < resident ? groups : resident), A16_THREADS, A16_SMEM, st>>>(
+      launch_pdl(PDL_BIG, edge_aggregate_c16_kernel, (unsigned)(groups < resident ? groups : resident), A16_THREADS, A16_SMEM, st, 
           g->row_ptr, g->send, (int)rows, g->N, g->N == 1 ? 0xffffffffu : (uint32_t)((1ull << 32) / (uint64_t)g->N), (int)g->E_cap,
           reinterpret_cast<const uint8_t*>(w.C),
           reinterpret_cast<const float4*>(Qr),
@@ -1297,7 +1303,7 @@ int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, bo
               "edge_aggregate: %lld rows / %lld relations exceed the 32-bit feature index", (long long)rows, (long long)g->E_cap);
   const int64_t groups = (rows + AGG_NODES - 1) / AGG_NODES, resident = (int64_t)num_sms() * AGG_CTAS_PER_SM;
   { ProfScope ps(AGX_KIND_EDGE_AGGREGATE, st);
-    edge_aggregate_split_kernel<<<(unsigned)(groups < resident ? groups : resident), AGG_THREADS, 0, st>>>(
+    launch_pdl(PDL_BIG, edge_aggregate_split_kernel, (unsigned)(groups < resident ? groups : resident), AGG_THREADS, 0, st, 
         g->row_ptr, g->send, (int)rows, g->N, (int)g->E_cap, reinterpret_cast<const float4*>(w.C), reinterpret_cast<const float4*>(Qr),
         reinterpret_cast<const float4*>(Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max,
         w.save ? reinterpret_cast<float4*>(w.save->agg_f32) : nullptr); }
@@ -1319,12 +1325,12 @@ int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL
   if (w.save) { a.sv_P = w.save->P_next; a.sv_u1 = w.save->u1; a.sv_u2 = w.save->u2; }
   if (last) {
     ProfScope ps(AGX_KIND_NODE_HEAD, st);
-    if (w.save) tc_node_update_kernel<true, true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
-    else tc_node_update_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
+    if (w.save) launch_pdl(PDL_BIG, tc_node_update_kernel<true, true>, grid, THREADS, SMEM_BYTES, st, a);
+    else launch_pdl(PDL_BIG, tc_node_update_kernel<true>, grid, THREADS, SMEM_BYTES, st, a);
   } else {
     ProfScope ps(AGX_KIND_NODE_UPDATE, st);
-    if (w.save) tc_node_update_kernel<false, true><<<grid, THREADS, SMEM_BYTES, st>>>(a);
-    else tc_node_update_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(a);
+    if (w.save) launch_pdl(PDL_BIG, tc_node_update_kernel<false, true>, grid, THREADS, SMEM_BYTES, st, a);
+    else launch_pdl(PDL_BIG, tc_node_update_kernel<false>, grid, THREADS, SMEM_BYTES, st, a);
   }
   AGX_LAUNCH_CHECK();
   return AGX_OK;
