@@ -34,7 +34,7 @@ LAYER_NAMES = [
 EXPORTS = [
     "agx_version", "agx_last_error", "agx_launch_count",
     "agx_packed_weights_bytes", "agx_pack_weights",
-    "agx_graph_workspace_bytes", "agx_graph_build", "agx_onehot_to_ids", "agx_edges_to_onehot", "agx_fps", "agx_chamfer",
+    "agx_graph_workspace_bytes", "agx_graph_build", "agx_onehot_to_ids", "agx_edges_to_onehot", "agx_fps", "agx_fps_radii", "agx_chamfer",
     "agx_running_cost_workspace_bytes", "agx_running_cost",
     "agx_forward_workspace_bytes", "agx_forward",
     "agx_rollout_workspace_bytes", "agx_rollout",
@@ -92,6 +92,7 @@ def _load() -> C.CDLL:
         "agx_onehot_to_ids": (C.c_int, [vp, i32, i32, i32, vp, vp]),
         "agx_edges_to_onehot": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "agx_fps": (C.c_int, [vp, vp, i32, i32, i32, vp, C.c_double, vp, vp, vp]),
+        "agx_fps_radii": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
         "agx_chamfer": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
         "agx_running_cost_workspace_bytes": (sz, [i32, i32]),
         "agx_running_cost": (C.c_int, [vp, vp, i32, vp, vp, i32, vp, i32, i32, C.c_float, i32, i32, i32, vp, sz, vp, vp]),

@@ -27,6 +27,7 @@ __device__ __forceinline__ void argmax_merge(float& v, int& i, float ov, int oi)
 template <bool SQRT_DOMAIN>
 __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restrict__ pos, const int32_t* __restrict__ n_points, int N,
                                                           int max_samples, const int32_t* __restrict__ start_idx, double radius,
+                                                          const double* __restrict__ radii /* per cloud, or null */,
                                                           int32_t* __restrict__ idx_out, int32_t* __restrict__ n_out) {
   extern __shared__ float fps_smem[];
   float* px = fps_smem;
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
   __shared__ int red_i[32];
   __shared__ int cur_s;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (radii) radius = radii[b];
   const int n = n_points ? min(max(n_points[b], 0), N) : N;
   const float* p = pos + (size_t)b * N * 3;
   int32_t* out = idx_out + (size_t)b * max_samples;
@@ -90,7 +92,8 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
 template <bool SQRT_DOMAIN>
 __global__ void __launch_bounds__(FPS_THREADS) fps_cluster_kernel(const float* __restrict__ pos, const int32_t* __restrict__ n_points, int N,
                                                                   int chunk, int max_samples, const int32_t* __restrict__ start_idx,
-                                                                  double radius, int32_t* __restrict__ idx_out, int32_t* __restrict__ n_out) {
+                                                                  double radius, const double* __restrict__ radii,
+                                                                  int32_t* __restrict__ idx_out, int32_t* __restrict__ n_out) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ float fps_smem[];
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_cluster_kernel(const float* _
   __shared__ int best_i[2];
   const int CL = (int)cluster.num_blocks(), q = (int)cluster.block_rank();
   const int b = blockIdx.x / CL, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (radii) radius = radii[b];
   const int n = n_points ? min(max(n_points[b], 0), N) : N;
   const float* p = pos + (size_t)b * N * 3;
   int32_t* out = idx_out + (size_t)b * max_samples;
@@ -163,7 +167,7 @@ constexpr size_t FPS_CTA_SMEM = 200 * 1024;        // 12800 points per CTA
 constexpr int FPS_MAX_CLUSTER = 16;               // non-portable cluster size: 204800 points per cloud
 
 static int fps_cluster_launch(const float* pos, const int32_t* n_points, int B, int N, int max_samples, const int32_t* start_idx,
-                              double radius, int32_t* idx_out, int32_t* n_out, cudaStream_t st) {
+                              double radius, const double* radii, int32_t* idx_out, int32_t* n_out, cudaStream_t st) {
   int CL = 2;
   while (CL < FPS_MAX_CLUSTER && (size_t)((N + CL - 1) / CL) * 16 > FPS_CTA_SMEM) CL *= 2;
   const int chunk = (N + CL - 1) / CL;
@@ -184,7 +188,7 @@ static int fps_cluster_launch(const float* pos, const int32_t* n_points, int B, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ProfScope ps(AGX_KIND_OTHER, st);
-    AGX_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, pos, n_points, N, chunk, max_samples, start_idx, radius, idx_out, n_out));
+    AGX_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, pos, n_points, N, chunk, max_samples, start_idx, radius, radii, idx_out, n_out));
     return AGX_OK;
   };
   if (int rc = radius < 0.0 ? launch(fps_cluster_kernel<false>) : launch(fps_cluster_kernel<true>)) return rc;
@@ -196,13 +200,13 @@ static int fps_cluster_launch(const float* pos, const int32_t* n_points, int B, 
 
 extern "C" {
 
-int agx_fps(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int32_t max_samples, const int32_t* start_idx,
-            double radius, int32_t* idx_out, int32_t* n_out, agx_stream_t stream) {
+static int fps_impl(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int32_t max_samples, const int32_t* start_idx,
+                    double radius, const double* radii, int32_t* idx_out, int32_t* n_out, agx_stream_t stream) {
   using namespace agx;
   AGX_REQUIRE(pos && start_idx && idx_out && n_out, AGX_ERR_ARG, "fps: null pointer argument");
   AGX_REQUIRE(B > 0 && N > 0 && max_samples > 0, AGX_ERR_ARG, "fps: B=%d N=%d max_samples=%d must be positive", B, N, max_samples);
   cudaStream_t st0 = static_cast<cudaStream_t>(stream);
-  if ((size_t)N * 16 > FPS_CTA_SMEM) return agx::fps_cluster_launch(pos, n_points, B, N, max_samples, start_idx, radius, idx_out, n_out, st0);
+  if ((size_t)N * 16 > FPS_CTA_SMEM) return agx::fps_cluster_launch(pos, n_points, B, N, max_samples, start_idx, radius, radii, idx_out, n_out, st0);
   const size_t smem = (size_t)N * 16;
   cudaStream_t st = st0;
   static thread_local size_t set_count = 0, set_radius = 0;
@@ -214,17 +218,28 @@ int agx_fps(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int
       set_count = smem;
     }
     ProfScope ps(AGX_KIND_OTHER, st);
-    fps_kernel<false><<<B, FPS_THREADS, smem, st>>>(pos, n_points, N, max_samples, start_idx, radius, idx_out, n_out);
+    fps_kernel<false><<<B, FPS_THREADS, smem, st>>>(pos, n_points, N, max_samples, start_idx, radius, nullptr, idx_out, n_out);
   } else {
     if (smem > 48 * 1024 && smem > set_radius) {
       AGX_CUDA_OK(cudaFuncSetAttribute(fps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       set_radius = smem;
     }
     ProfScope ps(AGX_KIND_OTHER, st);
-    fps_kernel<true><<<B, FPS_THREADS, smem, st>>>(pos, n_points, N, max_samples, start_idx, radius, idx_out, n_out);
+    fps_kernel<true><<<B, FPS_THREADS, smem, st>>>(pos, n_points, N, max_samples, start_idx, radius, radii, idx_out, n_out);
   }
   AGX_LAUNCH_CHECK();
   return AGX_OK;
+}
+
+int agx_fps(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int32_t max_samples, const int32_t* start_idx,
+            double radius, int32_t* idx_out, int32_t* n_out, agx_stream_t stream) {
+  return fps_impl(pos, n_points, B, N, max_samples, start_idx, radius, nullptr, idx_out, n_out, stream);
+}
+
+int agx_fps_radii(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int32_t max_samples, const int32_t* start_idx,
+                  const double* radii, int32_t* idx_out, int32_t* n_out, agx_stream_t stream) {
+  AGX_REQUIRE(radii, AGX_ERR_ARG, "fps_radii: null radius array");
+  return fps_impl(pos, n_points, B, N, max_samples, start_idx, 0.0, radii, idx_out, n_out, stream);
 }
 
 }  // extern "C"

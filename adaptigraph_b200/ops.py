@@ -163,6 +163,23 @@ def _(pos, n_points, start_idx, max_samples, radius):
     return pos.new_empty((B, max_samples), dtype=torch.int32), pos.new_empty((B,), dtype=torch.int32)
 
 
+def fps_radii(pos: Tensor, n_points: Tensor, start_idx: Tensor, max_samples: int, radii: Tensor) -> Tuple[Tensor, Tensor]:
+    """`fps` in its radius form with one radius per cloud: radii (B) float64 (agx_fps_radii)."""
+    _need_cuda(pos, n_points, start_idx, radii)
+    pos = _f32(pos)
+    B, N, _ = pos.shape
+    n_points = n_points.to(torch.int32).contiguous()
+    start_idx = start_idx.to(torch.int32).contiguous()
+    radii = radii.to(torch.float64).contiguous()
+    if radii.numel() != B or bool((radii < 0).any()):
+        raise ValueError("fps_radii: one non-negative radius per cloud")
+    idx = torch.zeros(B, max_samples, dtype=torch.int32, device=pos.device)
+    cnt = torch.empty(B, dtype=torch.int32, device=pos.device)
+    L.check(lib.agx_fps_radii(_ptr(pos), _ptr(n_points), B, N, max_samples, _ptr(start_idx), _ptr(radii), _ptr(idx), _ptr(cnt),
+                              _stream()), "agx_fps_radii")
+    return idx, cnt
+
+
 @torch.library.custom_op("agx::chamfer", mutates_args=())
 def chamfer(x: Tensor, y: Tensor) -> Tensor:
     """planning/losses.py:4-10: x (B,N,3), y (1,M,3) or (B,M,3) -> (B) symmetric mean-of-min distances."""

@@ -72,15 +72,19 @@ def fps(obj_kp_start, max_nobj, fps_radius_range, verbose=False):
     return np.array(fps_idx)
 
 
-def fps_batch(pos: torch.Tensor, n_points: torch.Tensor, max_nobj: int, radius: float, start_idx: torch.Tensor,
+def fps_batch(pos: torch.Tensor, n_points: torch.Tensor, max_nobj: int, radius, start_idx: torch.Tensor,
               start_idx_2: torch.Tensor):
     """Device-resident batched form of `fps` for B clouds at once (no host round trip): pos (B,N,3) CUDA, n_points (B),
-    start_idx (B) first pick among the cloud's points, start_idx_2 (B) first pick among the max_nobj survivors.
+    start_idx (B) first pick among the cloud's points, start_idx_2 (B) first pick among the max_nobj survivors; `radius` is a
+    float or a (B) tensor (one thinning radius per cloud, as a training batch draws them: graph.py:17-20).
     Returns idx (B, max_nobj) int32 indices into the clouds and counts (B)."""
     B, N, _ = pos.shape
     k = min(int(max_nobj), N)
     idx1, cnt1 = ops.fps(pos, n_points, start_idx, k, -1.0)
     cnt1 = torch.minimum(cnt1, n_points.to(torch.int32))          # a cloud with fewer than k points keeps them all once
     sub = torch.gather(pos, 1, idx1.to(torch.int64).unsqueeze(-1).expand(B, k, 3))
-    idx2, cnt2 = ops.fps(sub, cnt1, start_idx_2, k, float(radius))
+    if torch.is_tensor(radius):
+        idx2, cnt2 = ops.fps_radii(sub, cnt1, start_idx_2, k, radius.to(pos.device))
+    else:
+        idx2, cnt2 = ops.fps(sub, cnt1, start_idx_2, k, float(radius))
     return torch.gather(idx1, 1, idx2.to(torch.int64)), cnt2

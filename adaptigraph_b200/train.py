@@ -29,9 +29,10 @@ def unroll_loss(model, data: Dict[str, torch.Tensor], n_future: int, edges: Opti
     relations stay fixed, the prediction replaces the object rows of the newest history frame built from eef_future, the
     action becomes action_future[:, fi].  `data` is not modified."""
     data = dict(data)
+    own = data.pop("edges", None)                               # a batch of dataset.DynDataset carries its EdgeList
     future_state, future_eef, future_action = data["state_future"], data["eef_future"], data["action_future"]
     if edges is None:
-        edges = edges_from_onehots(data["Rr"], data["Rs"])     # once, not once per forward
+        edges = own if own is not None else edges_from_onehots(data["Rr"], data["Rs"])     # once, not once per forward
     loss_sum = 0
     for fi in range(n_future):
         gt_state = future_state[:, fi]
@@ -126,14 +127,14 @@ class Trainer:
         loss as a device scalar (no host synchronisation)."""
         self.model.train()
         if edges is None:
-            edges = edges_from_onehots(data["Rr"], data["Rs"])
+            edges = data["edges"] if data.get("edges") is not None else edges_from_onehots(data["Rr"], data["Rs"])
         if not self.cuda_graph:
             return self._step_impl(data, edges)
         return self._step_graphed(data, edges)
 
     # ------------------------------------------------------------------ CUDA-graph replay
     def _step_graphed(self, data, edges) -> torch.Tensor:
-        tens = {k: v for k, v in data.items() if torch.is_tensor(v) and k not in ("Rr", "Rs")}
+        tens = {k: v for k, v in data.items() if torch.is_tensor(v) and k not in ("Rr", "Rs")}    # an "edges" entry is not a tensor
         if self._graph is None:
             self._static = {k: v.clone() for k, v in tens.items()}
             self._static_edges = EdgeList(edges.row_ptr.clone(), edges.send.clone(), edges.recv.clone(), edges.n_edges.clone(),
@@ -195,3 +196,64 @@ class Trainer:
                 raise ValueError("per-parameter step counts differ; the fused optimiser keeps one")
             self.step_count.fill_(steps.pop() if steps else 0)
         self._graph = None     # the hyper-parameters are baked into a captured step: capture again on the next call
+
+
+# ---------------------------------------------------------------------- the epoch loop of train.py:19-147
+def train(config: dict, cuda_graph: bool = False, log=print) -> Dict[str, list]:
+    """`train(config)` of src/dynamics/train/train.py with the reference's YAML dict: the same phases, iteration counts, seeds,
+    sample order, loss and checkpoint files (`checkpoints/model_<epoch>.pth`, `latest.pth`, `latest_optim.pth` in torch.optim.Adam's
+    format), on `dataset.DynDataset` batches (sparse relations built on the device) and `Trainer.step`.  The loss-curve PNG of
+    train.py:125-141 is not drawn; the two curves are returned instead ({"train": [...], "valid": [...]}, one mean per epoch)."""
+    import os
+    import random
+    import time
+
+    import numpy as np
+
+    from .dataset import DynDataset, make_loader
+    from .model import DynamicsPredictor
+    dataset_config, train_config = config["dataset_config"], config["train_config"]
+    model_config, material_config = config["model_config"], config["material_config"]
+    out_dir = os.path.join(train_config["out_dir"], dataset_config["data_name"])
+    os.makedirs(os.path.join(out_dir, "checkpoints"), exist_ok=True)
+    seed = train_config["random_seed"]                                       # set_seed (utils.py:108-114)
+    torch.manual_seed(seed); torch.cuda.manual_seed_all(seed); np.random.seed(seed); random.seed(seed)
+    device = torch.device("cuda", torch.cuda.current_device())
+    n_future, phases = dataset_config["n_future"], train_config["phases"]
+    datasets = {phase: DynDataset(dataset_config, material_config, phase, device=device) for phase in phases}
+    loaders = {phase: make_loader(datasets[phase], train_config["batch_size"], shuffle=(phase == "train")) for phase in phases}
+
+    def forever(loader):                                                     # dataloader_wrapper (utils.py:116-122)
+        while True:
+            for data in loader:
+                yield data
+    streams = {phase: forever(loaders[phase]) for phase in phases}
+    model = DynamicsPredictor(model_config, material_config, dataset_config, device)
+    model.to(device)
+    trainer = Trainer(model, lr=0.001, n_future=n_future, cuda_graph=cuda_graph)
+    curves: Dict[str, list] = {"train": [], "valid": []}
+    for epoch in range(train_config["n_epochs"]):
+        t0 = time.time()
+        for phase in phases:
+            losses = []
+            n_iters = train_config["n_iters_per_epoch"][phase] if train_config["n_iters_per_epoch"][phase] != -1 else len(datasets[phase])
+            for i in range(n_iters):
+                data = next(streams[phase])
+                if phase == "train":
+                    loss = trainer.step(data)
+                    if i % train_config["log_interval"] == 0:
+                        log(f"Epoch {epoch}, iter {i}, loss {loss.item()}")
+                        losses.append(loss.item())
+                else:
+                    model.eval()
+                    with torch.no_grad():
+                        losses.append(unroll_loss(model, data, n_future).item())
+            if phase == "valid":
+                log(f"\nEpoch {epoch}, valid loss {np.mean(losses)}")
+            curves[phase].append(float(np.mean(losses)) if losses else float("nan"))
+        if ((epoch + 1) < 100 and (epoch + 1) % 10 == 0) or (epoch + 1) % 100 == 0:
+            torch.save(model.state_dict(), os.path.join(out_dir, "checkpoints", f"model_{epoch + 1}.pth"))
+        torch.save(model.state_dict(), os.path.join(out_dir, "checkpoints", "latest.pth"))
+        torch.save(trainer.optimizer_state_dict(), os.path.join(out_dir, "checkpoints", "latest_optim.pth"))
+        log(f"Epoch {epoch} time: {time.time() - t0}\n")
+    return curves

@@ -150,6 +150,10 @@ AGX_API int agx_edges_to_onehot(const int32_t* row_ptr, const int32_t* send, int
  * shared memory, with identical picks. */
 AGX_API int agx_fps(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int32_t max_samples,
             const int32_t* start_idx, double radius, int32_t* idx_out, int32_t* n_out, agx_stream_t stream);
+/* The radius form with one radius per cloud (device array of B doubles, each >= 0): a training batch draws
+ * fps_radius ~ U(fps_radius_range) per sample (graph.py:17-20), and the batched loader thins all its samples in one launch. */
+AGX_API int agx_fps_radii(const float* pos, const int32_t* n_points, int32_t B, int32_t N, int32_t max_samples,
+                  const int32_t* start_idx, const double* radii, int32_t* idx_out, int32_t* n_out, agx_stream_t stream);
 
 /* ---- chamfer distance of the MPC error term (planning/losses.py:4-10, used at plan.py:36 / :146 on the rollout's frames):
  * out[b] = mean_m min_n |x[b,n] - y[m]| + mean_n min_m |x[b,n] - y[m]|.  x (B,N,3); y (M,3) shared by every sample
