@@ -487,8 +487,9 @@ static int forward_impl(const AgxModelDims* dims, const float* wts, const AgxGra
     // same stages, dense layers on the tcgen05 tensor cores (tc_forward.cu); MIXED: relation chain at 2 MMAs per K step, C as C16
     const bool mixed = precision == AGX_PREC_TC_MIXED;
     const size_t base = L.total * sizeof(float);
-    const TcFwdBuffers tb{ws.nfeat, ws.P, ws.A, ws.Qr, ws.Qs, ws.agg, ws.C, ws.rowmaxP, ws.rowmaxA, ws.agg_exp, ws.agg_max,
-                          ws.P0, ws.Qr0, ws.Qs0, ws.rowmaxP0, ws.S0};
+    TcFwdBuffers tb{ws.nfeat, ws.P, ws.A, ws.Qr, ws.Qs, ws.agg, ws.C, ws.rowmaxP, ws.rowmaxA, ws.agg_exp, ws.agg_max,
+                    ws.P0, ws.Qr0, ws.Qs0, ws.rowmaxP0, ws.S0};
+    tb.agg_f32 = mixed;
     if (reuse_node_products) {
       if (!nfeat_ready)                          // (agx_rollout's advance kernel has normally written the records already)
         if (int rc = tc_nfeat(g, tb, st)) return rc;

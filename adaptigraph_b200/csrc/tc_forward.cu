@@ -549,7 +549,9 @@ struct UpdArgs {
   float* sv_P; float* sv_u1; float* sv_u2;
 };
 
-template <bool LAST, bool SAVE = false>
+// AGG32: the aggregate arrives as plain blocked fp32 rows (edge_aggregate_c16: that kernel is bound by instruction issue, this one
+// by HBM with issue slots to spare, so the row maximum / scale / fp16 split of the aggregate moved here: same bits).
+template <bool LAST, bool SAVE = false, bool AGG32 = false>
 __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   constexpr LayerStep prog[3] = {{T_PP_AGG, 10, IN_PRODUCER, 3}, {LAST ? T_PRED0 : T_RP_RECV, 10, IN_EPILOGUE, AGX_MMA_NODE},
@@ -575,6 +577,29 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
     if ((LAST ? 13 : 3) == AGX_TC_TIMELINE && cx.lane == 0 && (cx.warp == 0 || cx.warp == 4)) cx.tl_region = 3 + cx.warp / 4;
 #endif
     int tile = slot_tile(0, cx.slot, n_tiles);
+    // AGG32: maximum of this thread's row of tile t over both column halves (agg >= 0: a sum of ReLUs)
+    auto agg_row_max = [&](int t) {
+      const int64_t rr = (int64_t)t * TILE + cx.row;
+      float mx = 0.f;
+      if (rr < rows) {
+        const float* agg = reinterpret_cast<const float*>(a.agg_split);
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int col0 = 32 * c + HW * cx.half;
+          const float* p = agg + blk_off(rr, col0);
+          float t8[8];
+          ldg256(p, t8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) mx = fmaxf(mx, t8[i]);
+          if (col0 < BLK_LAST) {
+            ldg256(p + 8, t8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mx = fmaxf(mx, t8[i]);
+          }
+        }
+      }
+      return epi_exchange<true>(sh, cx, mx);
+    };
     for (int k = 0; tile >= 0; ++k) {
       const int64_t r = (int64_t)tile * TILE + cx.row;
       const bool valid = r < rows;
@@ -589,29 +614,64 @@ __global__ void __launch_bounds__(THREADS, 1) tc_node_update_kernel(const UpdArg
           bulk_prefetch_l2(a.P_in + (int64_t)tile * BLK_TILE, BLK_TILE * 4);
         }
       }
-      // ---- producer: the aggregated relation effects arrive already scaled and split (edge_aggregate): copy to A
-      {
+      if (AGG32) {
+        // ---- producer: fp32 rows -> row maximum (both column halves) -> exact power-of-two scale -> split into A.  Two passes over
+        // the row, back to back: the second read comes from L2 (80 floats per thread would not stay in registers).  split16 rounds
+        // exactly like edge_aggregate_split_kernel's own conversion, so both routes put the same bits into tensor memory.
+        // Measured alternatives (cloth-2k x 128, ms per launch of this kernel; 0.180 with the pre-split input): these two passes
+        // 0.194; the maximum taken a tile ahead, behind the first layer's MMAs: 0.246 (a tile period streams ~130 MB through L2, the
+        // rows are gone when the split wants them); two partial maxima per row left by the aggregate: 0.183 here, +0.016 there.
+        const float* agg = reinterpret_cast<const float*>(a.agg_split);
+        const float mx = agg_row_max(tile);
+        cx.e_in = scale_exp(mx);
+        cx.bound_in = mx;                                // actual row maximum (W_agg has no bias: no constant column needed)
+        const float sc = exp2i(cx.e_in);
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
-          uint32_t hi[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lo[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          if (valid) {   // 16 words per (row, piece): 8 hi then 8 lo; the narrow last piece: 4 hi then 4 lo
-            const int col0 = 32 * c + HW * cx.half;
-            const uint32_t* piece = a.agg_split + blk_off(r, col0);
-            if (col0 < BLK_LAST) {
-              ldg256(reinterpret_cast<const float*>(piece), reinterpret_cast<float(&)[8]>(hi));
-              ldg256(reinterpret_cast<const float*>(piece + 8), reinterpret_cast<float(&)[8]>(lo));
-            } else {
-              uint32_t w[8];
-              ldg256(reinterpret_cast<const float*>(piece), reinterpret_cast<float(&)[8]>(w));
+          const int col0 = 32 * c + HW * cx.half;
+          float v[HW];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) { hi[i] = w[i]; lo[i] = w[4 + i]; }
+          for (int i = 0; i < HW; ++i) v[i] = 0.f;
+          if (valid) {
+            const float* p = agg + blk_off(r, col0);
+            float t[8];
+            ldg256(p, t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = t[i];
+            if (col0 < BLK_LAST) {
+              ldg256(p + 8, t);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 + i] = t[i];
             }
           }
-          epi_store_packed(cx, c, hi, lo);
+          epi_store_a(cx, c, v, sc);
         }
-        cx.e_in = valid ? a.agg_exp[r] : 0;
-        cx.bound_in = valid ? a.agg_max[r] : 0.f;     // actual row maximum (W_agg has no bias: no constant column needed)
         epi_signal(cx, &sh.bar_in[cx.slot]);
+      } else {
+        // ---- producer: the aggregated relation effects arrive already scaled and split (edge_aggregate): copy to A
+        {
+#pragma unroll
+          for (int c = 0; c < NCHUNK; ++c) {
+            uint32_t hi[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lo[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (valid) {   // 16 words per (row, piece): 8 hi then 8 lo; the narrow last piece: 4 hi then 4 lo
+              const int col0 = 32 * c + HW * cx.half;
+              const uint32_t* piece = a.agg_split + blk_off(r, col0);
+              if (col0 < BLK_LAST) {
+                ldg256(reinterpret_cast<const float*>(piece), reinterpret_cast<float(&)[8]>(hi));
+                ldg256(reinterpret_cast<const float*>(piece + 8), reinterpret_cast<float(&)[8]>(lo));
+              } else {
+                uint32_t w[8];
+                ldg256(reinterpret_cast<const float*>(piece), reinterpret_cast<float(&)[8]>(w));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { hi[i] = w[i]; lo[i] = w[4 + i]; }
+              }
+            }
+            epi_store_packed(cx, c, hi, lo);
+          }
+          cx.e_in = valid ? a.agg_exp[r] : 0;
+          cx.bound_in = valid ? a.agg_max[r] : 0.f;     // actual row maximum (W_agg has no bias: no constant column needed)
+          epi_signal(cx, &sh.bar_in[cx.slot]);
+        }
       }
       AGX_STAMP_EPI(cx, 31);
       {  // P <- relu((W_agg*agg + A_n) + P)   (model.py:36-40, :299-301)
@@ -935,8 +995,9 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
 
 
 // ------------------------------------------------------------------------------------ edge aggregate on C16 (AGX_PREC_TC_MIXED)
-// Same reduction with C in the 16-bit block format above.  38 threads per receiver (4 columns each: 8 bytes of C16, one float4 of
-// the blocked fp32 Qr / Qs rows), 8 receivers per group, persistent CTAs as above.  C never goes through registers or L1 on its
+// Same reduction with C in the 16-bit block format above, the row leaving as plain blocked fp32 (the update chain scales and splits
+// it, tc_node_update_kernel<.., AGG32>).  38 threads per receiver (4 columns each: 8 bytes of C16, one float4 of the blocked fp32
+// Qr / Qs rows), 4 receivers per group, persistent CTAs as above.  C never goes through registers or L1 on its
 // way in: the first A16_BATCH relations of a receiver are one contiguous run of C16 rows, which thread 0 of the receiver's slot
 // brings into shared memory with ONE bulk copy of the TMA engine (cp.async.bulk + mbarrier transaction count), a whole group ahead
 // of its use -- next to the sender ids (cp.async) and the row_ptr pairs (two groups ahead).  What a thread waits for per group is
@@ -947,7 +1008,8 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
 // which is zero-initialised), because on this kernel the instruction issue and the L1 data pipe, not DRAM, are the bound: r02a's
 // ncu capture of the first version (per-relation branches, generic loads, 64-register build with spills) showed 120 issued warp
 // instructions per relation, 39 % DRAM utilisation and the L1 data pipe at 73 %.
-// Where the time goes now (cloth-2k x 128, 0.249 ms per launch; r02i / r02j, each line one thing removed): no Qs gather 0.190, no
+// Where the time went with the split output still in this kernel (cloth-2k x 128, 0.249 ms per launch; r02i / r02j, each line one
+// thing removed): no Qs gather 0.190, no
 // arithmetic 0.171, no output 0.226, no bulk copies 0.232, no shared-memory reads of C 0.237 -- no single limiter; issue slots
 // (87 warp instructions per relation, of which 35 are the per-relation loop) and the gather latency share it.  Tried and not
 // adopted (profiles/r02_experiments_not_adopted.patch): issuing the gather of the NEXT task before computing the current one
@@ -983,15 +1045,12 @@ __device__ __forceinline__ int lds_s32(uint32_t addr) {
 
 __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_kernel(
     const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send, int rows, int N, uint32_t N_magic, int E_cap,
-    const uint8_t* __restrict__ C16, const float4* __restrict__ Qr, const float4* __restrict__ Qs, uint32_t* __restrict__ agg_split,
-    int32_t* __restrict__ agg_exp, float* __restrict__ agg_max) {
+    const uint8_t* __restrict__ C16, const float4* __restrict__ Qr, const float4* __restrict__ Qs, float4* __restrict__ agg) {
   extern __shared__ uint8_t a16_raw[];
-  __shared__ int smax[3][A16_NODES];
   __shared__ __align__(16) int32_t ids[2][A16_NODES][A16_BATCH];
   __shared__ __align__(8) uint64_t bar[2];
   uint8_t* cbuf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a16_raw) + 127) & ~(uintptr_t)127);   // [2][NODES][BATCH][C16_ROW]
   const int slot = threadIdx.x / A16_LANES, j = threadIdx.x - slot * A16_LANES;
-  if (threadIdx.x < 3 * A16_NODES) (&smax[0][0])[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < 2 * A16_NODES * A16_BATCH; i += A16_THREADS) (&ids[0][0][0])[i] = 0;
   for (int i = threadIdx.x; i < 2 * A16_CBUF / 16; i += A16_THREADS) reinterpret_cast<uint4*>(cbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0) {
@@ -1015,7 +1074,8 @@ __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_
   const uint32_t jrow = narrow ? (BLK_COLS - BLK_LAST) / 4 : BLK_W / 4;
   const uint32_t jtile = BLK_TILE / 4 - TILE * jrow;
   const uint32_t joff = (uint32_t)p * (TILE * BLK_W / 4) + (j & 3);
-  auto at = [=](const float4* m, uint32_t row) { return __ldg(m + (row * jrow + (row >> 7) * jtile + joff)); };
+  auto idx = [=](uint32_t row) { return row * jrow + (row >> 7) * jtile + joff; };
+  auto at = [=](const float4* m, uint32_t row) { return __ldg(m + idx(row)); };
   // row bounds of this thread's receiver in group v, as loaded (clamped to the capacity where they are consumed: the loads are
   // issued two groups ahead and nothing may wait for them before the end of the iteration)
   auto load_bounds = [&](int v, int& beg, int& end) {
@@ -1054,7 +1114,7 @@ __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_
   // A task is (receiver group v, batch k): relations [beg + k * BATCH, +BATCH) of every receiver of the group.  Receivers with more
   // than BATCH relations (granular: up to topk + tools = 25) take further batches through the same pipeline; `more` (CTA-uniform,
   // from the barrier that ends the previous iteration) says whether the current group has relations left after the current batch.
-  int v = blockIdx.x, k = 0, gcnt = 0;
+  int v = blockIdx.x, k = 0;
   int beg, end, beg1, end1, raw2b = 0, raw2e = 0;
   uint32_t parity = 0;   // bit b: phase to wait for on bar[b]
   load_bounds(v, beg, end);
@@ -1098,40 +1158,20 @@ __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_
       for (int u = 0; u < A16_BATCH; ++u)
         accumulate(lds64u(ca + u * C16_ROW), lds_s8(ea + u * C16_ROW), qr, q[u], u < n0 ? 1.f : 0.f, acc);
     }
-    int* mxs = smax[gcnt % 3];
-    if (!more) {
-      // row maximum (agg >= 0, so the int view of the floats orders like the floats): one warp-level reduction per receiver
-      // segment of the warp, then one shared-memory atomic per segment instead of one per thread
-      const int mine = __float_as_int(fmaxf(fmaxf(acc.x, acc.y), fmaxf(acc.z, acc.w)));
-      const unsigned peers = __match_any_sync(0xffffffffu, slot);
-      const int seg = __reduce_max_sync(peers, mine);
-      if (valid && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicMax(&mxs[slot], seg);
-    }
+    // the finished row leaves as plain fp32 (blocked like Qr / Qs): the update chain takes the row maximum, scales and splits it for
+    // its tensor-memory A (tc_node_update_kernel<.., AGG32>).  This kernel is bound by instruction issue and by the length of a
+    // task's dependent chain: the row maximum (match / redux / shared-memory atomic, read back after the barrier), the power-of-two
+    // scale and the fp16 hi / lo conversion were a fifth of its instructions -- 0.249 -> 0.213 ms on cloth-2k x 128 (r02U), 4.9 TB/s.
+    // Leaving just two partial maxima per row behind (one REDUX per warp segment, 12 instructions) already costs 0.016 ms (r02V).
+    if (!more && valid) agg[idx((uint32_t)r)] = acc;
     asm volatile("cp.async.wait_group 0;" ::: "memory");   // the next task's sender ids have landed ...
-    // ... and are visible; row maxima complete; everyone is done with cbuf[buf]; does the next task's group go on after it?
+    // ... and are visible; everyone is done with cbuf[buf]; does the next task's group go on after it?
     const int more_next = __syncthreads_or(nend - nbeg > (nk + 1) * A16_BATCH);
     if (!more) {
-      if (threadIdx.x < A16_NODES) smax[(gcnt + 2) % 3][threadIdx.x] = 0;
-      if (valid) {
-        const float mx = __int_as_float(mxs[slot]);
-        const int e = scale_exp(mx);
-        const float sc = exp2i(e);
-        const float2 s0 = __fmul2_rn(make_float2(acc.x, acc.y), make_float2(sc, sc)), s1f = __fmul2_rn(make_float2(acc.z, acc.w), make_float2(sc, sc));
-        const __half2 h0 = __float22half2_rn(s0), h1 = __float22half2_rn(s1f);
-        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-        const __half2 l0 = __float22half2_rn(make_float2(s0.x - f0.x, s0.y - f0.y)), l1 = __float22half2_rn(make_float2(s1f.x - f1.x, s1f.y - f1.y));
-        // the 16 words of (row, piece = 16 columns): 8 packed hi pairs then 8 packed lo pairs (narrow last piece: 4 then 4)
-        uint32_t* piece = agg_split + blk_off(r, 16 * p);
-        const int lo_at = narrow ? (BLK_COLS - BLK_LAST) / 2 : BLK_W / 2;
-        *reinterpret_cast<uint2*>(piece + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-        *reinterpret_cast<uint2*>(piece + lo_at + 2 * (j & 3)) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
-        if (j == 0) { agg_exp[r] = e; agg_max[r] = mx; }
-      }
       acc = make_float4(0.f, 0.f, 0.f, 0.f);
       asm volatile("" : "+r"(raw2b), "+r"(raw2e));         // the row_ptr loads issued above are first waited for HERE
       beg = beg1; end = end1; beg1 = min(raw2b, E_cap); end1 = min(raw2e, E_cap);
       v += G;
-      ++gcnt;
     }
     k = nk;
     more = more_next;
@@ -1211,6 +1251,8 @@ static int tc_ensure_attrs() {
   AGX_CUDA_OK(cudaFuncSetAttribute((tc_node_update_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute((tc_node_update_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   AGX_CUDA_OK(cudaFuncSetAttribute(tc_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute((tc_node_update_kernel<false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  AGX_CUDA_OK(cudaFuncSetAttribute((tc_node_update_kernel<true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   return AGX_OK;
 }
 
@@ -1285,6 +1327,7 @@ int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, bo
   const float* Qs = first ? w.Qs0 : w.Qs;
   if (mixed) {
     if (int rc = tc_ensure_attrs()) return rc;
+    AGX_REQUIRE(w.agg_f32, AGX_ERR_ARG, "edge_aggregate: the C16 aggregate writes plain fp32 rows (TcFwdBuffers::agg_f32)");
     // the kernel indexes the blocked fp32 rows with 32-bit float offsets
     AGX_REQUIRE(blk_rows(rows) * (BLK_COLS / 4) < (1ll << 32) && g->E_cap < (1ll << 31), AGX_ERR_ARG,
                 "edge_aggregate: %lld rows / %lld relations exceed the 32-bit feature index", (long long)rows, (long long)g->E_cap);
@@ -1294,7 +1337,7 @@ int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, bo
           g->row_ptr, g->send, (int)rows, g->N, g->N == 1 ? 0xffffffffu : (uint32_t)((1ull << 32) / (uint64_t)g->N), (int)g->E_cap,
           reinterpret_cast<const uint8_t*>(w.C),
           reinterpret_cast<const float4*>(Qr),
-          reinterpret_cast<const float4*>(Qs), reinterpret_cast<uint32_t*>(w.agg), w.agg_exp, w.agg_max); }
+          reinterpret_cast<const float4*>(Qs), reinterpret_cast<float4*>(w.agg)); }
     AGX_LAUNCH_CHECK();
     return AGX_OK;
   }
@@ -1326,10 +1369,12 @@ int tc_node_update(const AgxGraphIn* g, const float* wts, const PackedLayout& PL
   if (last) {
     ProfScope ps(AGX_KIND_NODE_HEAD, st);
     if (w.save) launch_pdl(PDL_BIG, tc_node_update_kernel<true, true>, grid, THREADS, SMEM_BYTES, st, a);
+    else if (w.agg_f32) launch_pdl(PDL_BIG, (tc_node_update_kernel<true, false, true>), grid, THREADS, SMEM_BYTES, st, a);
     else launch_pdl(PDL_BIG, tc_node_update_kernel<true>, grid, THREADS, SMEM_BYTES, st, a);
   } else {
     ProfScope ps(AGX_KIND_NODE_UPDATE, st);
     if (w.save) launch_pdl(PDL_BIG, tc_node_update_kernel<false, true>, grid, THREADS, SMEM_BYTES, st, a);
+    else if (w.agg_f32) launch_pdl(PDL_BIG, (tc_node_update_kernel<false, false, true>), grid, THREADS, SMEM_BYTES, st, a);
     else launch_pdl(PDL_BIG, tc_node_update_kernel<false>, grid, THREADS, SMEM_BYTES, st, a);
   }
   AGX_LAUNCH_CHECK();

@@ -18,7 +18,8 @@ struct TcFwdBuffers {
   float* P0; float* Qr0; float* Qs0; float* rowmaxP0;   // the particle encoder's copies (read-only for the propagation steps)
   float* S0;                                            // A_n + P0
   const TcTrainSave* save = nullptr;                    // non-null: the SAVE instantiations of the chains run (fp32 C only)
-};
+  bool agg_f32 = false;                                 // agg holds plain blocked fp32 rows (written by the C16 aggregate, AGX_PREC_TC_MIXED)
+};                                                      // instead of the scaled fp16 hi / lo split + agg_exp / agg_max
 
 int tc_edge_aggregate(const AgxGraphIn* g, const TcFwdBuffers& w, bool mixed, bool first, cudaStream_t st);
 int tc_nfeat(const AgxGraphIn* g, const TcFwdBuffers& w, cudaStream_t st);

@@ -149,8 +149,8 @@ def forward_variant(p, pstep, state, attrs, row_ptr, send, p_instance, action, p
     a_node = store(qlinear(penc, Wp[:, :F], bp, m.get("pp_enc", "3")), cfg.get("A", "f32"))
     eff = store(penc, "f32")
     for _ in range(pstep):
-        q_r = store(qlinear(eff, Wr[:, F:2 * F], zero, m.get("rp_recv", "3")), cfg.get("Q", "f32"))
-        q_s = store(qlinear(eff, Wr[:, 2 * F:], zero, m.get("rp_send", "3")), cfg.get("Q", "f32"))
+        q_r = store(qlinear(eff, Wr[:, F:2 * F], zero, m.get("rp_recv", "3")), cfg.get("Qr", cfg.get("Q", "f32")))
+        q_s = store(qlinear(eff, Wr[:, 2 * F:], zero, m.get("rp_send", "3")), cfg.get("Qs", cfg.get("Q", "f32")))
         e_out = relu(c_edge + q_r[recv] + q_s[snd])
         agg = store(torch.zeros_like(eff).index_add_(0, recv, e_out), cfg.get("agg", "f32"))
         eff = store(relu(a_node + qlinear(agg, Wp[:, F:], zero, m.get("pp_agg", "3")) + eff), "f32")
@@ -213,6 +213,10 @@ def variants():
     v["edge-chain 2b + C i16 + agg i16"] = dict(mma={k: "2b" for k in EDGE + ("renc0",)}, C="i16", agg="i16")
     v["edge-chain 2b + C i16 + A,agg i16"] = dict(mma={k: "2b" for k in EDGE + ("renc0",)}, C="i16", A="i16", agg="i16")
     v["edge-chain 2b + C i16 + A,agg,Q i16"] = dict(mma={k: "2b" for k in EDGE + ("renc0",)}, C="i16", A="i16", agg="i16", Q="i16")
+    v["shipped (edge-chain 2b + C i16) + Qs i16"] = dict(mma={k: "2b" for k in EDGE + ("renc0",)}, C="i16", Qs="i16")
+    v["shipped (edge-chain 2b + C i16) + Qs,Qr i16"] = dict(mma={k: "2b" for k in EDGE + ("renc0",)}, C="i16", Q="i16")
+    v["only Qs i16"] = dict(mma={}, Qs="i16")
+    v["only Qr i16"] = dict(mma={}, Qr="i16")
     v["only A i16"] = dict(mma={}, A="i16")
     v["only agg i16"] = dict(mma={}, agg="i16")
     v["all 2a + C,Q i16"] = dict(mma={k: "2a" for k in EDGE + NODE_ENC + UPD + ("renc0", "penc0")}, C="i16", Q="i16")
