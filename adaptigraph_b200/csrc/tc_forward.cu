@@ -1018,12 +1018,18 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
 // node_encoder / node_update.
 #ifndef AGX_A16_NODES
 #define AGX_A16_NODES 4     // receivers per CTA group
-#define AGX_A16_CTAS 4      // resident CTAs per SM
+#define AGX_A16_CTAS 5      // resident CTAs per SM
 #endif
 constexpr int A16_NODES = AGX_A16_NODES;
 constexpr int A16_LANES = BLK_COLS / 4;                // 38
 constexpr int A16_THREADS = A16_NODES * A16_LANES;     // 304
-constexpr int A16_BATCH = 8;
+// Relations per receiver per task.  All A16_BATCH slots are always evaluated (branch-free), so a slot past the receiver's degree
+// still costs its arithmetic and a (stale) sender-row gather from L2: cloth's receivers have exactly topk + tools = 7 relations,
+// and with 7 slots instead of 8 nothing is wasted on them (0.215 -> 0.209 ms; granular-1k x 64: 0.098 -> 0.095; r02X / r02Y).
+#ifndef AGX_A16_BATCH
+#define AGX_A16_BATCH 7
+#endif
+constexpr int A16_BATCH = AGX_A16_BATCH;
 constexpr int A16_CBUF = A16_NODES * A16_BATCH * C16_ROW;   // bytes per stage
 constexpr size_t A16_SMEM = 2 * (size_t)A16_CBUF + 128;
 
@@ -1047,11 +1053,12 @@ __global__ void __launch_bounds__(A16_THREADS, AGX_A16_CTAS) edge_aggregate_c16_
     const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ send, int rows, int N, uint32_t N_magic, int E_cap,
     const uint8_t* __restrict__ C16, const float4* __restrict__ Qr, const float4* __restrict__ Qs, float4* __restrict__ agg) {
   extern __shared__ uint8_t a16_raw[];
-  __shared__ __align__(16) int32_t ids[2][A16_NODES][A16_BATCH];
+  constexpr int IDS = (A16_BATCH + 3) / 4 * 4;   // padded: a slot's ids are read with 128-bit loads
+  __shared__ __align__(16) int32_t ids[2][A16_NODES][IDS];
   __shared__ __align__(8) uint64_t bar[2];
   uint8_t* cbuf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a16_raw) + 127) & ~(uintptr_t)127);   // [2][NODES][BATCH][C16_ROW]
   const int slot = threadIdx.x / A16_LANES, j = threadIdx.x - slot * A16_LANES;
-  for (int i = threadIdx.x; i < 2 * A16_NODES * A16_BATCH; i += A16_THREADS) (&ids[0][0][0])[i] = 0;
+  for (int i = threadIdx.x; i < 2 * A16_NODES * IDS; i += A16_THREADS) (&ids[0][0][0])[i] = 0;
   for (int i = threadIdx.x; i < 2 * A16_CBUF / 16; i += A16_THREADS) reinterpret_cast<uint4*>(cbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], A16_NODES);
