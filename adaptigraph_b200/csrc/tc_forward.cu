@@ -263,6 +263,10 @@ __device__ __forceinline__ int c16_store16(uint8_t* base, int64_t row, int col0,
     w[i] = __byte_perm(a, b, 0x5410);       // {a.lo16, b.lo16}
   }
   uint8_t* p = base + row * C16_ROW + 2 * col0;
+#ifdef AGX_ABLATE_C16_STORE   // profiling aid: the relation term is computed but not written
+  asm volatile("" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+  return e;
+#endif
   if (col0 < BLK_LAST) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
                  "r"(w[5]), "r"(w[6]), "r"(w[7])

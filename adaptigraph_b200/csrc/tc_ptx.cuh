@@ -81,6 +81,12 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 // 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets lane (base_lane + i).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+#ifdef AGX_ABLATE_TMEM_LD   // profiling aid (tools/tc_ablate.py): no tensor-memory reads, the epilogues work on zeros
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = 0;
+  asm volatile("" ::"r"(taddr) : "memory");
+  return;
+#endif
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -99,6 +105,10 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4])
                : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+#ifdef AGX_ABLATE_TMEM_ST   // profiling aid: no tensor-memory writes by the epilogues
+  asm volatile("" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+  return;
+#endif
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
@@ -124,6 +134,10 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
 __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+#ifdef AGX_ABLATE_MMA       // profiling aid: no MMAs issued (the commits still arrive)
+  asm volatile("" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  return;
+#endif
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
