@@ -16,13 +16,13 @@ print("%-10s value %.1fM e2e %.1fM frac %.3f rmse %.2e | agg %.4f enc %.4f upd %
 PY
 }
 for rep in 1 2; do
-  for v in prev new b7c5; do
+  for v in prev new; do
     case $v in prev) L=$PWD/variants/libagx_prev.so;; new) L=$PWD/adaptigraph_b200/libadaptigraph_b200.so;; b7c5) L=$PWD/variants/libagx_b7c5.so;; esac
     X=""; [ $rep = 2 ] && X="--no-cpu-baseline"
     AGX_LIB=$L timeout 300 python bench.py --steps 5 --warmup 3 $X > $OUT/${T}_bench_${v}_$rep.json 2> $OUT/${T}_bench_${v}_$rep.err; summ $OUT/${T}_bench_${v}_$rep.json $v
   done
 done
-for v in prev new b7c5; do
+for v in prev new; do
   case $v in prev) L=$PWD/variants/libagx_prev.so;; new) L=$PWD/adaptigraph_b200/libadaptigraph_b200.so;; b7c5) L=$PWD/variants/libagx_b7c5.so;; esac
   AGX_LIB=$L timeout 300 python bench.py --workload cfg3 --steps 5 --warmup 3 > $OUT/${T}_cfg3_${v}.json 2> $OUT/${T}_cfg3_${v}.err; summ $OUT/${T}_cfg3_${v}.json cfg3-$v
 done
