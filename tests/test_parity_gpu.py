@@ -168,6 +168,33 @@ def test_forward_matches_oracle_on_seeded_inputs(agx, material, n_p, B, pstep, p
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
+def test_forward_with_long_rows(agx, precision):
+    """Receivers with up to topk + tools = 48 relations (the aggregate takes a row in batches of 7 relations: seven batches, the
+    last one ragged) next to tool receivers with none: forward against the dense oracle on the same relation lists."""
+    from adaptigraph_b200 import synthetic as syn
+    from oracle import dynamics_oracle as orc
+    w = syn.make_workload("cloth", 150, 3, seed=91, n_s=16)
+    w.topk, w.adj_thresh = 32, 5.0
+    p = H.golden_weights()
+    Rr, Rs = orc.edges_dense_batch(w.state[:, -1], w.adj_thresh, w.state_mask, w.eef_mask, w.topk, w.connect_tools_all)
+    deg = Rr.sum(1).max().item()
+    assert deg >= 40, deg
+    ref_pos, ref_motion = orc.forward_dense(p, 2, w.state, w.attrs, Rr, Rs, w.p_instance, w.action, w.physics_param)
+    m = _model(agx, "cloth", 2, precision)
+    wd = w.to("cuda")
+    el = agx.build_edges(wd.state[:, -1], w.adj_thresh, wd.state_mask, wd.eef_mask, w.topk, w.connect_tools_all).check()
+    r_ref, s_ref = H.lists_from_onehots(Rr, Rs)
+    r, s = _edge_lists(el, Rr.shape[1])
+    assert np.array_equal(r, r_ref.numpy()) and np.array_equal(s, s_ref.numpy())
+    with torch.no_grad():
+        pos, motion = m(**wd.graph_dict(), edges=el)
+    # long rows sum ~7 times more terms than the shipped configurations: the tolerance scales with the magnitude of the motion
+    tol = FWD_TOLS[precision] * max(1.0, float(ref_motion.abs().max()))
+    assert (pos.cpu() - ref_pos).abs().max() <= tol
+    assert (motion.cpu() - ref_motion).abs().max() <= tol
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
 def test_graph_without_relations_and_single_particle_tiles(agx, precision):
     """Empty relation set (radius below every pair distance except self excluded by topk... here: all
     particles invalid but one) and B*N smaller than one tile."""
