@@ -1,6 +1,6 @@
 #!/bin/bash
-# Fused degrees + scan + fill kernel (scan_fill_rows_kernel) against the two-kernel path (AGX_GRAPH_FUSED_FILL=0): full GPU suite,
-# then the bench at 128 and at 16 graphs, same library, same box.  Usage: bash tools/gpu_fill_ab.sh TAG
+# Fused degrees + scan + fill kernel (profiles/r02L_experiment_fused_scan_fill.patch applied: scan_fill_rows_kernel) against the
+# two-kernel path (AGX_GRAPH_FUSED_FILL=0): full GPU suite, then the bench at 128 and at 16 graphs.  Usage: bash tools/gpu_fill_ab.sh TAG
 T=${1:-fill}; OUT=gpurun_out; mkdir -p $OUT
 timeout 900 python -m pytest tests -q -m gpu --tb=short -p no:cacheprovider -x > $OUT/${T}_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 $OUT/${T}_pytest.log | cut -c1-300
 summ() { python - "$1" "$2" <<'PY'

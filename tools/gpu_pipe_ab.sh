@@ -1,6 +1,6 @@
 #!/bin/bash
-# Pipelined relation encoder (tc_edge_encoder_pipe_kernel) against the unpipelined chain (AGX_EDGE_PIPE=0), same library, same box.
-# Usage: bash tools/gpu_pipe_ab.sh TAG
+# Pipelined relation encoder (profiles/r02P_experiment_pipelined_edge_encoder.patch applied: tc_edge_encoder_pipe_kernel) against the
+# unpipelined chain (AGX_EDGE_PIPE=0), same library, same box.  Usage: bash tools/gpu_pipe_ab.sh TAG
 T=${1:-pipe}; OUT=gpurun_out; mkdir -p $OUT
 timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_baseline_sizes_gpu.py -q -m gpu --tb=short -p no:cacheprovider -x > $OUT/${T}_pytest.log 2>&1; echo "pytest rc=$?"; tail -6 $OUT/${T}_pytest.log | cut -c1-400
 summ() { python - "$1" "$2" <<'PY'

@@ -1,6 +1,6 @@
 #!/bin/bash
-# Pipelined relation encoder (tc_edge_encoder_pipe_kernel) against the unpipelined chain (AGX_EDGE_S3=0), same library, same box.
-# Usage: bash tools/gpu_pipe_ab.sh TAG
+# Three-slot relation encoder (profiles/r02S3_experiment_three_slot_edge_encoder.patch applied: tc_edge_encoder_s3_kernel) against the
+# two-slot chain (AGX_EDGE_S3=0), same library, same box.  Usage: bash tools/gpu_s3_ab.sh TAG
 T=${1:-pipe}; OUT=gpurun_out; mkdir -p $OUT
 timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_baseline_sizes_gpu.py -q -m gpu --tb=short -p no:cacheprovider -x > $OUT/${T}_pytest.log 2>&1; echo "pytest rc=$?"; tail -6 $OUT/${T}_pytest.log | cut -c1-400
 summ() { python - "$1" "$2" <<'PY'
