@@ -1029,7 +1029,8 @@ constexpr int A16_LANES = BLK_COLS / 4;                // 38
 constexpr int A16_THREADS = A16_NODES * A16_LANES;     // 304
 // Relations per receiver per task.  All A16_BATCH slots are always evaluated (branch-free), so a slot past the receiver's degree
 // still costs its arithmetic and a (stale) sender-row gather from L2: cloth's receivers have exactly topk + tools = 7 relations,
-// and with 7 slots instead of 8 nothing is wasted on them (0.215 -> 0.209 ms; granular-1k x 64: 0.098 -> 0.095; r02X / r02Y).
+// and with 7 slots instead of 8 nothing is wasted on them (0.213 -> 0.205 ms; granular-1k x 64: 0.098 -> 0.094; r02Y).  With 7
+// slots the kernel fits 71 registers and 5 CTAs per SM pay (-> 0.194 ms; at 8 slots the fifth CTA lost).
 #ifndef AGX_A16_BATCH
 #define AGX_A16_BATCH 7
 #endif
