@@ -1001,7 +1001,7 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
 // ------------------------------------------------------------------------------------ edge aggregate on C16 (AGX_PREC_TC_MIXED)
 // Same reduction with C in the 16-bit block format above, the row leaving as plain blocked fp32 (the update chain scales and splits
 // it, tc_node_update_kernel<.., AGG32>).  38 threads per receiver (4 columns each: 8 bytes of C16, one float4 of the blocked fp32
-// Qr / Qs rows), 4 receivers per group, persistent CTAs as above.  C never goes through registers or L1 on its
+// Qr / Qs rows), 5 receivers per group, persistent CTAs as above.  C never goes through registers or L1 on its
 // way in: the first A16_BATCH relations of a receiver are one contiguous run of C16 rows, which thread 0 of the receiver's slot
 // brings into shared memory with ONE bulk copy of the TMA engine (cp.async.bulk + mbarrier transaction count), a whole group ahead
 // of its use -- next to the sender ids (cp.async) and the row_ptr pairs (two groups ahead).  What a thread waits for per group is
@@ -1021,8 +1021,8 @@ __global__ void __launch_bounds__(AGG_THREADS, AGG_CTAS_PER_SM) edge_aggregate_s
 // 2 x 8 0.26, 4 x 3 0.26 against 4 x 4 0.250; Qr / Qs rows row-major instead of blocked: -0.014 ms here, +0.033 ms in each of
 // node_encoder / node_update.
 #ifndef AGX_A16_NODES
-#define AGX_A16_NODES 4     // receivers per CTA group
-#define AGX_A16_CTAS 5      // resident CTAs per SM
+#define AGX_A16_NODES 5     // receivers per CTA group
+#define AGX_A16_CTAS 4      // resident CTAs per SM
 #endif
 constexpr int A16_NODES = AGX_A16_NODES;
 constexpr int A16_LANES = BLK_COLS / 4;                // 38
@@ -1030,7 +1030,8 @@ constexpr int A16_THREADS = A16_NODES * A16_LANES;     // 304
 // Relations per receiver per task.  All A16_BATCH slots are always evaluated (branch-free), so a slot past the receiver's degree
 // still costs its arithmetic and a (stale) sender-row gather from L2: cloth's receivers have exactly topk + tools = 7 relations,
 // and with 7 slots instead of 8 nothing is wasted on them (0.213 -> 0.205 ms; granular-1k x 64: 0.098 -> 0.094; r02Y).  With 7
-// slots the kernel fits 71 registers and 5 CTAs per SM pay (-> 0.194 ms; at 8 slots the fifth CTA lost).
+// slots the kernel fits 71 registers and 20 receivers per SM pay -- 5 CTAs x 4 receivers 0.194 ms, 4 CTAs x 5 receivers (shipped)
+// the same on cloth and 2 % more rollout throughput on granular over the whole configs[4] sweep (r02K); at 8 slots 4 x 4 was best.
 #ifndef AGX_A16_BATCH
 #define AGX_A16_BATCH 7
 #endif
